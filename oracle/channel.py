@@ -1,0 +1,89 @@
+"""Power-normalised noisy channel — eager PyTorch restatement of SPEC v0 rows a3/a4.
+
+Reference citation: no upstream code exists (/root/reference/README.md:1-2 only);
+this follows SURVEY.md §8 rows a3 (power_normalize) and a4 (awgn, rayleigh).
+All functions are differentiable torch code so autograd provides the oracle gradients.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import philox
+
+
+def power_normalize(z: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """z[B, 2, k] -> unit mean power per (sample, modality): z * rsqrt(mean(z^2) + eps)."""
+    p = z.pow(2).mean(dim=-1, keepdim=True)
+    return z * torch.rsqrt(p + eps)
+
+
+def snr_to_sigma(snr_db, batch: int, device, dtype) -> torch.Tensor:
+    """sigma[B,1,1] with sigma^2 = 10^(-snr_db/10) per real dimension."""
+    s = torch.as_tensor(snr_db, dtype=torch.float32, device=device)
+    if s.dim() == 0:
+        s = s.expand(batch)
+    sigma = torch.pow(torch.tensor(10.0, dtype=torch.float32, device=device), -s / 20.0)
+    return sigma.to(dtype).view(batch, 1, 1)
+
+
+def make_noise(seed: int, batch: int, k: int, sample_offset: int = 0) -> torch.Tensor:
+    return torch.from_numpy(philox.noise_normal(seed, batch, k, sample_offset))
+
+
+def make_fading(seed: int, batch: int, sample_offset: int = 0) -> torch.Tensor:
+    return torch.from_numpy(philox.fading_coeff(seed, batch, sample_offset))
+
+
+def awgn(zn: torch.Tensor, sigma: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """y = zn + sigma * n."""
+    return zn + sigma * noise.to(zn.dtype)
+
+
+def rayleigh(zn: torch.Tensor, sigma: torch.Tensor, noise: torch.Tensor,
+             h: torch.Tensor) -> torch.Tensor:
+    """Block Rayleigh fading with MMSE equalisation.
+    reals are paired (even, odd) -> complex s; r = h s + sigma n; y = conj(h) r / (|h|^2 + sigma^2).
+    h: [B, 2, 2] = (re, im) per (sample, modality)."""
+    B, M, k = zn.shape
+    s = zn.reshape(B, M, k // 2, 2)
+    n = noise.to(zn.dtype).reshape(B, M, k // 2, 2)
+    hr = h[..., 0].to(zn.dtype).view(B, M, 1)
+    hi = h[..., 1].to(zn.dtype).view(B, M, 1)
+    sr, si = s[..., 0], s[..., 1]
+    sg = sigma.view(B, 1, 1)
+    rr = hr * sr - hi * si + sg * n[..., 0]
+    ri = hr * si + hi * sr + sg * n[..., 1]
+    den = hr * hr + hi * hi + sg * sg
+    yr = (hr * rr + hi * ri) / den
+    yi = (hr * ri - hi * rr) / den
+    return torch.stack([yr, yi], dim=-1).reshape(B, M, k)
+
+
+def channel_forward(z: torch.Tensor, snr_db, kind: str, *, seed=None, noise=None, fading=None,
+                    sample_offset: int = 0, eps: float = 1e-12):
+    """z[B,2,k] -> (y[B,2,k], zn).  kind in {"awgn", "rayleigh", "none"}."""
+    B, M, k = z.shape
+    zn = power_normalize(z, eps)
+    if kind == "none":
+        return zn, zn
+    sigma = snr_to_sigma(snr_db, B, z.device, z.dtype)
+    if noise is None:
+        if seed is None:
+            raise ValueError("channel needs seed= or noise=")
+        noise = make_noise(seed, B, k, sample_offset).to(z.device)
+    if kind == "awgn":
+        return awgn(zn, sigma, noise), zn
+    if kind == "rayleigh":
+        if fading is None:
+            if seed is None:
+                raise ValueError("rayleigh channel needs seed= or fading=")
+            fading = make_fading(seed, B, sample_offset).to(z.device)
+        return rayleigh(zn, sigma, noise, fading), zn
+    raise ValueError(f"unknown channel kind {kind!r}")
+
+
+def empirical_snr_db(zn: torch.Tensor, y: torch.Tensor) -> float:
+    """10 log10(P_signal / P_noise) for an AWGN output (test helper)."""
+    n = (y - zn).double()
+    return float(10.0 * np.log10(zn.double().pow(2).mean().item() / n.pow(2).mean().item()))
