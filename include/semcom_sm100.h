@@ -1,0 +1,198 @@
+/* semcom_sm100.h — C ABI of libsemcom_sm100.so (hand-written sm_100a kernels).
+ *
+ * Drop-in boundary of the SemCom-PPO hot path.  The upstream repository
+ * (/root/reference/README.md:1-2) contains no code and therefore no plugin / FFI interface
+ * to replace; each entry point below cites the SPEC v0 row it implements
+ * instead, and INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless noted;
+ *   - the caller owns every buffer; the library never allocates, frees or retains pointers;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no internal
+ *     synchronisation, no default-stream use -> CUDA-graph capturable;
+ *   - return 0 (SC_OK) or a negative SC_E_* code; sc_last_error() gives the thread-local
+ *     message; no exceptions, no exit();
+ *   - tensors are contiguous row-major unless a leading dimension is passed, 16-byte aligned;
+ *   - a device that is not compute capability 10.x is refused with SC_E_ARCH (no fallback).
+ */
+#ifndef SEMCOM_SM100_H_
+#define SEMCOM_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_OK 0
+#define SC_E_SHAPE (-1)
+#define SC_E_ALIGN (-2)
+#define SC_E_ARCH (-3)
+#define SC_E_LAUNCH (-4)
+#define SC_E_DRIVER (-5)
+
+#define SC_ABI_VERSION 1
+
+/* channel kinds (SPEC v0 a4) */
+#define SC_CH_NONE 0
+#define SC_CH_AWGN 1
+#define SC_CH_RAYLEIGH 2
+
+/* activation ids for the GEMM epilogue */
+#define SC_ACT_NONE 0
+#define SC_ACT_GELU 1 /* tanh-form GELU */
+#define SC_ACT_TANH 2
+
+int sc_version(void);
+const char* sc_last_error(void);
+/* SC_OK when the current device is sm_100; SC_E_ARCH otherwise. */
+int sc_device_ok(void);
+/* number of kernels launched by this library since load (all threads); bench.py's gpu_launches */
+int64_t sc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores, operands by TMA (SPEC v0 a1/a2/a5 GEMMs:
+ * patch-embed, QKV, out-proj, MLP, symbol/in/recon projections, and their dgrad/wgrad).
+ *
+ *   acc[m,n] = sum_k A(m,k) * B(n,k)                 bf16 x bf16 -> fp32 (TMEM accumulators)
+ *   a_mn = 0: A is stored [M,K] row-major (lda);  a_mn = 1: A is stored [K,M] row-major (lda)
+ *   b_mn = 0: B is stored [N,K] row-major (ldb);  b_mn = 1: B is stored [K,N] row-major (ldb)
+ *   so  fwd   y = x W^T      : (a_mn,b_mn) = (0,0)
+ *       dgrad dx = dy W      : (0,1)   (W itself, no transposed copy)
+ *       wgrad dW = dy^T x    : (1,1)   (reduction over the huge M, use ksplit > 1 + atomic)
+ *
+ * epilogue, applied per element in this order (null pointer / zero = skipped):
+ *   v = alpha * acc
+ *   v += bias[n]                                    fp32 [N]
+ *   v += rowadd[(m % rowadd_period) * N + n]        fp32 [period, N]     (pos-embed)
+ *   v += rowgrp[(m / rowgrp_size) * N + n] * rowgrp_scale   fp32          (mean-pool bwd)
+ *   aux_out[m*ldo + n] = bf16(v)                    pre-activation copy   (GELU fwd)
+ *   v = act(v)
+ *   v *= gelu'(aux_in[m*ldo + n])                   bf16                  (GELU bwd)
+ *   v += resid[m*ldo + n]                           bf16                  (residual)
+ *   out_bf16[m*ldo + n] = bf16(v)  and/or  out_f32[m*ldo + n] (= or +=) v
+ * ldo is the leading dimension of out_bf16 / out_f32 / aux_out / aux_in / resid.
+ * atomic != 0 accumulates out_f32 with red.global.add (required when ksplit > 1).
+ * Requirements: lda, ldb multiples of 8; A, B 16-byte aligned; K > 0.
+ * ------------------------------------------------------------------------------------- */
+typedef struct sc_gemm_epilogue {
+  const float* bias;
+  const float* rowadd;
+  int64_t rowadd_period;
+  const float* rowgrp;
+  int64_t rowgrp_size;
+  float rowgrp_scale;
+  float alpha;
+  const void* resid;  /* bf16 */
+  const void* aux_in; /* bf16 */
+  void* aux_out;      /* bf16 */
+  void* out_bf16;
+  float* out_f32;
+  int64_t ldo;
+  int32_t act;
+  int32_t atomic;
+} sc_gemm_epilogue;
+
+int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn,
+                 int64_t lda, int64_t ldb, const sc_gemm_epilogue* epi, int ksplit, void* stream);
+
+/* test hook: override UMMA descriptor fields (0 = library default). Not for product use. */
+int sc_debug_set(const char* key, int64_t value);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused multi-head self-attention for S in {64,128}, d_head = 64 (SPEC v0 a1/a2/a5 blocks).
+ * qkv: bf16 [B*S, 3*H*64], columns [q(h,d) | k(h,d) | v(h,d)];  out: bf16 [B*S, H*64];
+ * lse: fp32 [B*S, H] (log2-domain log-sum-exp of the scaled scores, saved for backward).
+ * Whole S x S score tile lives in TMEM; QK^T and PV on tcgen05.
+ * ------------------------------------------------------------------------------------- */
+int sc_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int S, int H, void* stream);
+int sc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                int64_t B, int S, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Memory-bound fused kernels.
+ * ------------------------------------------------------------------------------------- */
+/* a1/a2: img fp32 [B,C,H,W] -> patch tokens bf16 [B*(H/P)*(W/P), C*P*P], feature order (c,py,px) */
+int sc_patchify_bf16(const float* img, void* out, int64_t B, int C, int H, int W, int P,
+                     void* stream);
+
+/* LayerNorm over the last dim D (D % 256 == 0, D <= 1024).  io_f32: 0 = bf16 x/y, 1 = fp32 x/y.
+ * mean/rstd: fp32 [M] saved for backward (may be null in fwd for inference). */
+int sc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                     float* rstd, int64_t M, int D, float eps, int io_f32, void* stream);
+/* dx = dres + LN'(dy); dgamma/dbeta (+=, fp32 [D]); colsum (+=, fp32 [D], optional) gets the
+ * column sums of the OUTPUT dx (the bias gradient of the linear layer that produced x). */
+int sc_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                     const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
+                     float* colsum, int64_t M, int D, int io_f32, void* stream);
+
+/* out[n] += sum_m x[m*ld + n]   (bias gradients); x bf16 */
+int sc_colsum_bf16(const void* x, float* out, int64_t M, int N, int64_t ld, void* stream);
+
+/* a3+a4: power normalisation + channel, fused, in-kernel Philox4x32-10 + Box-Muller.
+ * z (fp32) is addressed as z[b*z_sb + m*z_sm + j], y likewise with (y_sb, y_sm); b<B, m<2, j<k.
+ * scale: fp32 [B,2] = rsqrt(mean z^2 + eps), saved for backward.
+ * snr_db: device fp32 [B] or null (then snr_db_scalar is used).
+ * noise / fading: optional explicit tensors (fp32 [B,2,k] / [B,2,2]) replacing the Philox draw.
+ * y_f32 / y_bf16: either may be null.  Counter layout: see oracle/philox.py. */
+int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f32, void* y_bf16,
+                         int64_t y_sb, int64_t y_sm, float* scale, int64_t B, int k, int kind,
+                         const float* snr_db, float snr_db_scalar, uint64_t seed,
+                         int64_t sample_offset, const float* noise, const float* fading,
+                         float eps, void* stream);
+/* dz = scale * (g - zn * mean(g * zn)),  g = dy (AWGN/none) or |h|^2/(|h|^2+sigma^2) dy (Rayleigh) */
+int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const float* z, int64_t z_sb,
+                         int64_t z_sm, const float* scale, float* dz_f32, void* dz_bf16, int64_t B,
+                         int k, int kind, const float* snr_db, float snr_db_scalar, uint64_t seed,
+                         int64_t sample_offset, const float* fading, void* stream);
+/* raw Philox words for parity tests: out u32 [n_quads,4], counters quad_offset.. */
+int sc_philox_words(uint32_t* out, int64_t n_quads, uint32_t stream_id, uint64_t seed,
+                    int64_t quad_offset, void* stream);
+
+/* a5: mean over S tokens: x bf16 [B,S,D] -> out_bf16 [B,D] (and fp32 copy, optional) */
+int sc_meanpool_fwd(const void* x, void* out_bf16, float* out_f32, int64_t B, int S, int D,
+                    void* stream);
+
+/* a6: semantic distortion, fused forward + backward:
+ *   loss_accum[0] += sum((r - t)^2) * inv_numel ;  dr = bf16(2 (r - t) * grad_scale) */
+int sc_mse_fwd_bwd(const void* r, const void* t, float* loss_accum, void* dr, int64_t numel,
+                   float inv_numel, float grad_scale, void* stream);
+
+/* a7: actor-critic output layer on the tanh trunk: head_out[b, 0..A] = trunk[b,:] W^T + bias
+ * trunk bf16 [B,D]; W fp32 [A+1, D]; head_out fp32 [B, A+1] (cols 0..A-1 logits, col A value) */
+int sc_heads_fwd(const void* trunk, const float* W, const float* bias, float* head_out, int64_t B,
+                 int D, int A1, void* stream);
+/* dtrunk_pre = (dho W) * (1 - trunk^2) (bf16) ; dW += dho^T trunk ; dbias += colsum(dho) */
+int sc_heads_bwd(const float* dho, const void* trunk, const float* W, void* dtrunk_pre, float* dW,
+                 float* dbias, int64_t B, int D, int A1, void* stream);
+/* a7: inverse-CDF sampling from supplied uniforms (fp64 cdf): action int64, logp fp32 */
+int sc_sample_action(const float* head_out, int ld, const float* u, int64_t* action, float* logp,
+                     int64_t B, int A, void* stream);
+
+/* a8: GAE reverse scan, warp-shuffle linear-recurrence scan over T.
+ * rewards/values/dones fp32 [T,N], last_value [N] -> adv, ret [T,N]; sums (double[2]) += (sum, sumsq) of adv */
+int sc_gae(const float* rewards, const float* values, const float* dones, const float* last_value,
+           float* adv, float* ret, double* sums, int T, int64_t N, float gamma, float lam,
+           void* stream);
+/* adv = (adv - mean) / (std + eps) with mean/std from sums over `count` elements */
+int sc_adv_normalize(float* adv, const double* sums, int64_t count, int64_t n, float eps,
+                     void* stream);
+
+/* a9: PPO clipped loss, forward + backward fused.
+ * head_out fp32 [M, ld] (A logits + value); writes dho fp32 [M, ld] (d total / d head_out, incl.
+ * the 1/M_global factor) and accumulates stats[8] += {pi, v, ent, kl, clipfrac, 0,0,0} * inv_m */
+int sc_ppo_loss(const float* head_out, int ld, const int64_t* actions, const float* logp_old,
+                const float* adv, const float* ret, float* dho, float* stats, int64_t M, int A,
+                float clip_eps, float c_v, float c_ent, float inv_m, void* stream);
+
+/* a10: fused Adam over the flat parameter bucket; also refreshes the bf16 shadow copy.
+ * g is multiplied by grad_scale (1/world_size) first. step >= 1. */
+int sc_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                 float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+
+int sc_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMCOM_SM100_H_ */

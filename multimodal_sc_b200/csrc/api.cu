@@ -1,0 +1,107 @@
+// api.cu — library plumbing: error string, device check, launch counter, TMA descriptor
+// encoding through the driver entry point (no link-time dependency on libcuda).
+#include <atomic>
+#include <cstring>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void sc_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void sc_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct DevInfo {
+  int checked = 0;
+  int major = 0;
+  int sms = 0;
+};
+static DevInfo g_dev[64];
+
+static DevInfo* dev_info() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+  DevInfo* di = &g_dev[d];
+  if (!di->checked) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) != cudaSuccess) return nullptr;
+    di->major = p.major;
+    di->sms = p.multiProcessorCount;
+    di->checked = 1;
+  }
+  return di;
+}
+
+int sc_check_device() {
+  DevInfo* di = dev_info();
+  if (!di) {
+    sc_set_error("no CUDA device available: %s", cudaGetErrorString(cudaGetLastError()));
+    return SC_E_ARCH;
+  }
+  if (di->major != 10) {
+    sc_set_error("libsemcom_sm100 requires an sm_100 (B200) device, found sm_%d0; there is no fallback",
+                 di->major);
+    return SC_E_ARCH;
+  }
+  return SC_OK;
+}
+
+int sc_num_sms() {
+  DevInfo* di = dev_info();
+  return di ? di->sms : 148;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode) return SC_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    sc_set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return SC_E_DRIVER;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return SC_OK;
+}
+
+// 2-D bf16 tensor, inner dimension contiguous, SWIZZLE_128B boxes (box_inner * 2 bytes == 128).
+int sc_encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
+                           uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  int rc = load_encode();
+  if (rc != SC_OK) return rc;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sc_set_error("cuTensorMapEncodeTiled failed (CUresult %d): base=%p inner=%llu outer=%llu stride=%llu box=%ux%u",
+                 (int)r, base, (unsigned long long)inner, (unsigned long long)outer,
+                 (unsigned long long)row_stride_bytes, box_inner, box_outer);
+    return SC_E_DRIVER;
+  }
+  return SC_OK;
+}
+
+extern "C" {
+
+int sc_version(void) { return SC_ABI_VERSION; }
+const char* sc_last_error(void) { return g_err; }
+int sc_device_ok(void) { return sc_check_device(); }
+int64_t sc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

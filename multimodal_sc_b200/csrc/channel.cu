@@ -1,0 +1,296 @@
+// channel.cu — fused power normalisation + noisy channel (SPEC v0 rows a3 + a4).
+//
+// One CTA per (sample, modality) row of k real symbols: one pass computes sum z^2 (warp shuffle
+// + smem), the scale rsqrt(mean z^2 + eps), draws the noise in-kernel (Philox4x32-10 +
+// Box-Muller, counter layout of oracle/philox.py) and writes y.  z stays in registers between
+// the reduction and the output, so HBM traffic is the algorithmic 1 read + 1 write.
+// Backward needs no noise at all (it is additive): dz = s (g - zn mean(g zn)).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxV = 4;                      // float4 per thread -> k <= 4096
+
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) { k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
+    const uint32_t hi1 = __umulhi(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+  }
+  return c;
+}
+__device__ __forceinline__ float u32_to_uniform(uint32_t x) {
+  return (static_cast<float>(x >> 9) + 0.5f) * 1.1920928955078125e-07f;   // 2^-23, exact
+}
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float r = sqrtf(-2.0f * logf(u32_to_uniform(a)));
+  float s, c;
+  sincospif(2.0f * u32_to_uniform(b), &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+__device__ __forceinline__ float4 normal4(uint64_t quad, uint32_t stream, uint32_t k0, uint32_t k1) {
+  const uint4 w = philox4x32_10(make_uint4(static_cast<uint32_t>(quad), stream, static_cast<uint32_t>(quad >> 32), 0u),
+                                k0, k1);
+  float4 n;
+  box_muller(w.x, w.y, n.x, n.y);
+  box_muller(w.z, w.w, n.z, n.w);
+  return n;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = (threadIdx.x < kThreads / 32) ? sh[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    t = warp_sum(t);
+    if (lane == 0) sh[0] = t;
+  }
+  __syncthreads();
+  const float r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+struct ChanArgs {
+  const float* z; int64_t z_sb, z_sm;
+  float* y_f32; bf16* y_bf16; int64_t y_sb, y_sm;
+  float* scale;
+  int64_t B; int k; int kind;
+  const float* snr_db; float snr_db_scalar;
+  uint32_t key0, key1; int64_t sample_offset;
+  const float* noise; const float* fading;
+  float eps;
+};
+
+__device__ __forceinline__ float sigma_of(const float* snr_db, float snr_scalar, int64_t b) {
+  const float s = snr_db ? snr_db[b] : snr_scalar;
+  return exp10f(-s * 0.05f);
+}
+__device__ __forceinline__ float2 fading_of(const float* fading, int64_t b, int m, int64_t sample_offset,
+                                            uint32_t k0, uint32_t k1) {
+  if (fading) return make_float2(fading[(b * 2 + m) * 2], fading[(b * 2 + m) * 2 + 1]);
+  const uint64_t j = static_cast<uint64_t>(sample_offset + b) * 2 + m;
+  const uint4 w = philox4x32_10(make_uint4(static_cast<uint32_t>(j), 1u, static_cast<uint32_t>(j >> 32), 0u), k0, k1);
+  float hr, hi;
+  box_muller(w.x, w.y, hr, hi);
+  return make_float2(hr * 0.70710678118654752f, hi * 0.70710678118654752f);
+}
+
+__global__ void __launch_bounds__(kThreads)
+pnorm_channel_fwd_kernel(const ChanArgs a) {
+  __shared__ float sh[kThreads / 32];
+  const int nv = a.k / 4;                                    // float4 per row
+  for (int64_t row = blockIdx.x; row < a.B * 2; row += gridDim.x) {
+    const int64_t b = row >> 1;
+    const int m = static_cast<int>(row & 1);
+    const float* zr = a.z + b * a.z_sb + m * a.z_sm;
+    float4 v[kMaxV];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int q = threadIdx.x + i * kThreads;
+      if (q < nv) {
+        v[i] = *reinterpret_cast<const float4*>(zr + q * 4);
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    }
+    ss = block_sum(ss, sh);
+    const float scale = rsqrtf(ss / static_cast<float>(a.k) + a.eps);
+    if (threadIdx.x == 0 && a.scale) a.scale[row] = scale;
+    float sigma = 0.f, hr = 1.f, hi = 0.f, inv_den = 1.f;
+    if (a.kind != SC_CH_NONE) sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
+    if (a.kind == SC_CH_RAYLEIGH) {
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, a.key0, a.key1);
+      hr = h.x; hi = h.y;
+      inv_den = 1.0f / (hr * hr + hi * hi + sigma * sigma);
+    }
+    const uint64_t quad0 = (static_cast<uint64_t>(a.sample_offset + b) * 2 + m) * static_cast<uint64_t>(nv);
+    float* yf = a.y_f32 ? a.y_f32 + b * a.y_sb + m * a.y_sm : nullptr;
+    bf16* yb = a.y_bf16 ? a.y_bf16 + b * a.y_sb + m * a.y_sm : nullptr;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int q = threadIdx.x + i * kThreads;
+      if (q < nv) {
+        float4 s = make_float4(v[i].x * scale, v[i].y * scale, v[i].z * scale, v[i].w * scale);
+        float4 o = s;
+        if (a.kind != SC_CH_NONE) {
+          float4 n;
+          if (a.noise) n = *reinterpret_cast<const float4*>(a.noise + row * a.k + q * 4);
+          else n = normal4(quad0 + q, 0u, a.key0, a.key1);
+          if (a.kind == SC_CH_AWGN) {
+            o = make_float4(fmaf(sigma, n.x, s.x), fmaf(sigma, n.y, s.y), fmaf(sigma, n.z, s.z), fmaf(sigma, n.w, s.w));
+          } else {
+            // two complex symbols (x,y) and (z,w): r = h s + sigma n ; y = conj(h) r / (|h|^2 + sigma^2)
+            const float r0r = hr * s.x - hi * s.y + sigma * n.x, r0i = hr * s.y + hi * s.x + sigma * n.y;
+            const float r1r = hr * s.z - hi * s.w + sigma * n.z, r1i = hr * s.w + hi * s.z + sigma * n.w;
+            o = make_float4((hr * r0r + hi * r0i) * inv_den, (hr * r0i - hi * r0r) * inv_den,
+                            (hr * r1r + hi * r1i) * inv_den, (hr * r1i - hi * r1r) * inv_den);
+          }
+        }
+        if (yf) *reinterpret_cast<float4*>(yf + q * 4) = o;
+        if (yb) *reinterpret_cast<uint2*>(yb + q * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
+struct ChanBwdArgs {
+  const float* dy; int64_t y_sb, y_sm;
+  const float* z; int64_t z_sb, z_sm;
+  const float* scale;
+  float* dz_f32; bf16* dz_bf16;
+  int64_t B; int k; int kind;
+  const float* snr_db; float snr_db_scalar;
+  uint32_t key0, key1; int64_t sample_offset;
+  const float* fading;
+};
+
+__global__ void __launch_bounds__(kThreads)
+pnorm_channel_bwd_kernel(const ChanBwdArgs a) {
+  __shared__ float sh[kThreads / 32];
+  const int nv = a.k / 4;
+  for (int64_t row = blockIdx.x; row < a.B * 2; row += gridDim.x) {
+    const int64_t b = row >> 1;
+    const int m = static_cast<int>(row & 1);
+    const float* zr = a.z + b * a.z_sb + m * a.z_sm;
+    const float* gr = a.dy + b * a.y_sb + m * a.y_sm;
+    const float scale = a.scale[row];
+    float gain = 1.f;
+    if (a.kind == SC_CH_RAYLEIGH) {
+      const float sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, a.key0, a.key1);
+      const float h2 = h.x * h.x + h.y * h.y;
+      gain = h2 / (h2 + sigma * sigma);
+    }
+    float4 zn[kMaxV], g[kMaxV];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int q = threadIdx.x + i * kThreads;
+      if (q < nv) {
+        const float4 zv = *reinterpret_cast<const float4*>(zr + q * 4);
+        const float4 gv = *reinterpret_cast<const float4*>(gr + q * 4);
+        zn[i] = make_float4(zv.x * scale, zv.y * scale, zv.z * scale, zv.w * scale);
+        g[i] = make_float4(gv.x * gain, gv.y * gain, gv.z * gain, gv.w * gain);
+        dot += g[i].x * zn[i].x + g[i].y * zn[i].y + g[i].z * zn[i].z + g[i].w * zn[i].w;
+      }
+    }
+    dot = block_sum(dot, sh) / static_cast<float>(a.k);
+    float* df = a.dz_f32 ? a.dz_f32 + b * a.z_sb + m * a.z_sm : nullptr;
+    bf16* db = a.dz_bf16 ? a.dz_bf16 + b * a.z_sb + m * a.z_sm : nullptr;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int q = threadIdx.x + i * kThreads;
+      if (q < nv) {
+        const float4 o = make_float4(scale * (g[i].x - zn[i].x * dot), scale * (g[i].y - zn[i].y * dot),
+                                     scale * (g[i].z - zn[i].z * dot), scale * (g[i].w - zn[i].w * dot));
+        if (df) *reinterpret_cast<float4*>(df + q * 4) = o;
+        if (db) *reinterpret_cast<uint2*>(db + q * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
+__global__ void philox_words_kernel(uint32_t* out, int64_t n_quads, uint32_t stream_id, uint32_t k0, uint32_t k1,
+                                    int64_t quad_offset) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_quads;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t q = static_cast<uint64_t>(quad_offset + i);
+    const uint4 w = philox4x32_10(make_uint4(static_cast<uint32_t>(q), stream_id, static_cast<uint32_t>(q >> 32), 0u), k0, k1);
+    *reinterpret_cast<uint4*>(out + i * 4) = w;
+  }
+}
+
+int check_common(const char* nm, int64_t B, int k, int kind, int64_t sb, int64_t sm) {
+  SC_REQUIRE(B > 0 && k > 0 && k % 4 == 0 && k <= kMaxV * kThreads * 4, SC_E_SHAPE,
+             "%s: B=%lld k=%d (need k %% 4 == 0 and k <= %d)", nm, (long long)B, k, kMaxV * kThreads * 4);
+  SC_REQUIRE(kind >= SC_CH_NONE && kind <= SC_CH_RAYLEIGH, SC_E_SHAPE, "%s: unknown channel kind %d", nm, kind);
+  SC_REQUIRE(sb % 4 == 0 && sm % 4 == 0, SC_E_ALIGN, "%s: strides must be multiples of 4 elements", nm);
+  return SC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f32, void* y_bf16, int64_t y_sb,
+                         int64_t y_sm, float* scale, int64_t B, int k, int kind, const float* snr_db,
+                         float snr_db_scalar, uint64_t seed, int64_t sample_offset, const float* noise,
+                         const float* fading, float eps, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(z && (y_f32 || y_bf16), SC_E_SHAPE, "sc_pnorm_channel_fwd: null pointer");
+  if ((rc = check_common("sc_pnorm_channel_fwd", B, k, kind, z_sb, z_sm)) != SC_OK) return rc;
+  if ((rc = check_common("sc_pnorm_channel_fwd", B, k, kind, y_sb, y_sm)) != SC_OK) return rc;
+  SC_REQUIRE(sc_aligned16(z) && sc_aligned16(y_f32) && sc_aligned16(noise) &&
+                 (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
+             SC_E_ALIGN, "sc_pnorm_channel_fwd: unaligned pointer");
+  ChanArgs a;
+  a.z = z; a.z_sb = z_sb; a.z_sm = z_sm;
+  a.y_f32 = y_f32; a.y_bf16 = (bf16*)y_bf16; a.y_sb = y_sb; a.y_sm = y_sm;
+  a.scale = scale; a.B = B; a.k = k; a.kind = kind;
+  a.snr_db = snr_db; a.snr_db_scalar = snr_db_scalar;
+  a.key0 = (uint32_t)(seed & 0xffffffffu); a.key1 = (uint32_t)(seed >> 32);
+  a.sample_offset = sample_offset; a.noise = noise; a.fading = fading; a.eps = eps;
+  const int64_t rows = B * 2;
+  const int64_t cap = (int64_t)sc_num_sms() * 8;
+  const int grid = (int)(rows < cap ? rows : cap);
+  pnorm_channel_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_pnorm_channel_fwd");
+  return SC_OK;
+}
+
+int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const float* z, int64_t z_sb, int64_t z_sm,
+                         const float* scale, float* dz_f32, void* dz_bf16, int64_t B, int k, int kind,
+                         const float* snr_db, float snr_db_scalar, uint64_t seed, int64_t sample_offset,
+                         const float* fading, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(dy && z && scale && (dz_f32 || dz_bf16), SC_E_SHAPE, "sc_pnorm_channel_bwd: null pointer");
+  if ((rc = check_common("sc_pnorm_channel_bwd", B, k, kind, z_sb, z_sm)) != SC_OK) return rc;
+  if ((rc = check_common("sc_pnorm_channel_bwd", B, k, kind, y_sb, y_sm)) != SC_OK) return rc;
+  SC_REQUIRE(sc_aligned16(dy) && sc_aligned16(z) && sc_aligned16(dz_f32) &&
+                 (reinterpret_cast<uintptr_t>(dz_bf16) & 7) == 0,
+             SC_E_ALIGN, "sc_pnorm_channel_bwd: unaligned pointer");
+  ChanBwdArgs a;
+  a.dy = dy; a.y_sb = y_sb; a.y_sm = y_sm; a.z = z; a.z_sb = z_sb; a.z_sm = z_sm; a.scale = scale;
+  a.dz_f32 = dz_f32; a.dz_bf16 = (bf16*)dz_bf16; a.B = B; a.k = k; a.kind = kind;
+  a.snr_db = snr_db; a.snr_db_scalar = snr_db_scalar;
+  a.key0 = (uint32_t)(seed & 0xffffffffu); a.key1 = (uint32_t)(seed >> 32);
+  a.sample_offset = sample_offset; a.fading = fading;
+  const int64_t rows = B * 2;
+  const int64_t cap = (int64_t)sc_num_sms() * 8;
+  const int grid = (int)(rows < cap ? rows : cap);
+  pnorm_channel_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_pnorm_channel_bwd");
+  return SC_OK;
+}
+
+int sc_philox_words(uint32_t* out, int64_t n_quads, uint32_t stream_id, uint64_t seed, int64_t quad_offset,
+                    void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(out && n_quads > 0, SC_E_SHAPE, "sc_philox_words: bad arguments");
+  SC_REQUIRE(sc_aligned16(out), SC_E_ALIGN, "sc_philox_words: unaligned pointer");
+  const int grid = (int)((n_quads + 255) / 256 < 1184 ? (n_quads + 255) / 256 : 1184);
+  philox_words_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n_quads, stream_id, (uint32_t)(seed & 0xffffffffu),
+                                                              (uint32_t)(seed >> 32), quad_offset);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_philox_words");
+  return SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,430 @@
+// elementwise.cu — memory-bound fused kernels: patchify+cast, LayerNorm fwd/bwd, column sums,
+// mean-pool, fused MSE fwd+bwd, casts.  All 128-bit vectorised, coalesced, warp-shuffle
+// reductions; grids are persistent (a multiple of the SM count) with grid-stride loops.
+// SPEC v0 rows a1/a2 (patchify), a1/a2/a5 (LayerNorm), a5 (mean-pool), a6 (semantic distortion).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void load8(const bf16* p, float (&x)[8]) {
+  uint4 w = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(w.x), b = unpack_bf16(w.y), c = unpack_bf16(w.z), d = unpack_bf16(w.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+}
+__device__ __forceinline__ void load8(const float* p, float (&x)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&x)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
+                                            pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+}
+__device__ __forceinline__ void store8(float* p, const float (&x)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+}
+
+inline int persistent_blocks(int64_t work_blocks, int per_sm) {
+  int64_t cap = static_cast<int64_t>(sc_num_sms()) * per_sm;
+  return static_cast<int>(work_blocks < cap ? (work_blocks > 0 ? work_blocks : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------
+// patchify + cast: one thread per 8 output features (always inside one image row)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int64_t groups, int C, int H,
+                int W, int P) {
+  const int Wt = W / P, Ht = H / P;
+  const int K = C * P * P;
+  const int K8 = K / 8;
+  const int P8 = P / 8;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int kg = static_cast<int>(g % K8);
+    const int64_t tok = g / K8;
+    const int px0 = (kg % P8) * 8;
+    const int py = (kg / P8) % P;
+    const int c = kg / (P8 * P);
+    const int tx = static_cast<int>(tok % Wt);
+    const int ty = static_cast<int>((tok / Wt) % Ht);
+    const int64_t b = tok / (Wt * Ht);
+    const float* src = img + ((b * C + c) * H + (ty * P + py)) * static_cast<int64_t>(W) + tx * P + px0;
+    float x[8];
+    load8(src, x);
+    store8(out + g * 8, x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, lane owns NCH chunks of 8 contiguous elements (D = 256*NCH)
+// ------------------------------------------------------------------------------------------
+template <typename T, int NCH>
+__global__ void __launch_bounds__(kThreads)
+layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int64_t M, float eps) {
+  constexpr int D = 256 * NCH;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float g[NCH][8], bta[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    load8(gamma + c * 256 + lane * 8, g[c]);
+    load8(beta + c * 256 + lane * 8, bta[c]);
+  }
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    float v[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      load8(x + row * D + c * 256 + lane * 8, v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[c][j] - mean) * rstd, g[c][j], bta[c][j]);
+      store8(y + row * D + c * 256 + lane * 8, o);
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; colsum += sum_rows dx
+template <typename T, int NCH>
+__global__ void __launch_bounds__(kThreads)
+layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma,
+                     const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ colsum, int64_t M) {
+  constexpr int D = 256 * NCH;
+  __shared__ float red[3][D];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  float gm[NCH][8];
+  float a_dg[NCH][8], a_db[NCH][8], a_cs[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    load8(gamma + c * 256 + lane * 8, gm[c]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a_dg[c][j] = a_db[c][j] = a_cs[c][j] = 0.f;
+  }
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NCH][8], g[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float xv[8], dyv[8];
+      load8(x + row * D + c * 256 + lane * 8, xv);
+      load8(dy + row * D + c * 256 + lane * 8, dyv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[c][j] = (xv[j] - mu) * rs;
+        g[c][j] = dyv[j] * gm[c][j];
+        s1 += g[c][j];
+        s2 = fmaf(g[c][j], xh[c][j], s2);
+        a_dg[c][j] = fmaf(dyv[j], xh[c][j], a_dg[c][j]);
+        a_db[c][j] += dyv[j];
+      }
+    }
+    const float m1 = warp_sum(s1) * (1.0f / D);
+    const float m2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - m1 - xh[c][j] * m2);
+      if (dres) {
+        float r[8];
+        load8(dres + row * D + c * 256 + lane * 8, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      store8(dx + row * D + c * 256 + lane * 8, o);
+      if (colsum) {
+        // accumulate what was actually written (bf16-rounded for T = bf16) — matches a later colsum(dx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a_cs[c][j] += o[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = c * 256 + lane * 8 + j;
+      atomicAdd(&red[0][col], a_dg[c][j]);
+      atomicAdd(&red[1][col], a_db[c][j]);
+      if (colsum) atomicAdd(&red[2][col], a_cs[c][j]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[0][i]);
+    atomicAdd(dbeta + i, red[1][i]);
+    if (colsum) atomicAdd(colsum + i, red[2][i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums of a bf16 [M, N] matrix (bias gradients)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t M, int N, int64_t ld,
+              int64_t rows_per_block) {
+  extern __shared__ float sred[];          // [N]
+  const int G = N / 8;                      // column groups
+  const int rpi = blockDim.x / G;           // rows per iteration
+  const int cg = threadIdx.x % G;
+  const int rg = threadIdx.x / G;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t r0 = blockIdx.x * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  if (rg < rpi) {
+    for (int64_t r = r0 + rg; r < r1; r += rpi) {
+      float v[8];
+      load8(x + r * ld + cg * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sred[cg * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(out + i, sred[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// mean-pool over S tokens: one block of 4 warps per sample, D = 256 (lane owns 8 columns)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+meanpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                int64_t B, int S, int D) {
+  __shared__ float red[4][1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nch = D / 256;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int c = 0; c < nch; ++c) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s = warp; s < S; s += 4) {
+        float v[8];
+        load8(x + (b * S + s) * D + c * 256 + lane * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][c * 256 + lane * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      const float m = (red[0][i] + red[1][i] + red[2][i] + red[3][i]) * (1.0f / S);
+      if (out_bf16) out_bf16[b * D + i] = __float2bfloat16(m);
+      if (out_f32) out_f32[b * D + i] = m;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused MSE forward + backward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+mse_kernel(const bf16* __restrict__ r, const bf16* __restrict__ t, float* __restrict__ loss,
+           bf16* __restrict__ dr, int64_t groups, float inv_numel, float grad_scale) {
+  __shared__ float wsum[kThreads / 32];
+  float acc = 0.f;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a[8], b[8], d[8];
+    load8(r + g * 8, a);
+    load8(t + g * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float e = a[j] - b[j];
+      acc = fmaf(e, e, acc);
+      d[j] = 2.0f * e * grad_scale;
+    }
+    if (dr) store8(dr + g * 8, d);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kThreads / 32 ? wsum[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss, v * inv_numel);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  const int64_t groups = n / 8;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float v[8];
+    load8(src + g * 8, v);
+    store8(dst + g * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const int64_t i = groups * 8 + threadIdx.x;
+    dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sc_patchify_bf16(const float* img, void* out, int64_t B, int C, int H, int W, int P, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(img && out, SC_E_SHAPE, "sc_patchify_bf16: null pointer");
+  SC_REQUIRE(B > 0 && C > 0 && P > 0 && P % 8 == 0 && H % P == 0 && W % P == 0, SC_E_SHAPE,
+             "sc_patchify_bf16: need P %% 8 == 0 and H, W multiples of P (B=%lld C=%d H=%d W=%d P=%d)",
+             (long long)B, C, H, W, P);
+  SC_REQUIRE(sc_aligned16(img) && sc_aligned16(out), SC_E_ALIGN, "sc_patchify_bf16: unaligned pointer");
+  const int64_t groups = B * C * H * (int64_t)W / 8;
+  const int grid = persistent_blocks((groups + kThreads - 1) / kThreads, 8);
+  patchify_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img, (bf16*)out, groups, C, H, W, P);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_patchify_bf16");
+  return SC_OK;
+}
+
+int sc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int64_t M, int D, float eps, int io_f32, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(x && gamma && beta && y, SC_E_SHAPE, "sc_layernorm_fwd: null pointer");
+  SC_REQUIRE(M > 0 && (D == 256 || D == 512 || D == 1024), SC_E_SHAPE,
+             "sc_layernorm_fwd: M=%lld D=%d (D must be 256, 512 or 1024)", (long long)M, D);
+  SC_REQUIRE(sc_aligned16(x) && sc_aligned16(y) && sc_aligned16(gamma) && sc_aligned16(beta), SC_E_ALIGN,
+             "sc_layernorm_fwd: unaligned pointer");
+  const int grid = persistent_blocks((M + 7) / 8, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LN_FWD(T, NCH) \
+  layernorm_fwd_kernel<T, NCH><<<grid, kThreads, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, M, eps)
+  if (io_f32) {
+    if (D == 256) LN_FWD(float, 1); else if (D == 512) LN_FWD(float, 2); else LN_FWD(float, 4);
+  } else {
+    if (D == 256) LN_FWD(bf16, 1); else if (D == 512) LN_FWD(bf16, 2); else LN_FWD(bf16, 4);
+  }
+#undef LN_FWD
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_layernorm_fwd");
+  return SC_OK;
+}
+
+int sc_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, float* colsum, int64_t M, int D,
+                     int io_f32, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, SC_E_SHAPE, "sc_layernorm_bwd: null pointer");
+  SC_REQUIRE(M > 0 && (D == 256 || D == 512 || D == 1024), SC_E_SHAPE,
+             "sc_layernorm_bwd: M=%lld D=%d (D must be 256, 512 or 1024)", (long long)M, D);
+  SC_REQUIRE(sc_aligned16(dy) && sc_aligned16(x) && sc_aligned16(dx) && sc_aligned16(dres) && sc_aligned16(gamma),
+             SC_E_ALIGN, "sc_layernorm_bwd: unaligned pointer");
+  const int grid = persistent_blocks((M + 7) / 8, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LN_BWD(T, NCH)                                                                                   \
+  layernorm_bwd_kernel<T, NCH><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma,  \
+                                                          (const T*)dres, (T*)dx, dgamma, dbeta, colsum, M)
+  if (io_f32) {
+    if (D == 256) LN_BWD(float, 1); else if (D == 512) LN_BWD(float, 2); else LN_BWD(float, 4);
+  } else {
+    if (D == 256) LN_BWD(bf16, 1); else if (D == 512) LN_BWD(bf16, 2); else LN_BWD(bf16, 4);
+  }
+#undef LN_BWD
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_layernorm_bwd");
+  return SC_OK;
+}
+
+int sc_colsum_bf16(const void* x, float* out, int64_t M, int N, int64_t ld, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(x && out, SC_E_SHAPE, "sc_colsum_bf16: null pointer");
+  SC_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && N <= 2048 && ld >= N && ld % 8 == 0, SC_E_SHAPE,
+             "sc_colsum_bf16: M=%lld N=%d ld=%lld (need N %% 8 == 0, N <= 2048)", (long long)M, N, (long long)ld);
+  SC_REQUIRE(sc_aligned16(x), SC_E_ALIGN, "sc_colsum_bf16: unaligned pointer");
+  const int target = sc_num_sms() * 4;
+  int64_t rpb = (M + target - 1) / target;
+  if (rpb < 32) rpb = 32;
+  const int grid = (int)((M + rpb - 1) / rpb);
+  colsum_kernel<<<grid, kThreads, N * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, out, M, N, ld, rpb);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_colsum_bf16");
+  return SC_OK;
+}
+
+int sc_meanpool_fwd(const void* x, void* out_bf16, float* out_f32, int64_t B, int S, int D, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(x && (out_bf16 || out_f32), SC_E_SHAPE, "sc_meanpool_fwd: null pointer");
+  SC_REQUIRE(B > 0 && S > 0 && D % 256 == 0 && D <= 1024, SC_E_SHAPE, "sc_meanpool_fwd: B=%lld S=%d D=%d",
+             (long long)B, S, D);
+  SC_REQUIRE(sc_aligned16(x), SC_E_ALIGN, "sc_meanpool_fwd: unaligned pointer");
+  const int grid = persistent_blocks(B, 16);
+  meanpool_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out_bf16, out_f32, B, S, D);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_meanpool_fwd");
+  return SC_OK;
+}
+
+int sc_mse_fwd_bwd(const void* r, const void* t, float* loss_accum, void* dr, int64_t numel, float inv_numel,
+                   float grad_scale, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(r && t && loss_accum, SC_E_SHAPE, "sc_mse_fwd_bwd: null pointer");
+  SC_REQUIRE(numel > 0 && numel % 8 == 0, SC_E_SHAPE, "sc_mse_fwd_bwd: numel=%lld must be a positive multiple of 8",
+             (long long)numel);
+  SC_REQUIRE(sc_aligned16(r) && sc_aligned16(t) && sc_aligned16(dr), SC_E_ALIGN, "sc_mse_fwd_bwd: unaligned pointer");
+  const int64_t groups = numel / 8;
+  const int grid = persistent_blocks((groups + kThreads - 1) / kThreads, 8);
+  mse_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const bf16*)r, (const bf16*)t, loss_accum, (bf16*)dr,
+                                                          groups, inv_numel, grad_scale);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_mse_fwd_bwd");
+  return SC_OK;
+}
+
+int sc_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(src && dst && n > 0, SC_E_SHAPE, "sc_cast_f32_bf16: bad arguments");
+  SC_REQUIRE(sc_aligned16(src) && sc_aligned16(dst), SC_E_ALIGN, "sc_cast_f32_bf16: unaligned pointer");
+  const int grid = persistent_blocks((n / 8 + kThreads - 1) / kThreads, 8);
+  cast_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_cast_f32_bf16");
+  return SC_OK;
+}
+
+}  // extern "C"

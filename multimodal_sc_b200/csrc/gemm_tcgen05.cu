@@ -1,0 +1,448 @@
+// gemm_tcgen05.cu — persistent, warp-specialised bf16 GEMM for sm_100a.
+//
+//   acc[m,n] = sum_k A(m,k) B(n,k), fp32 accumulation in TMEM, fused epilogue (see
+//   include/semcom_sm100.h: sc_gemm_bf16).  Implements every dense contraction of SPEC v0
+//   rows a1/a2/a5 and their dgrad / wgrad forms.
+//
+// Structure (one CTA per SM, 256 threads):
+//   warp 0 / lane 0 : TMA producer     — cp.async.bulk.tensor.2d into a 4-stage smem ring
+//   warp 1 / lane 0 : MMA issuer       — tcgen05.mma.cta_group::1.kind::f16, 128x256x16
+//   warp 2          : TMEM allocator   — 512 columns = two 128x256 fp32 accumulators
+//   warps 4..7      : epilogue         — tcgen05.ld 32x32b, fused math, 16-byte stores
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+// The accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Operand layouts in shared memory (all SWIZZLE_128B, written by TMA):
+//   K-major  operand (stored [rows, K]): tile = rows x 64 k  -> rows x 128 B, 8-row groups of
+//            1024 B (SBO = 1024); successive UMMA_K=16 slices advance the start by 32 B.
+//   MN-major operand (stored [K, cols]): tile = 64-column chunks, each 64 k-rows x 128 B
+//            (8192 B, LBO = 8192 between chunks, SBO = 1024 between 8-k-row groups);
+//            successive UMMA_K slices advance the start by 16 rows = 2048 B.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;                 // 16384
+constexpr int B_BYTES = BN * BK * 2;                 // 32768
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 49152
+constexpr int CHUNK_BYTES = 64 * BK * 2;             // 8192: one 64-wide MN-major chunk
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+constexpr int NUM_THREADS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct GemmParams {
+  int64_t M, N, K;
+  int tiles_m, tiles_n, ksplit, kb_total, kb_per_split;
+  // epilogue
+  const float* bias;
+  const float* rowadd;
+  uint32_t rowadd_period;
+  const float* rowgrp;
+  uint32_t rowgrp_size;
+  float rowgrp_scale;
+  float alpha;
+  const bf16* resid;
+  const bf16* aux_in;
+  bf16* aux_out;
+  bf16* out_bf16;
+  float* out_f32;
+  int64_t ldo;
+  int act;
+  int atomic;
+  int vec_ok;
+  // UMMA descriptor fields (bytes); defaults set by the host, overridable for bring-up
+  uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+};
+
+struct Item {
+  int m_blk, n_blk, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
+  Item it;
+  int s = item % p.ksplit;
+  int t = item / p.ksplit;
+  it.n_blk = t % p.tiles_n;
+  it.m_blk = t / p.tiles_n;
+  it.kb_begin = s * p.kb_per_split;
+  it.kb_end = min(p.kb_total, it.kb_begin + p.kb_per_split);
+  return it;
+}
+
+template <bool kFast>
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == SC_ACT_GELU) return gelu_fwd<kFast>(x);
+  if (act == SC_ACT_TANH) return kFast ? tanh_fast(x) : tanhf(x);
+  return x;
+}
+
+// 8 consecutive columns of one row (vector path: everything 16-byte aligned)
+__device__ __forceinline__ void epilogue_vec8(const GemmParams& p, const uint32_t* acc, int64_t row,
+                                              int col, uint32_t row_mod, uint32_t row_grp) {
+  float x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(acc[j]) * p.alpha;
+  if (p.bias) {
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+  }
+  if (p.rowadd) {
+    const float* ra = p.rowadd + static_cast<int64_t>(row_mod) * p.N + col;
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(ra));
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(ra + 4));
+    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+  }
+  if (p.rowgrp) {
+    const float* rg = p.rowgrp + static_cast<int64_t>(row_grp) * p.N + col;
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(rg));
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(rg + 4));
+    const float s = p.rowgrp_scale;
+    x[0] = fmaf(b0.x, s, x[0]); x[1] = fmaf(b0.y, s, x[1]); x[2] = fmaf(b0.z, s, x[2]);
+    x[3] = fmaf(b0.w, s, x[3]); x[4] = fmaf(b1.x, s, x[4]); x[5] = fmaf(b1.y, s, x[5]);
+    x[6] = fmaf(b1.z, s, x[6]); x[7] = fmaf(b1.w, s, x[7]);
+  }
+  const int64_t off = row * p.ldo + col;
+  if (p.aux_out) {
+    uint4 w = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                         pack_bf16(x[6], x[7]));
+    *reinterpret_cast<uint4*>(p.aux_out + off) = w;
+  }
+  if (p.act != SC_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = apply_act<true>(x[j], p.act);
+  }
+  if (p.aux_in) {
+    uint4 w = __ldg(reinterpret_cast<const uint4*>(p.aux_in + off));
+    float2 a0 = unpack_bf16(w.x), a1 = unpack_bf16(w.y), a2 = unpack_bf16(w.z), a3 = unpack_bf16(w.w);
+    x[0] *= gelu_bwd<true>(a0.x); x[1] *= gelu_bwd<true>(a0.y);
+    x[2] *= gelu_bwd<true>(a1.x); x[3] *= gelu_bwd<true>(a1.y);
+    x[4] *= gelu_bwd<true>(a2.x); x[5] *= gelu_bwd<true>(a2.y);
+    x[6] *= gelu_bwd<true>(a3.x); x[7] *= gelu_bwd<true>(a3.y);
+  }
+  if (p.resid) {
+    uint4 w = __ldg(reinterpret_cast<const uint4*>(p.resid + off));
+    float2 a0 = unpack_bf16(w.x), a1 = unpack_bf16(w.y), a2 = unpack_bf16(w.z), a3 = unpack_bf16(w.w);
+    x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
+    x[4] += a2.x; x[5] += a2.y; x[6] += a3.x; x[7] += a3.y;
+  }
+  if (p.out_bf16) {
+    uint4 w = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                         pack_bf16(x[6], x[7]));
+    *reinterpret_cast<uint4*>(p.out_bf16 + off) = w;
+  }
+  if (p.out_f32) {
+    float* o = p.out_f32 + off;
+    if (p.atomic) {
+      red_add_v4_f32(o, x[0], x[1], x[2], x[3]);
+      red_add_v4_f32(o + 4, x[4], x[5], x[6], x[7]);
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    }
+  }
+}
+
+// scalar path for ragged N / unaligned leading dimensions
+__device__ __forceinline__ void epilogue_scalar(const GemmParams& p, float a, int64_t row, int col,
+                                                uint32_t row_mod, uint32_t row_grp) {
+  float x = a * p.alpha;
+  if (p.bias) x += __ldg(p.bias + col);
+  if (p.rowadd) x += __ldg(p.rowadd + static_cast<int64_t>(row_mod) * p.N + col);
+  if (p.rowgrp) x = fmaf(__ldg(p.rowgrp + static_cast<int64_t>(row_grp) * p.N + col), p.rowgrp_scale, x);
+  const int64_t off = row * p.ldo + col;
+  if (p.aux_out) p.aux_out[off] = __float2bfloat16(x);
+  x = apply_act<true>(x, p.act);
+  if (p.aux_in) x *= gelu_bwd<true>(__bfloat162float(p.aux_in[off]));
+  if (p.resid) x += __bfloat162float(p.resid[off]);
+  if (p.out_bf16) p.out_bf16[off] = __float2bfloat16(x);
+  if (p.out_f32) {
+    if (p.atomic) atomicAdd(p.out_f32 + off, x);
+    else p.out_f32[off] = x;
+  }
+}
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms: 1 KB aligned
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tmem_full_bar[s]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int num_items = p.tiles_m * p.tiles_n * p.ksplit;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        const int m0 = it.m_blk * BM, n0 = it.n_blk * BN;
+        for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          mbar_arrive_expect_tx(fb, STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_BYTES;
+          const int k0 = kb * BK;
+          if (A_MN == 0) {
+            tma_load_2d(a_dst, &tmA, fb, k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(b_dst, &tmB, fb, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = umma_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
+            const uint64_t bd = umma_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
+            umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > it.kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));            // smem slot reusable when MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&tmem_full_bar[as]));             // accumulator complete
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                                    // == warp % 4: TMEM lane quarter
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const Item it = decode_item(p, item);
+      const int64_t row = static_cast<int64_t>(it.m_blk) * BM + q * 32 + lane;
+      const int n0 = it.n_blk * BN;
+      const bool row_ok = row < p.M;
+      uint32_t row_mod = 0, row_grp = 0;
+      if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
+      if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
+      mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_addr + c * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          if (p.vec_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col < p.N) epilogue_vec8(p, &v[g * 8], row, col, row_mod, row_grp);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col < p.N) epilogue_scalar(p, __uint_as_float(v[j]), row, col, row_mod, row_grp);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+struct DebugOverrides {
+  int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0;
+};
+DebugOverrides g_dbg;
+
+template <int A_MN, int B_MN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      sc_set_error("sc_gemm_bf16: cannot set %d B dynamic smem: %s", SMEM_BYTES, cudaGetErrorString(e));
+      return SC_E_LAUNCH;
+    }
+    attr_set = true;
+  }
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_gemm_bf16");
+  return SC_OK;
+}
+
+}  // namespace
+
+extern "C" int sc_debug_set(const char* key, int64_t value) {
+  if (!key) return SC_E_SHAPE;
+  if (!strcmp(key, "a_lbo")) g_dbg.a_lbo = value;
+  else if (!strcmp(key, "a_sbo")) g_dbg.a_sbo = value;
+  else if (!strcmp(key, "a_kstep")) g_dbg.a_kstep = value;
+  else if (!strcmp(key, "b_lbo")) g_dbg.b_lbo = value;
+  else if (!strcmp(key, "b_sbo")) g_dbg.b_sbo = value;
+  else if (!strcmp(key, "b_kstep")) g_dbg.b_kstep = value;
+  else if (!strcmp(key, "max_ctas")) g_dbg.max_ctas = value;
+  else if (!strcmp(key, "reset")) g_dbg = DebugOverrides();
+  else {
+    sc_set_error("sc_debug_set: unknown key %s", key);
+    return SC_E_SHAPE;
+  }
+  return SC_OK;
+}
+
+extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int a_mn,
+                            int b_mn, int64_t lda, int64_t ldb, const sc_gemm_epilogue* epi, int ksplit,
+                            void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(A && B && epi, SC_E_SHAPE, "sc_gemm_bf16: null operand");
+  SC_REQUIRE(M > 0 && N > 0 && K > 0, SC_E_SHAPE, "sc_gemm_bf16: empty problem M=%lld N=%lld K=%lld",
+             (long long)M, (long long)N, (long long)K);
+  SC_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SC_E_SHAPE, "sc_gemm_bf16: dims must fit int32");
+  SC_REQUIRE((a_mn == 0 || a_mn == 1) && (b_mn == 0 || b_mn == 1), SC_E_SHAPE, "sc_gemm_bf16: a_mn/b_mn must be 0/1");
+  SC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, SC_E_ALIGN, "sc_gemm_bf16: lda=%lld ldb=%lld must be multiples of 8",
+             (long long)lda, (long long)ldb);
+  SC_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), SC_E_SHAPE, "sc_gemm_bf16: leading dimension too small");
+  SC_REQUIRE(sc_aligned16(A) && sc_aligned16(B), SC_E_ALIGN, "sc_gemm_bf16: A/B must be 16-byte aligned");
+  SC_REQUIRE(epi->out_bf16 || epi->out_f32, SC_E_SHAPE, "sc_gemm_bf16: no output pointer");
+  SC_REQUIRE(epi->ldo >= N, SC_E_SHAPE, "sc_gemm_bf16: ldo < N");
+  SC_REQUIRE(!epi->rowadd || epi->rowadd_period > 0, SC_E_SHAPE, "sc_gemm_bf16: rowadd_period must be > 0");
+  SC_REQUIRE(!epi->rowgrp || epi->rowgrp_size > 0, SC_E_SHAPE, "sc_gemm_bf16: rowgrp_size must be > 0");
+  SC_REQUIRE(epi->act >= SC_ACT_NONE && epi->act <= SC_ACT_TANH, SC_E_SHAPE, "sc_gemm_bf16: bad act");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = static_cast<int>((M + BM - 1) / BM);
+  p.tiles_n = static_cast<int>((N + BN - 1) / BN);
+  p.kb_total = static_cast<int>((K + BK - 1) / BK);
+  int ks = ksplit < 1 ? 1 : ksplit;
+  if (ks > p.kb_total) ks = p.kb_total;
+  p.kb_per_split = (p.kb_total + ks - 1) / ks;
+  p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
+  if (p.ksplit > 1) {
+    SC_REQUIRE(epi->atomic && epi->out_f32 && !epi->out_bf16 && !epi->bias && !epi->rowadd && !epi->rowgrp &&
+                   !epi->resid && !epi->aux_in && !epi->aux_out && epi->act == SC_ACT_NONE,
+               SC_E_SHAPE, "sc_gemm_bf16: ksplit > 1 needs a pure atomic fp32 epilogue");
+  }
+  p.bias = epi->bias;
+  p.rowadd = epi->rowadd;
+  p.rowadd_period = static_cast<uint32_t>(epi->rowadd_period);
+  p.rowgrp = epi->rowgrp;
+  p.rowgrp_size = static_cast<uint32_t>(epi->rowgrp_size);
+  p.rowgrp_scale = epi->rowgrp_scale;
+  p.alpha = epi->alpha;
+  p.resid = static_cast<const bf16*>(epi->resid);
+  p.aux_in = static_cast<const bf16*>(epi->aux_in);
+  p.aux_out = static_cast<bf16*>(epi->aux_out);
+  p.out_bf16 = static_cast<bf16*>(epi->out_bf16);
+  p.out_f32 = epi->out_f32;
+  p.ldo = epi->ldo;
+  p.act = epi->act;
+  p.atomic = epi->atomic;
+  p.vec_ok = (N % 8 == 0) && (epi->ldo % 8 == 0) && sc_aligned16(epi->bias) && sc_aligned16(epi->rowadd) &&
+             sc_aligned16(epi->rowgrp) && sc_aligned16(epi->resid) && sc_aligned16(epi->aux_in) &&
+             sc_aligned16(epi->aux_out) && sc_aligned16(epi->out_bf16) && sc_aligned16(epi->out_f32);
+
+  // UMMA shared-memory descriptor fields
+  p.a_lbo = a_mn ? CHUNK_BYTES : 16;   p.a_sbo = 1024;   p.a_kstep = a_mn ? 2048 : 32;
+  p.b_lbo = b_mn ? CHUNK_BYTES : 16;   p.b_sbo = 1024;   p.b_kstep = b_mn ? 2048 : 32;
+  if (g_dbg.a_lbo) p.a_lbo = (uint32_t)g_dbg.a_lbo;
+  if (g_dbg.a_sbo) p.a_sbo = (uint32_t)g_dbg.a_sbo;
+  if (g_dbg.a_kstep) p.a_kstep = (uint32_t)g_dbg.a_kstep;
+  if (g_dbg.b_lbo) p.b_lbo = (uint32_t)g_dbg.b_lbo;
+  if (g_dbg.b_sbo) p.b_sbo = (uint32_t)g_dbg.b_sbo;
+  if (g_dbg.b_kstep) p.b_kstep = (uint32_t)g_dbg.b_kstep;
+
+  CUtensorMap tmA, tmB;
+  if (a_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
+  else           rc = sc_encode_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK);
+  if (rc != SC_OK) return rc;
+  if (b_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, BN);
+  else           rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK);
+  if (rc != SC_OK) return rc;
+
+  const long long items = 1LL * p.tiles_m * p.tiles_n * p.ksplit;
+  int grid = sc_num_sms();
+  if (g_dbg.max_ctas > 0 && grid > g_dbg.max_ctas) grid = (int)g_dbg.max_ctas;
+  if (items < grid) grid = (int)items;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a_mn == 0 && b_mn == 0) return launch<0, 0>(tmA, tmB, p, grid, st);
+  if (a_mn == 0 && b_mn == 1) return launch<0, 1>(tmA, tmB, p, grid, st);
+  if (a_mn == 1 && b_mn == 1) return launch<1, 1>(tmA, tmB, p, grid, st);
+  return launch<1, 0>(tmA, tmB, p, grid, st);
+}

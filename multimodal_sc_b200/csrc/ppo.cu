@@ -1,0 +1,457 @@
+// ppo.cu — actor-critic output layer, action sampling, GAE reverse scan, PPO clipped loss
+// (forward + backward fused) and the fused flat Adam.  SPEC v0 rows a7, a8, a9, a10.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxA1 = 16;     // actions + 1 (value) supported by the register-resident heads
+
+__device__ __forceinline__ void load8f(const bf16* p, float (&x)[8]) {
+  uint4 w = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(w.x), b = unpack_bf16(w.y), c = unpack_bf16(w.z), d = unpack_bf16(w.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&x)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------
+// heads: warp per sample, lane owns 8 trunk features (D = 256); A1 <= 16 outputs
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+heads_fwd_kernel(const bf16* __restrict__ trunk, const float* __restrict__ W, const float* __restrict__ bias,
+                 float* __restrict__ out, int64_t B, int D, int A1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    float acc[kMaxA1];
+#pragma unroll
+    for (int j = 0; j < kMaxA1; ++j) acc[j] = 0.f;
+    for (int c = 0; c < D; c += 256) {
+      float t[8];
+      load8f(trunk + b * D + c + lane * 8, t);
+#pragma unroll
+      for (int j = 0; j < kMaxA1; ++j) {
+        if (j < A1) {
+          float w[8];
+          load8f(W + static_cast<int64_t>(j) * D + c + lane * 8, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j] = fmaf(t[i], w[i], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxA1; ++j) {
+      if (j < A1) {
+        const float s = warp_sum(acc[j]);
+        if (lane == 0) out[b * A1 + j] = s + bias[j];
+      }
+    }
+  }
+}
+
+// dtrunk_pre = (dho W) (1 - trunk^2); dW += dho^T trunk; dbias += colsum(dho).  D == 256.
+__global__ void __launch_bounds__(kThreads)
+heads_bwd_kernel(const float* __restrict__ dho, const bf16* __restrict__ trunk, const float* __restrict__ W,
+                 bf16* __restrict__ dtrunk_pre, float* __restrict__ dW, float* __restrict__ dbias, int64_t B,
+                 int A1) {
+  constexpr int D = 256;
+  __shared__ float sW[kMaxA1 * D];
+  __shared__ float sdW[kMaxA1 * D];
+  __shared__ float sdb[kMaxA1];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < A1 * D; i += blockDim.x) { sW[i] = W[i]; sdW[i] = 0.f; }
+  if (threadIdx.x < kMaxA1) sdb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float adw[kMaxA1][8];
+  float adb = 0.f;                                   // lane j accumulates dbias[j]
+#pragma unroll
+  for (int j = 0; j < kMaxA1; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) adw[j][i] = 0.f;
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    float t[8], dt[8];
+    load8f(trunk + b * D + lane * 8, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dt[i] = 0.f;
+    const float mine = lane < A1 ? dho[b * A1 + lane] : 0.f;
+    adb += mine;
+#pragma unroll
+    for (int j = 0; j < kMaxA1; ++j) {
+      if (j < A1) {
+        const float g = __shfl_sync(0xffffffffu, mine, j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          dt[i] = fmaf(g, sW[j * D + lane * 8 + i], dt[i]);
+          adw[j][i] = fmaf(g, t[i], adw[j][i]);
+        }
+      }
+    }
+    uint4 o = make_uint4(pack_bf16(dt[0] * (1.f - t[0] * t[0]), dt[1] * (1.f - t[1] * t[1])),
+                         pack_bf16(dt[2] * (1.f - t[2] * t[2]), dt[3] * (1.f - t[3] * t[3])),
+                         pack_bf16(dt[4] * (1.f - t[4] * t[4]), dt[5] * (1.f - t[5] * t[5])),
+                         pack_bf16(dt[6] * (1.f - t[6] * t[6]), dt[7] * (1.f - t[7] * t[7])));
+    *reinterpret_cast<uint4*>(dtrunk_pre + b * D + lane * 8) = o;
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxA1; ++j) {
+    if (j < A1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sdW[j * D + lane * 8 + i], adw[j][i]);
+    }
+  }
+  if (lane < A1) atomicAdd(&sdb[lane], adb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < A1 * D; i += blockDim.x) atomicAdd(dW + i, sdW[i]);
+  if (threadIdx.x < A1) atomicAdd(dbias + threadIdx.x, sdb[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// inverse-CDF sampling, fp64 cdf in index order (SPEC v0 a7); logp in fp32
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+sample_kernel(const float* __restrict__ ho, int ld, const float* __restrict__ u, int64_t* __restrict__ action,
+              float* __restrict__ logp, int64_t B, int A) {
+  for (int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; b < B;
+       b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float* l = ho + b * ld;
+    float mx = l[0];
+    for (int j = 1; j < A; ++j) mx = fmaxf(mx, l[j]);
+    double den = 0.0;
+    for (int j = 0; j < A; ++j) den += exp(static_cast<double>(l[j]) - static_cast<double>(mx));
+    const double uu = static_cast<double>(u[b]);
+    double cdf = 0.0;
+    int a = 0;
+    for (int j = 0; j < A; ++j) {
+      cdf += exp(static_cast<double>(l[j]) - static_cast<double>(mx)) / den;
+      a += (cdf <= uu) ? 1 : 0;
+    }
+    a = min(a, A - 1);
+    float se = 0.f;
+    for (int j = 0; j < A; ++j) se += expf(l[j] - mx);
+    action[b] = a;
+    logp[b] = (l[a] - mx) - logf(se);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GAE: A_t = delta_t + c_t A_{t+1} is a composition of affine maps f_t(x) = delta_t + c_t x.
+// Block = 32 warps = 32 environments; a [TC x 32] tile of r, v, d is loaded coalesced into
+// smem, then warp w scans environment w: lane l holds timestep l of each 32-step segment and
+// a suffix scan of (a, b) pairs with __shfl_down composes the maps; segments are chained from
+// the end of the rollout backwards with the carried A_{t+1}.
+// ------------------------------------------------------------------------------------------
+constexpr int kGaeTC = 64;
+__global__ void __launch_bounds__(1024)
+gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ done,
+           const float* __restrict__ last_value, float* __restrict__ adv, float* __restrict__ ret,
+           double* __restrict__ sums, int T, int64_t N, float gamma, float lam) {
+  __shared__ float sr[kGaeTC][33], sv[kGaeTC + 1][33], sd[kGaeTC][33], sa[kGaeTC][33];
+  __shared__ double ssum[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * 32;
+  if (threadIdx.x < 2) ssum[threadIdx.x] = 0.0;
+  const int64_t n_col = n0 + lane;                   // column this lane loads/stores
+  const int64_t n_env = n0 + warp;                   // environment this warp scans
+  float carry_a = 0.f;                               // A_{t+1} entering the current chunk
+  double acc_s = 0.0, acc_q = 0.0;
+  for (int t_hi = T; t_hi > 0; t_hi -= kGaeTC) {
+    const int t_lo = max(0, t_hi - kGaeTC);
+    const int tc = t_hi - t_lo;
+    __syncthreads();
+    for (int t = warp; t < tc; t += 32) {
+      const bool ok = n_col < N;
+      const int64_t o = static_cast<int64_t>(t_lo + t) * N + n_col;
+      sr[t][lane] = ok ? rew[o] : 0.f;
+      sv[t][lane] = ok ? val[o] : 0.f;
+      sd[t][lane] = ok ? done[o] : 0.f;
+    }
+    if (warp == 0) {                                 // V_{t_hi}: next chunk's first value or last_value
+      float vn = 0.f;
+      if (n_col < N) vn = (t_hi == T) ? last_value[n_col] : val[static_cast<int64_t>(t_hi) * N + n_col];
+      sv[tc][lane] = vn;
+    }
+    __syncthreads();
+    // scan segments of 32 timesteps from the end of the chunk backwards
+    for (int seg_hi = tc; seg_hi > 0; seg_hi -= 32) {
+      const int seg_lo = max(0, seg_hi - 32);
+      const int t = seg_lo + lane;
+      float a = 1.f, b = 0.f;                        // identity map for lanes past the segment
+      if (t < seg_hi) {
+        const float nd = 1.f - sd[t][warp];
+        b = sr[t][warp] + gamma * sv[t + 1][warp] * nd - sv[t][warp];      // delta_t
+        a = gamma * lam * nd;                                               // c_t
+      }
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const float a2 = __shfl_down_sync(0xffffffffu, a, off);
+        const float b2 = __shfl_down_sync(0xffffffffu, b, off);
+        if (lane + off < 32) { b = fmaf(a, b2, b); a *= a2; }
+      }
+      const float A = fmaf(a, carry_a, b);
+      if (t < seg_hi) sa[t][warp] = A;
+      carry_a = __shfl_sync(0xffffffffu, A, 0);
+    }
+    __syncthreads();
+    for (int t = warp; t < tc; t += 32) {
+      if (n_col < N) {
+        const int64_t o = static_cast<int64_t>(t_lo + t) * N + n_col;
+        const float A = sa[t][lane];
+        adv[o] = A;
+        ret[o] = A + sv[t][lane];
+        acc_s += A;
+        acc_q += static_cast<double>(A) * A;
+      }
+    }
+  }
+  (void)n_env;
+  if (sums) {
+    for (int o = 16; o > 0; o >>= 1) {
+      acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+      acc_q += __shfl_xor_sync(0xffffffffu, acc_q, o);
+    }
+    if (lane == 0) { atomicAdd(&ssum[0], acc_s); atomicAdd(&ssum[1], acc_q); }
+    __syncthreads();
+    if (threadIdx.x < 2) atomicAdd(sums + threadIdx.x, ssum[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+adv_normalize_kernel(float* __restrict__ adv, const double* __restrict__ sums, int64_t count, int64_t n,
+                     float eps) {
+  const double mean = sums[0] / static_cast<double>(count);
+  double var = sums[1] / static_cast<double>(count) - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  const float m = static_cast<float>(mean);
+  const float inv = 1.0f / (static_cast<float>(sqrt(var)) + eps);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    adv[i] = (adv[i] - m) * inv;
+}
+
+// ------------------------------------------------------------------------------------------
+// PPO clipped loss, forward + backward fused: one thread per sample, block reduce of 5 stats
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+ppo_loss_kernel(const float* __restrict__ ho, int ld, const int64_t* __restrict__ actions,
+                const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
+                float* __restrict__ dho, float* __restrict__ stats, int64_t M, int A, float clip_eps, float c_v,
+                float c_ent, float inv_m) {
+  __shared__ float red[5][kThreads / 32];
+  float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < M;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float* l = ho + i * ld;
+    float lg[kMaxA1];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMaxA1; ++j)
+      if (j < A) { lg[j] = l[j]; mx = fmaxf(mx, lg[j]); }
+    float se = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxA1; ++j)
+      if (j < A) se += expf(lg[j] - mx);
+    const float lse = mx + logf(se);
+    const int a = static_cast<int>(actions[i]);
+    float ent = 0.f, logp = 0.f;
+    float p[kMaxA1], lp[kMaxA1];
+#pragma unroll
+    for (int j = 0; j < kMaxA1; ++j)
+      if (j < A) {
+        lp[j] = lg[j] - lse;
+        p[j] = expf(lp[j]);
+        ent -= p[j] * lp[j];
+        if (j == a) logp = lp[j];
+      }
+    const float Ad = adv[i];
+    const float ratio = expf(logp - logp_old[i]);
+    const float s1 = ratio * Ad;
+    const float rc = fminf(fmaxf(ratio, 1.f - clip_eps), 1.f + clip_eps);
+    const float s2 = rc * Ad;
+    const bool inside = (ratio >= 1.f - clip_eps) && (ratio <= 1.f + clip_eps);
+    const float gmin = (inside || s1 < s2) ? Ad : 0.f;          // d min(s1,s2) / d ratio
+    const float v = l[A];
+    const float dv = v - ret[i];
+    st[0] += -fminf(s1, s2);
+    st[1] += 0.5f * dv * dv;
+    st[2] += ent;
+    st[3] += logp_old[i] - logp;
+    st[4] += (fabsf(ratio - 1.f) > clip_eps) ? 1.f : 0.f;
+    // d total / d logit_j = inv_m * [ -gmin*ratio*(1[j==a] - p_j) + c_ent * p_j (lp_j + ent) ]
+    const float gp = -gmin * ratio;
+    float* d = dho + i * ld;
+#pragma unroll
+    for (int j = 0; j < kMaxA1; ++j)
+      if (j < A) d[j] = inv_m * (gp * ((j == a ? 1.f : 0.f) - p[j]) + c_ent * p[j] * (lp[j] + ent));
+    d[A] = inv_m * c_v * dv;
+  }
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const float w = warp_sum(st[s]);
+    if ((threadIdx.x & 31) == 0) red[s][threadIdx.x >> 5] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += red[threadIdx.x][w];
+    atomicAdd(stats + threadIdx.x, t * inv_m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused flat Adam (torch.optim.Adam arithmetic order) + bf16 shadow refresh
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            bf16* __restrict__ pb, int64_t n, float step_size, float b1, float b2, float eps, float inv_sqrt_bc2,
+            float grad_scale) {
+  const int64_t n4 = n / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; float* G = &gg.x; float* Mo = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gs = G[j] * grad_scale;
+      Mo[j] = Mo[j] + (1.f - b1) * (gs - Mo[j]);            // lerp form used by torch
+      V[j] = b2 * V[j] + (1.f - b2) * gs * gs;
+      const float denom = sqrtf(V[j]) * inv_sqrt_bc2 + eps;
+      P[j] = P[j] - step_size * (Mo[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (pb) reinterpret_cast<uint2*>(pb)[i] = make_uint2(pack_bf16(pp.x, pp.y), pack_bf16(pp.z, pp.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = n4 * 4 + threadIdx.x;
+    const float gs = g[i] * grad_scale;
+    const float mo = m[i] + (1.f - b1) * (gs - m[i]);
+    const float vo = b2 * v[i] + (1.f - b2) * gs * gs;
+    const float po = p[i] - step_size * (mo / (sqrtf(vo) * inv_sqrt_bc2 + eps));
+    m[i] = mo; v[i] = vo; p[i] = po;
+    if (pb) pb[i] = __float2bfloat16(po);
+  }
+}
+
+inline int grid_for(int64_t work_items, int per_block, int per_sm) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = static_cast<int64_t>(sc_num_sms()) * per_sm;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sc_heads_fwd(const void* trunk, const float* W, const float* bias, float* head_out, int64_t B, int D, int A1,
+                 void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(trunk && W && bias && head_out, SC_E_SHAPE, "sc_heads_fwd: null pointer");
+  SC_REQUIRE(B > 0 && D % 256 == 0 && A1 >= 2 && A1 <= kMaxA1, SC_E_SHAPE, "sc_heads_fwd: B=%lld D=%d A1=%d",
+             (long long)B, D, A1);
+  SC_REQUIRE(sc_aligned16(trunk) && sc_aligned16(W), SC_E_ALIGN, "sc_heads_fwd: unaligned pointer");
+  heads_fwd_kernel<<<grid_for(B, 8, 8), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)trunk, W, bias, head_out,
+                                                                            B, D, A1);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_heads_fwd");
+  return SC_OK;
+}
+
+int sc_heads_bwd(const float* dho, const void* trunk, const float* W, void* dtrunk_pre, float* dW, float* dbias,
+                 int64_t B, int D, int A1, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(dho && trunk && W && dtrunk_pre && dW && dbias, SC_E_SHAPE, "sc_heads_bwd: null pointer");
+  SC_REQUIRE(B > 0 && D == 256 && A1 >= 2 && A1 <= kMaxA1, SC_E_SHAPE, "sc_heads_bwd: B=%lld D=%d A1=%d (D must be 256)",
+             (long long)B, D, A1);
+  SC_REQUIRE(sc_aligned16(trunk) && sc_aligned16(dtrunk_pre), SC_E_ALIGN, "sc_heads_bwd: unaligned pointer");
+  heads_bwd_kernel<<<grid_for(B, 64, 1), kThreads, 0, (cudaStream_t)stream>>>(dho, (const bf16*)trunk, W,
+                                                                             (bf16*)dtrunk_pre, dW, dbias, B, A1);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_heads_bwd");
+  return SC_OK;
+}
+
+int sc_sample_action(const float* head_out, int ld, const float* u, int64_t* action, float* logp, int64_t B, int A,
+                     void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(head_out && u && action && logp, SC_E_SHAPE, "sc_sample_action: null pointer");
+  SC_REQUIRE(B > 0 && A >= 1 && ld >= A, SC_E_SHAPE, "sc_sample_action: B=%lld A=%d ld=%d", (long long)B, A, ld);
+  sample_kernel<<<grid_for(B, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(head_out, ld, u, action, logp, B, A);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_sample_action");
+  return SC_OK;
+}
+
+int sc_gae(const float* rewards, const float* values, const float* dones, const float* last_value, float* adv,
+           float* ret, double* sums, int T, int64_t N, float gamma, float lam, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(rewards && values && dones && last_value && adv && ret, SC_E_SHAPE, "sc_gae: null pointer");
+  SC_REQUIRE(T > 0 && N > 0, SC_E_SHAPE, "sc_gae: T=%d N=%lld", T, (long long)N);
+  const int grid = (int)((N + 31) / 32);
+  gae_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_value, adv, ret, sums, T, N,
+                                                      gamma, lam);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_gae");
+  return SC_OK;
+}
+
+int sc_adv_normalize(float* adv, const double* sums, int64_t count, int64_t n, float eps, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(adv && sums && count > 0 && n > 0, SC_E_SHAPE, "sc_adv_normalize: bad arguments");
+  adv_normalize_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(adv, sums, count, n, eps);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_adv_normalize");
+  return SC_OK;
+}
+
+int sc_ppo_loss(const float* head_out, int ld, const int64_t* actions, const float* logp_old, const float* adv,
+                const float* ret, float* dho, float* stats, int64_t M, int A, float clip_eps, float c_v,
+                float c_ent, float inv_m, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(head_out && actions && logp_old && adv && ret && dho && stats, SC_E_SHAPE, "sc_ppo_loss: null pointer");
+  SC_REQUIRE(M > 0 && A >= 1 && A < kMaxA1 && ld >= A + 1, SC_E_SHAPE, "sc_ppo_loss: M=%lld A=%d ld=%d",
+             (long long)M, A, ld);
+  ppo_loss_kernel<<<grid_for(M, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(
+      head_out, ld, actions, logp_old, adv, ret, dho, stats, M, A, clip_eps, c_v, c_ent, inv_m);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_ppo_loss");
+  return SC_OK;
+}
+
+int sc_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                 float beta2, float eps, int64_t step, float grad_scale, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(p && g && m && v && n > 0 && step >= 1, SC_E_SHAPE, "sc_adam_flat: bad arguments");
+  SC_REQUIRE(sc_aligned16(p) && sc_aligned16(g) && sc_aligned16(m) && sc_aligned16(v) &&
+                 (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
+             SC_E_ALIGN, "sc_adam_flat: unaligned pointer");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  adam_kernel<<<grid_for(n / 4 + 1, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, (bf16*)p_bf16, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_adam_flat");
+  return SC_OK;
+}
+
+}  // extern "C"

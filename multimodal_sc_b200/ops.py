@@ -1,0 +1,200 @@
+"""Tensor-level wrappers over the C ABI (one Python function per `sc_*` entry point).
+
+These do shape bookkeeping only; all arithmetic happens in libsemcom_sm100.so on the
+current CUDA stream.  Inputs must already live on the GPU; nothing here falls back to torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmEpilogue, SC_ACT, SC_CH, check, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.SemcomError("semcom ops need CUDA tensors (no CPU fallback)")
+
+
+def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, rowgrp_size=0,
+         rowgrp_scale=1.0, alpha=1.0, resid=None, aux_in=None, aux_out=None, out=None,
+         out_f32=None, act=None, atomic=False, ksplit=1):
+    """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of sc_gemm_bf16.
+
+    a_mn=False: A is [M,K]; a_mn=True: A is [K,M].  b_mn=False: B is [N,K]; b_mn=True: B is [K,N].
+    `out` (bf16 [M,N]) and/or `out_f32` (fp32 [M,N]) receive the result; both may be strided
+    views with the same leading dimension."""
+    _cuda(A, B)
+    assert A.dtype == BF16 and B.dtype == BF16 and A.dim() == 2 and B.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    if a_mn:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    if b_mn:
+        Kb, N = B.shape
+    else:
+        N, Kb = B.shape
+    assert K == Kb, f"K mismatch {K} vs {Kb}"
+    o = out if out is not None else out_f32
+    assert o is not None and o.shape == (M, N) and o.stride(1) == 1
+    ldo = o.stride(0)
+    for t in (out, out_f32, resid, aux_in, aux_out):
+        if t is not None:
+            assert t.shape == (M, N) and t.stride(1) == 1 and t.stride(0) == ldo
+    if out is not None:
+        assert out.dtype == BF16
+    if out_f32 is not None:
+        assert out_f32.dtype == F32
+    epi = GemmEpilogue(
+        bias=ptr(bias), rowadd=ptr(rowadd), rowadd_period=(rowadd.shape[0] if rowadd is not None else 0),
+        rowgrp=ptr(rowgrp), rowgrp_size=rowgrp_size, rowgrp_scale=rowgrp_scale, alpha=alpha,
+        resid=ptr(resid), aux_in=ptr(aux_in), aux_out=ptr(aux_out), out_bf16=ptr(out),
+        out_f32=ptr(out_f32), ldo=ldo, act=SC_ACT[act], atomic=int(atomic))
+    rc = _lib.load().sc_gemm_bf16(ptr(A), ptr(B), M, N, K, int(a_mn), int(b_mn), A.stride(0),
+                                  B.stride(0), C.byref(epi), ksplit, stream_ptr())
+    check(rc, "sc_gemm_bf16")
+    return o
+
+
+def debug_set(key: str, value: int):
+    check(_lib.load().sc_debug_set(key.encode(), value), "sc_debug_set")
+
+
+def patchify(img, patch: int, out=None):
+    """img fp32 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P]"""
+    _cuda(img)
+    assert img.dtype == F32 and img.is_contiguous()
+    B, Cc, H, W = img.shape
+    T = (H // patch) * (W // patch)
+    if out is None:
+        out = torch.empty(B * T, Cc * patch * patch, device=img.device, dtype=BF16)
+    check(_lib.load().sc_patchify_bf16(ptr(img), ptr(out), B, Cc, H, W, patch, stream_ptr()), "sc_patchify_bf16")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, y=None, mean=None, rstd=None):
+    _cuda(x, gamma, beta)
+    assert x.is_contiguous() and x.dtype in (BF16, F32)
+    D = x.shape[-1]
+    M = x.numel() // D
+    if y is None:
+        y = torch.empty_like(x)
+    check(_lib.load().sc_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, eps,
+                                       int(x.dtype == F32), stream_ptr()), "sc_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, dx=None, colsum=None):
+    _cuda(dy, x)
+    assert dy.is_contiguous() and x.is_contiguous() and dy.dtype == x.dtype
+    D = x.shape[-1]
+    M = x.numel() // D
+    if dx is None:
+        dx = torch.empty_like(x)
+    check(_lib.load().sc_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx),
+                                       ptr(dgamma), ptr(dbeta), ptr(colsum), M, D, int(x.dtype == F32),
+                                       stream_ptr()), "sc_layernorm_bwd")
+    return dx
+
+
+def colsum(x, out):
+    """out[n] += sum_m x[m, n]; x bf16 [M,N] (row stride allowed)"""
+    _cuda(x, out)
+    assert x.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32
+    M, N = x.shape
+    check(_lib.load().sc_colsum_bf16(ptr(x), ptr(out), M, N, x.stride(0), stream_ptr()), "sc_colsum_bf16")
+    return out
+
+
+def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, fading=None, eps=1e-12,
+                      y_f32=None, y_bf16=None, scale=None, z_strides=None, y_strides=None):
+    """z fp32 logical [B,2,k] addressed with z_strides=(sb, sm) (default: contiguous [B,2,k]).
+    Returns (y_f32, y_bf16, scale)."""
+    _cuda(z)
+    assert z.dtype == F32
+    if z_strides is None:
+        B, _, k = z.shape
+        z_strides = (z.stride(0), z.stride(1))
+    else:
+        B, k = z_strides[2], z_strides[3]
+        z_strides = z_strides[:2]
+    if y_strides is None:
+        y_strides = (2 * k, k)
+    if y_f32 is None and y_bf16 is None:
+        y_f32 = torch.empty(B, 2, k, device=z.device, dtype=F32)
+    if scale is None:
+        scale = torch.empty(B, 2, device=z.device, dtype=F32)
+    snr_t, snr_s = (snr_db, 0.0) if torch.is_tensor(snr_db) else (None, float(snr_db))
+    if snr_t is not None:
+        assert snr_t.dtype == F32 and snr_t.numel() == B and snr_t.is_cuda
+    check(_lib.load().sc_pnorm_channel_fwd(ptr(z), z_strides[0], z_strides[1], ptr(y_f32), ptr(y_bf16),
+                                           y_strides[0], y_strides[1], ptr(scale), B, k, SC_CH[kind],
+                                           ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1), sample_offset,
+                                           ptr(noise), ptr(fading), eps, stream_ptr()), "sc_pnorm_channel_fwd")
+    return y_f32, y_bf16, scale
+
+
+def pnorm_channel_bwd(dy, z, scale, kind, snr_db, *, seed=0, sample_offset=0, fading=None, dz_f32=None,
+                      dz_bf16=None, z_strides=None, y_strides=None):
+    _cuda(dy, z, scale)
+    assert dy.dtype == F32 and z.dtype == F32
+    if z_strides is None:
+        B, _, k = z.shape
+        z_strides = (z.stride(0), z.stride(1))
+    else:
+        B, k = z_strides[2], z_strides[3]
+        z_strides = z_strides[:2]
+    if y_strides is None:
+        y_strides = (2 * k, k)
+    if dz_f32 is None and dz_bf16 is None:
+        dz_f32 = torch.empty(B, 2, k, device=z.device, dtype=F32)
+    snr_t, snr_s = (snr_db, 0.0) if torch.is_tensor(snr_db) else (None, float(snr_db))
+    check(_lib.load().sc_pnorm_channel_bwd(ptr(dy), y_strides[0], y_strides[1], ptr(z), z_strides[0],
+                                           z_strides[1], ptr(scale), ptr(dz_f32), ptr(dz_bf16), B, k,
+                                           SC_CH[kind], ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1),
+                                           sample_offset, ptr(fading), stream_ptr()), "sc_pnorm_channel_bwd")
+    return dz_f32, dz_bf16
+
+
+def philox_words(n_quads, stream_id, seed, quad_offset=0, device="cuda"):
+    out = torch.empty(n_quads, 4, device=device, dtype=torch.int32)
+    check(_lib.load().sc_philox_words(ptr(out), n_quads, stream_id, int(seed) & (2 ** 64 - 1), quad_offset,
+                                      stream_ptr()), "sc_philox_words")
+    return out
+
+
+def meanpool_fwd(x, out_bf16=None, out_f32=None):
+    _cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 3
+    B, S, D = x.shape
+    if out_bf16 is None and out_f32 is None:
+        out_bf16 = torch.empty(B, D, device=x.device, dtype=BF16)
+    check(_lib.load().sc_meanpool_fwd(ptr(x), ptr(out_bf16), ptr(out_f32), B, S, D, stream_ptr()),
+          "sc_meanpool_fwd")
+    return out_bf16 if out_bf16 is not None else out_f32
+
+
+def mse_fwd_bwd(r, t, loss_accum, dr=None, grad_scale=1.0):
+    """loss_accum[0] += mean((r-t)^2); dr = bf16(2 (r-t) grad_scale)"""
+    _cuda(r, t, loss_accum)
+    assert r.dtype == BF16 and t.dtype == BF16 and r.is_contiguous() and t.is_contiguous()
+    n = r.numel()
+    check(_lib.load().sc_mse_fwd_bwd(ptr(r), ptr(t), ptr(loss_accum), ptr(dr), n, 1.0 / n, grad_scale,
+                                     stream_ptr()), "sc_mse_fwd_bwd")
+    return dr
+
+
+def cast_f32_bf16(src, dst=None):
+    _cuda(src)
+    assert src.dtype == F32 and src.is_contiguous()
+    if dst is None:
+        dst = torch.empty_like(src, dtype=BF16)
+    check(_lib.load().sc_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "sc_cast_f32_bf16")
+    return dst

@@ -10,6 +10,9 @@ Revisions relative to SURVEY.md §8 (allowed "once in PR1, then frozen"):
     bit-identical between numpy, torch-CPU and the CUDA kernels.
   * power normalisation is z * rsqrt(mean(z^2) + 1e-12) (eps inside the sqrt, on
     the mean rather than the sum).
+  * GELU is the tanh form 0.5 x (1 + tanh(0.79788456 (x + 0.044715 x^3))) (one MUFU.TANH per
+    element in the GEMM epilogue instead of an erf polynomial; the D=256 GEMMs leave ~10
+    issue slots per output element before the epilogue, not the tensor pipe, bounds them).
   * every encoder and the decoder end with a LayerNorm (pre-LN stacks need one);
     the semantic target of L_sem is that final-LN encoder feature.
 """

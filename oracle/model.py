@@ -27,7 +27,7 @@ def patchify(img: torch.Tensor, p: int) -> torch.Tensor:
 
 
 class Block(nn.Module):
-    """pre-LN transformer block: x += proj(attn(ln1 x)); x += fc2(gelu(fc1(ln2 x)))."""
+    """pre-LN transformer block: x += proj(attn(ln1 x)); x += fc2(gelu_tanh(fc1(ln2 x)))."""
 
     def __init__(self, spec: SpecV0):
         super().__init__()
@@ -50,7 +50,7 @@ class Block(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = x + self.proj(self.attention(self.ln1(x)))
-        x = x + self.fc2(F.gelu(self.fc1(self.ln2(x))))
+        x = x + self.fc2(F.gelu(self.fc1(self.ln2(x)), approximate="tanh"))
         return x
 
 

@@ -1,0 +1,176 @@
+"""GPU parity: memory-bound sm_100a kernels (through the C ABI) vs the CPU oracle.
+
+Tolerances: fp32 kernels rtol 1e-5 (+ a small atol where a reduction reorders sums),
+bf16-I/O kernels rtol 2e-2 relative to the output scale, integer streams bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from multimodal_sc_b200.spec import SpecV0
+from oracle import channel as och
+from oracle import philox as oph
+from oracle.model import patchify as o_patchify
+
+pytestmark = pytest.mark.gpu
+
+SPEC = SpecV0()
+
+
+def _close(got, ref, rtol, atol=0.0, what=""):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    err = (got - ref).abs()
+    lim = atol + rtol * ref.abs()
+    bad = err > lim
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} bad, max err {float(err.max()):.3e}, " \
+                          f"ref scale {float(ref.abs().max()):.3e}"
+
+
+def _close_scaled(got, ref, rtol, what=""):
+    """bf16-style check: error relative to the tensor's scale."""
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    err = float((got - ref).abs().max())
+    scale = float(ref.abs().max()) + 1e-12
+    assert err <= rtol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e})"
+
+
+def test_philox_words_bit_exact(cuda_lib):
+    from multimodal_sc_b200 import ops
+    for seed, stream, off, n in [(0, 0, 0, 64), (1234, 0, 5, 4096), (0xDEADBEEFCAFEF00D, 1, (1 << 33) + 7, 1000)]:
+        got = ops.philox_words(n, stream, seed, off).cpu().numpy().view(np.uint32)
+        ref = oph.philox_words(seed, n, stream, off)
+        assert np.array_equal(got, ref), (seed, stream, off)
+
+
+@pytest.mark.parametrize("kind", ["none", "awgn", "rayleigh"])
+@pytest.mark.parametrize("B,off", [(1, 0), (7, 3), (64, 100000)])
+def test_pnorm_channel_fwd_bwd_philox(cuda_lib, kind, B, off):
+    from multimodal_sc_b200 import ops
+    k = SPEC.k_sym
+    g = torch.Generator().manual_seed(B)
+    z = torch.randn(B, 2, k, generator=g) * 0.3
+    snr = torch.linspace(-5, 20, B) if B > 1 else torch.tensor([10.0])
+    dy = torch.randn(B, 2, k, generator=g)
+    seed = 1234
+    # oracle
+    zr = z.clone().requires_grad_(True)
+    y_ref, zn_ref = och.channel_forward(zr, snr, kind, seed=seed, sample_offset=off)
+    (y_ref * dy).sum().backward()
+    # native
+    zc, dyc, snrc = z.cuda(), dy.cuda(), snr.cuda()
+    y, _, scale = ops.pnorm_channel_fwd(zc, kind, snrc, seed=seed, sample_offset=off)
+    dz, _ = ops.pnorm_channel_bwd(dyc, zc, scale, kind, snrc, seed=seed, sample_offset=off)
+    _close(y, y_ref, 1e-5, 2e-5, f"y {kind}")
+    _close(dz, zr.grad, 1e-5, 2e-5, f"dz {kind}")
+    ref_scale = torch.rsqrt(z.pow(2).mean(-1) + SPEC.pnorm_eps)
+    _close(scale, ref_scale, 1e-5, 0, "scale")
+
+
+def test_pnorm_channel_explicit_noise_and_strides(cuda_lib):
+    """explicit noise/fading tensors, modality-major z layout, bf16 y."""
+    from multimodal_sc_b200 import ops
+    B, k = 5, SPEC.k_sym
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(B, 2, k, generator=g)
+    noise = torch.randn(B, 2, k, generator=g)
+    h = torch.randn(B, 2, 2, generator=g)
+    y_ref, _ = och.channel_forward(z, 3.0, "rayleigh", noise=noise, fading=h)
+    z_mm = z.permute(1, 0, 2).contiguous().cuda()            # physical [2,B,k]
+    yb = torch.empty(B, 2, k, device="cuda", dtype=torch.bfloat16)
+    yf = torch.empty(B, 2, k, device="cuda")
+    ops.pnorm_channel_fwd(z_mm, "rayleigh", 3.0, noise=noise.cuda(), fading=h.cuda(), y_f32=yf, y_bf16=yb,
+                          z_strides=(k, B * k, B, k))
+    _close(yf, y_ref, 1e-5, 2e-5, "rayleigh explicit")
+    _close_scaled(yb, y_ref, 1e-2, "rayleigh bf16")
+
+
+def test_channel_unit_power_and_snr(cuda_lib):
+    from multimodal_sc_b200 import ops
+    B, k = 512, SPEC.k_sym
+    z = torch.randn(B, 2, k, device="cuda") * 3
+    for snr in (-5.0, 10.0, 20.0):
+        y, _, scale = ops.pnorm_channel_fwd(z, "awgn", snr, seed=7)
+        zn = z * scale.unsqueeze(-1)
+        assert abs(float(zn.pow(2).mean()) - 1.0) < 1e-4
+        emp = och.empirical_snr_db(zn.cpu(), y.cpu())
+        assert abs(emp - snr) < 0.1, (snr, emp)
+
+
+def test_patchify(cuda_lib):
+    from multimodal_sc_b200 import ops
+    for (B, C, H, P) in [(3, 3, 128, 16), (2, 1, 64, 8)]:
+        img = torch.rand(B, C, H, H)
+        ref = o_patchify(img, P).reshape(-1, C * P * P).bfloat16()
+        got = ops.patchify(img.cuda(), P)
+        assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("M,D", [(1, 256), (777, 256), (64, 1024)])
+def test_layernorm_fwd_bwd(cuda_lib, dtype, rtol, M, D):
+    from multimodal_sc_b200 import ops
+    g = torch.Generator().manual_seed(M + D)
+    x = (torch.randn(M, D, generator=g) * 2 + 0.5).to(dtype)
+    gamma = torch.randn(D, generator=g)
+    beta = torch.randn(D, generator=g)
+    dy = torch.randn(M, D, generator=g).to(dtype)
+    dres = torch.randn(M, D, generator=g).to(dtype)
+    xr = x.float().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    br = beta.clone().requires_grad_(True)
+    y_ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, SPEC.ln_eps)
+    (y_ref * dy.float()).sum().backward()
+    dx_ref = xr.grad + dres.float()
+    xc = x.cuda()
+    mean = torch.empty(M, device="cuda")
+    rstd = torch.empty(M, device="cuda")
+    y = ops.layernorm_fwd(xc, gamma.cuda(), beta.cuda(), SPEC.ln_eps, mean=mean, rstd=rstd)
+    dgamma = torch.zeros(D, device="cuda")
+    dbeta = torch.zeros(D, device="cuda")
+    cs = torch.zeros(D, device="cuda")
+    dx = ops.layernorm_bwd(dy.cuda(), xc, mean, rstd, gamma.cuda(), dgamma, dbeta, dres=dres.cuda(), colsum=cs)
+    if dtype == torch.float32:
+        _close(y, y_ref, rtol, 1e-5, "ln y")
+        _close(dx, dx_ref, rtol, 2e-5, "ln dx")
+        _close(dgamma, gr.grad, 1e-4, 1e-4, "ln dgamma")
+        _close(dbeta, br.grad, 1e-4, 1e-4, "ln dbeta")
+        _close(cs, dx_ref.sum(0), 1e-4, 1e-3, "ln colsum")
+    else:
+        _close_scaled(y, y_ref, rtol, "ln y bf16")
+        _close_scaled(dx, dx_ref, rtol, "ln dx bf16")
+        _close_scaled(dgamma, gr.grad, rtol, "ln dgamma bf16")
+        _close_scaled(dbeta, br.grad, rtol, "ln dbeta bf16")
+
+
+def test_colsum_meanpool_mse_cast(cuda_lib):
+    from multimodal_sc_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 768, generator=g).bfloat16()
+    out = torch.ones(768, device="cuda")
+    ops.colsum(x.cuda(), out)
+    _close(out, 1.0 + x.float().sum(0), 1e-4, 1e-3, "colsum")
+    xs = torch.randn(1000, 1024, generator=g).bfloat16().cuda()
+    out2 = torch.zeros(256, device="cuda")
+    ops.colsum(xs[:, 256:512], out2)                         # strided view
+    _close(out2, xs[:, 256:512].float().sum(0), 1e-4, 1e-3, "colsum strided")
+
+    t = torch.randn(9, 128, 256, generator=g).bfloat16()
+    pooled = torch.empty(9, 256, device="cuda")
+    pooled_b = torch.empty(9, 256, device="cuda", dtype=torch.bfloat16)
+    ops.meanpool_fwd(t.cuda(), out_bf16=pooled_b, out_f32=pooled)
+    _close(pooled, t.float().mean(1), 1e-5, 1e-6, "meanpool")
+    assert torch.equal(pooled_b.cpu(), pooled.cpu().bfloat16())
+
+    r = torch.randn(33, 128, 256, generator=g).bfloat16()
+    tt = torch.randn(33, 128, 256, generator=g).bfloat16()
+    loss = torch.zeros(1, device="cuda")
+    dr = torch.empty_like(r, device="cuda")
+    ops.mse_fwd_bwd(r.cuda(), tt.cuda(), loss, dr, grad_scale=0.25)
+    ref = (r.float() - tt.float()).pow(2).mean()
+    assert abs(float(loss) - float(ref)) < 1e-5 * float(ref) + 1e-6
+    _close_scaled(dr, 2 * (r.float() - tt.float()) * 0.25, 1e-2, "mse dr")
+
+    src = torch.randn(100003, generator=g)
+    assert torch.equal(ops.cast_f32_bf16(src.cuda()).cpu(), src.bfloat16())
