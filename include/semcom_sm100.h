@@ -154,9 +154,14 @@ int sc_meanpool_fwd(const void* x, void* out_bf16, float* out_f32, int64_t B, in
                     void* stream);
 
 /* a6: semantic distortion, fused forward + backward:
- *   loss_accum[0] += sum((r - t)^2) * inv_numel ;  dr = bf16(2 (r - t) * grad_scale) */
-int sc_mse_fwd_bwd(const void* r, const void* t, float* loss_accum, void* dr, int64_t numel,
-                   float inv_numel, float grad_scale, void* stream);
+ *   loss_accum[0] += sum((r - t)^2) * inv_numel ;  dr = bf16(2 (r - t) * grad_scale)   (dr may be null)
+ * r: bf16, numel elements.  t1 == null: t has the same flat layout as r.  t1 != null: r is
+ * [samples, 2*seg_rows, D] (decoder tokens, modality-major per sample) and the target of rows
+ * [0,seg_rows) is t[sample*seg_rows + row], of rows [seg_rows, 2*seg_rows) is t1[...] — the two
+ * encoders' feature matrices, so no concatenated copy is ever made. */
+int sc_mse_fwd_bwd(const void* r, const void* t, const void* t1, int seg_rows, int D,
+                   float* loss_accum, void* dr, int64_t numel, float inv_numel, float grad_scale,
+                   void* stream);
 
 /* a7: actor-critic output layer on the tanh trunk: head_out[b, 0..A] = trunk[b,:] W^T + bias
  * trunk bf16 [B,D]; W fp32 [A+1, D]; head_out fp32 [B, A+1] (cols 0..A-1 logits, col A value) */

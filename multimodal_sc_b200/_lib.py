@@ -62,7 +62,7 @@ _PROTOS = {
                              _I64, _P, _P],
     "sc_philox_words": [_P, _I64, _U32, _U64, _I64, _P],
     "sc_meanpool_fwd": [_P, _P, _P, _I64, _I, _I, _P],
-    "sc_mse_fwd_bwd": [_P, _P, _P, _P, _I64, _F, _F, _P],
+    "sc_mse_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _I64, _F, _F, _P],
     "sc_heads_fwd": [_P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_heads_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_sample_action": [_P, _I, _P, _P, _P, _I64, _I, _P],

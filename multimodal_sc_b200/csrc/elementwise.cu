@@ -194,9 +194,13 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 // column sums of a bf16 [M, N] matrix (bias gradients)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t M, int N, int64_t ld,
+colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t M, int N_total, int64_t ld,
               int64_t rows_per_block) {
-  extern __shared__ float sred[];          // [N]
+  extern __shared__ float sred[];          // [<= 1024]
+  const int col0 = blockIdx.y * 1024;
+  const int N = min(1024, N_total - col0);  // columns handled by this block
+  x += col0;
+  out += col0;
   const int G = N / 8;                      // column groups
   const int rpi = blockDim.x / G;           // rows per iteration
   const int cg = threadIdx.x % G;
@@ -255,15 +259,26 @@ meanpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ out_bf16, float* 
 // fused MSE forward + backward
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-mse_kernel(const bf16* __restrict__ r, const bf16* __restrict__ t, float* __restrict__ loss,
-           bf16* __restrict__ dr, int64_t groups, float inv_numel, float grad_scale) {
+mse_kernel(const bf16* __restrict__ r, const bf16* __restrict__ t, const bf16* __restrict__ t1,
+           float* __restrict__ loss, bf16* __restrict__ dr, int64_t groups, float inv_numel, float grad_scale,
+           int seg_rows, int D8) {
   __shared__ float wsum[kThreads / 32];
   float acc = 0.f;
   for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
        g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float a[8], b[8], d[8];
     load8(r + g * 8, a);
-    load8(t + g * 8, b);
+    if (t1) {
+      // r rows are (sample, modality, token); targets are two [samples*seg_rows, D] matrices
+      const int64_t row = g / D8;
+      const int c8 = static_cast<int>(g % D8);
+      const int64_t smp = row / (2 * seg_rows);
+      const int rem = static_cast<int>(row % (2 * seg_rows));
+      const bf16* tb = rem < seg_rows ? t : t1;
+      load8(tb + ((smp * seg_rows + (rem % seg_rows)) * D8 + c8) * 8, b);
+    } else {
+      load8(t + g * 8, b);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float e = a[j] - b[j];
@@ -371,14 +386,15 @@ int sc_colsum_bf16(const void* x, float* out, int64_t M, int N, int64_t ld, void
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(x && out, SC_E_SHAPE, "sc_colsum_bf16: null pointer");
-  SC_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && N <= 2048 && ld >= N && ld % 8 == 0, SC_E_SHAPE,
-             "sc_colsum_bf16: M=%lld N=%d ld=%lld (need N %% 8 == 0, N <= 2048)", (long long)M, N, (long long)ld);
+  SC_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && ld >= N && ld % 8 == 0, SC_E_SHAPE,
+             "sc_colsum_bf16: M=%lld N=%d ld=%lld (need N %% 8 == 0)", (long long)M, N, (long long)ld);
   SC_REQUIRE(sc_aligned16(x), SC_E_ALIGN, "sc_colsum_bf16: unaligned pointer");
-  const int target = sc_num_sms() * 4;
+  const int ychunks = (N + 1023) / 1024;
+  const int target = (sc_num_sms() * 4 + ychunks - 1) / ychunks;
   int64_t rpb = (M + target - 1) / target;
   if (rpb < 32) rpb = 32;
-  const int grid = (int)((M + rpb - 1) / rpb);
-  colsum_kernel<<<grid, kThreads, N * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, out, M, N, ld, rpb);
+  const dim3 grid((unsigned)((M + rpb - 1) / rpb), (unsigned)ychunks);
+  colsum_kernel<<<grid, kThreads, 1024 * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, out, M, N, ld, rpb);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_colsum_bf16");
   return SC_OK;
@@ -398,18 +414,22 @@ int sc_meanpool_fwd(const void* x, void* out_bf16, float* out_f32, int64_t B, in
   return SC_OK;
 }
 
-int sc_mse_fwd_bwd(const void* r, const void* t, float* loss_accum, void* dr, int64_t numel, float inv_numel,
-                   float grad_scale, void* stream) {
+int sc_mse_fwd_bwd(const void* r, const void* t, const void* t1, int seg_rows, int D, float* loss_accum, void* dr,
+                   int64_t numel, float inv_numel, float grad_scale, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(r && t && loss_accum, SC_E_SHAPE, "sc_mse_fwd_bwd: null pointer");
   SC_REQUIRE(numel > 0 && numel % 8 == 0, SC_E_SHAPE, "sc_mse_fwd_bwd: numel=%lld must be a positive multiple of 8",
              (long long)numel);
-  SC_REQUIRE(sc_aligned16(r) && sc_aligned16(t) && sc_aligned16(dr), SC_E_ALIGN, "sc_mse_fwd_bwd: unaligned pointer");
+  SC_REQUIRE(sc_aligned16(r) && sc_aligned16(t) && sc_aligned16(t1) && sc_aligned16(dr), SC_E_ALIGN,
+             "sc_mse_fwd_bwd: unaligned pointer");
+  SC_REQUIRE(!t1 || (seg_rows > 0 && D > 0 && D % 8 == 0 && numel % (2LL * seg_rows * D) == 0), SC_E_SHAPE,
+             "sc_mse_fwd_bwd: two-target mode needs numel %% (2*seg_rows*D) == 0");
   const int64_t groups = numel / 8;
   const int grid = persistent_blocks((groups + kThreads - 1) / kThreads, 8);
-  mse_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const bf16*)r, (const bf16*)t, loss_accum, (bf16*)dr,
-                                                          groups, inv_numel, grad_scale);
+  mse_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const bf16*)r, (const bf16*)t, (const bf16*)t1, loss_accum,
+                                                          (bf16*)dr, groups, inv_numel, grad_scale, seg_rows,
+                                                          D > 0 ? D / 8 : 1);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_mse_fwd_bwd");
   return SC_OK;

@@ -181,13 +181,15 @@ def meanpool_fwd(x, out_bf16=None, out_f32=None):
     return out_bf16 if out_bf16 is not None else out_f32
 
 
-def mse_fwd_bwd(r, t, loss_accum, dr=None, grad_scale=1.0):
-    """loss_accum[0] += mean((r-t)^2); dr = bf16(2 (r-t) grad_scale)"""
+def mse_fwd_bwd(r, t, loss_accum, dr=None, grad_scale=1.0, t1=None, seg_rows=0):
+    """loss_accum[0] += mean((r-t)^2); dr = bf16(2 (r-t) grad_scale).
+    With t1: r is [samples, 2*seg_rows, D]; t / t1 are the per-modality targets [samples*seg_rows, D]."""
     _cuda(r, t, loss_accum)
     assert r.dtype == BF16 and t.dtype == BF16 and r.is_contiguous() and t.is_contiguous()
     n = r.numel()
-    check(_lib.load().sc_mse_fwd_bwd(ptr(r), ptr(t), ptr(loss_accum), ptr(dr), n, 1.0 / n, grad_scale,
-                                     stream_ptr()), "sc_mse_fwd_bwd")
+    D = r.shape[-1]
+    check(_lib.load().sc_mse_fwd_bwd(ptr(r), ptr(t), ptr(t1), seg_rows, D, ptr(loss_accum), ptr(dr), n, 1.0 / n,
+                                     grad_scale, stream_ptr()), "sc_mse_fwd_bwd")
     return dr
 
 
@@ -198,3 +200,108 @@ def cast_f32_bf16(src, dst=None):
         dst = torch.empty_like(src, dtype=BF16)
     check(_lib.load().sc_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "sc_cast_f32_bf16")
     return dst
+
+
+def attn_fwd(qkv, B, S, H, out=None, lse=None):
+    """qkv bf16 [B*S, 3*H*64] -> out bf16 [B*S, H*64], lse fp32 [B*S, H] (log2 domain)"""
+    _cuda(qkv)
+    assert qkv.dtype == BF16 and qkv.is_contiguous() and qkv.shape == (B * S, 3 * H * 64)
+    if out is None:
+        out = torch.empty(B * S, H * 64, device=qkv.device, dtype=BF16)
+    if lse is None:
+        lse = torch.empty(B * S, H, device=qkv.device, dtype=F32)
+    check(_lib.load().sc_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, S, H, stream_ptr()), "sc_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, B, S, H, dqkv=None):
+    _cuda(qkv, dout, lse)
+    assert qkv.dtype == BF16 and dout.dtype == BF16 and qkv.is_contiguous() and dout.is_contiguous()
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    check(_lib.load().sc_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, S, H, stream_ptr()),
+          "sc_attn_bwd")
+    return dqkv
+
+
+def heads_fwd(trunk, W, bias, out=None):
+    """trunk bf16 [B,D], W fp32 [A1,D], bias fp32 [A1] -> fp32 [B,A1]"""
+    _cuda(trunk, W, bias)
+    B, D = trunk.shape
+    A1 = W.shape[0]
+    assert trunk.dtype == BF16 and W.dtype == F32 and W.is_contiguous() and trunk.is_contiguous()
+    if out is None:
+        out = torch.empty(B, A1, device=trunk.device, dtype=F32)
+    check(_lib.load().sc_heads_fwd(ptr(trunk), ptr(W), ptr(bias), ptr(out), B, D, A1, stream_ptr()), "sc_heads_fwd")
+    return out
+
+
+def heads_bwd(dho, trunk, W, dW, dbias, dtrunk_pre=None):
+    _cuda(dho, trunk, W, dW, dbias)
+    B, D = trunk.shape
+    A1 = W.shape[0]
+    assert dho.dtype == F32 and dho.is_contiguous() and dho.shape == (B, A1)
+    if dtrunk_pre is None:
+        dtrunk_pre = torch.empty_like(trunk)
+    check(_lib.load().sc_heads_bwd(ptr(dho), ptr(trunk), ptr(W), ptr(dtrunk_pre), ptr(dW), ptr(dbias), B, D, A1,
+                                   stream_ptr()), "sc_heads_bwd")
+    return dtrunk_pre
+
+
+def sample_action(head_out, u, n_actions, action=None, logp=None):
+    _cuda(head_out, u)
+    B, ld = head_out.shape
+    assert head_out.dtype == F32 and head_out.is_contiguous() and u.dtype == F32
+    if action is None:
+        action = torch.empty(B, device=u.device, dtype=torch.int64)
+    if logp is None:
+        logp = torch.empty(B, device=u.device, dtype=F32)
+    check(_lib.load().sc_sample_action(ptr(head_out), ld, ptr(u), ptr(action), ptr(logp), B, n_actions,
+                                       stream_ptr()), "sc_sample_action")
+    return action, logp
+
+
+def gae(rewards, values, dones, last_value, gamma, lam, adv=None, ret=None, sums=None):
+    _cuda(rewards, values, dones, last_value)
+    T, N = rewards.shape
+    for t in (rewards, values, dones, last_value):
+        assert t.dtype == F32 and t.is_contiguous()
+    if adv is None:
+        adv = torch.empty_like(rewards)
+    if ret is None:
+        ret = torch.empty_like(rewards)
+    if sums is not None:
+        assert sums.dtype == torch.float64 and sums.numel() == 2
+    check(_lib.load().sc_gae(ptr(rewards), ptr(values), ptr(dones), ptr(last_value), ptr(adv), ptr(ret), ptr(sums),
+                             T, N, gamma, lam, stream_ptr()), "sc_gae")
+    return adv, ret
+
+
+def adv_normalize(adv, sums, count, eps):
+    _cuda(adv, sums)
+    assert adv.dtype == F32 and adv.is_contiguous() and sums.dtype == torch.float64
+    check(_lib.load().sc_adv_normalize(ptr(adv), ptr(sums), count, adv.numel(), eps, stream_ptr()),
+          "sc_adv_normalize")
+    return adv
+
+
+def ppo_loss(head_out, actions, logp_old, adv, ret, n_actions, clip_eps, c_v, c_ent, inv_m, dho=None, stats=None):
+    """fused PPO loss fwd+bwd. stats[0:5] += (pi, v, ent, kl, clipfrac) * inv_m"""
+    _cuda(head_out, actions, logp_old, adv, ret)
+    M, ld = head_out.shape
+    assert head_out.dtype == F32 and head_out.is_contiguous() and actions.dtype == torch.int64
+    if dho is None:
+        dho = torch.empty_like(head_out)
+    if stats is None:
+        stats = torch.zeros(8, device=head_out.device, dtype=F32)
+    check(_lib.load().sc_ppo_loss(ptr(head_out), ld, ptr(actions), ptr(logp_old), ptr(adv), ptr(ret), ptr(dho),
+                                  ptr(stats), M, n_actions, clip_eps, c_v, c_ent, inv_m, stream_ptr()),
+          "sc_ppo_loss")
+    return dho, stats
+
+
+def adam_flat(p, g, m, v, p_bf16, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _cuda(p, g, m, v)
+    n = p.numel()
+    check(_lib.load().sc_adam_flat(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), n, lr, beta1, beta2, eps, step,
+                                   grad_scale, stream_ptr()), "sc_adam_flat")
