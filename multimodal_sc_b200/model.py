@@ -1,0 +1,425 @@
+"""Native SemComPolicy: the SPEC v0 model driven kernel-by-kernel through the C ABI.
+
+Drop-in for the oracle's `nn.Module` API (upstream /root/reference/README.md:1-2
+has no code, so the API is the one `oracle/model.py` fixes): same constructor, same
+`forward(cam, bev, snr_db, *, channel, seed, noise, fading, sample_offset) -> (logits, value, aux)`,
+same `act()`, same `state_dict()` keys and shapes.
+
+B200-first layout instead of a module-per-layer autograd graph:
+  * every parameter is a view into ONE flat fp32 bucket (`FlatParams.p32`) with a bf16 shadow
+    for the tensor-core operands, one flat fp32 gradient bucket (the NCCL all-reduce payload)
+    and flat Adam moments — the optimizer and the collective are single launches;
+  * forward and backward are explicit kernel schedules (`Engine`) over a preallocated
+    activation arena, no autograd tape, no allocator traffic in the step, CUDA-graph capturable;
+  * weight gradients accumulate straight into the flat bucket from the wgrad GEMM epilogue
+    (split-K + red.global.add.f32) — there are no per-layer grad tensors to concatenate.
+`forward()` still participates in torch autograd (one custom Function around the whole engine)
+so that `loss.backward()` works exactly as with the oracle.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .spec import SpecV0
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+# ----------------------------------------------------------------------------------------------
+# parameters
+# ----------------------------------------------------------------------------------------------
+def _block_shapes(prefix: str, spec: SpecV0):
+    D, R = spec.d_model, spec.d_mlp
+    return [(f"{prefix}.ln1.weight", (D,)), (f"{prefix}.ln1.bias", (D,)),
+            (f"{prefix}.qkv.weight", (3 * D, D)), (f"{prefix}.qkv.bias", (3 * D,)),
+            (f"{prefix}.proj.weight", (D, D)), (f"{prefix}.proj.bias", (D,)),
+            (f"{prefix}.ln2.weight", (D,)), (f"{prefix}.ln2.bias", (D,)),
+            (f"{prefix}.fc1.weight", (R, D)), (f"{prefix}.fc1.bias", (R,)),
+            (f"{prefix}.fc2.weight", (D, R)), (f"{prefix}.fc2.bias", (D,))]
+
+
+def param_shapes(spec: SpecV0) -> "OrderedDict[str, tuple]":
+    """name -> shape, in the oracle's state_dict order (tests assert equality with the oracle)."""
+    D = spec.d_model
+    out = []
+    for enc, tokens, k in (("cam_enc", spec.cam_tokens, spec.cam_k), ("bev_enc", spec.bev_tokens, spec.bev_k)):
+        out += [(f"{enc}.pos", (tokens, D)), (f"{enc}.patch_embed.weight", (D, k)),
+                (f"{enc}.patch_embed.bias", (D,))]
+        for l in range(spec.enc_layers):
+            out += _block_shapes(f"{enc}.blocks.{l}", spec)
+        out += [(f"{enc}.norm.weight", (D,)), (f"{enc}.norm.bias", (D,)),
+                (f"{enc}.sym.weight", (spec.c_sym, D)), (f"{enc}.sym.bias", (spec.c_sym,))]
+    out += [("dec.pos", (spec.dec_tokens, D)), ("dec.in_proj.weight", (D, spec.c_sym)), ("dec.in_proj.bias", (D,))]
+    for l in range(spec.dec_layers):
+        out += _block_shapes(f"dec.blocks.{l}", spec)
+    out += [("dec.norm.weight", (D,)), ("dec.norm.bias", (D,)), ("dec.recon.weight", (D, D)),
+            ("dec.recon.bias", (D,)), ("ac.trunk.weight", (D, D)), ("ac.trunk.bias", (D,)),
+            ("ac.head.weight", (spec.n_actions + 1, D)), ("ac.head.bias", (spec.n_actions + 1,))]
+    return OrderedDict(out)
+
+
+class FlatParams:
+    """flat fp32 master / bf16 shadow / fp32 grad / Adam moments; 256-byte aligned slots."""
+    ALIGN = 64   # elements
+
+    def __init__(self, spec: SpecV0, device):
+        self.shapes = param_shapes(spec)
+        self.offsets = OrderedDict()
+        off = 0
+        for name, shp in self.shapes.items():
+            n = 1
+            for s in shp:
+                n *= s
+            self.offsets[name] = (off, n)
+            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.p32 = torch.zeros(off, device=device, dtype=F32)
+        self.p16 = torch.zeros(off, device=device, dtype=BF16)
+        self.g32 = torch.zeros(off, device=device, dtype=F32)
+        self.m = torch.zeros(off, device=device, dtype=F32)
+        self.v = torch.zeros(off, device=device, dtype=F32)
+
+    def _view(self, buf, name):
+        off, n = self.offsets[name]
+        return buf[off:off + n].view(self.shapes[name])
+
+    def w32(self, name): return self._view(self.p32, name)
+    def w16(self, name): return self._view(self.p16, name)
+    def g(self, name): return self._view(self.g32, name)
+
+    def sync_shadow(self):
+        ops.cast_f32_bf16(self.p32, self.p16)
+
+    def n_params(self) -> int:
+        return sum(n for _, n in self.offsets.values())
+
+
+def _init_flat(flat: FlatParams, spec: SpecV0, std: float, seed: int):
+    """same init rule (and the same host RNG stream) as oracle SemComPolicy.reset_parameters."""
+    g = torch.Generator().manual_seed(seed)
+    for name, shp in flat.shapes.items():
+        dst = flat.w32(name)
+        if name.endswith("bias"):
+            dst.zero_()
+        elif ".ln" in name or "norm" in name:
+            dst.fill_(1.0)
+        else:
+            w = torch.empty(shp).normal_(0.0, 1.0, generator=g).clamp_(-2.0, 2.0) * std
+            dst.copy_(w)
+    flat.sync_shadow()
+
+
+# ----------------------------------------------------------------------------------------------
+# engine: explicit forward / backward schedules over a per-batch-size activation arena
+# ----------------------------------------------------------------------------------------------
+class _Arena(dict):
+    """named activation buffers for one batch size"""
+
+    def __init__(self, device):
+        super().__init__()
+        self.device = device
+
+    def buf(self, name, shape, dtype=BF16):
+        t = self.get(name)
+        if t is None:
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self[name] = t
+        return t
+
+
+def _wgrad_ksplit(n_out: int, k_out: int, m_red: int, sms: int = 148) -> int:
+    tiles = ((n_out + 127) // 128) * ((k_out + 255) // 256)
+    ks = max(1, sms // tiles)
+    return max(1, min(ks, (m_red + 63) // 64))
+
+
+class Engine:
+    def __init__(self, spec: SpecV0, flat: FlatParams, device):
+        self.spec, self.flat, self.device = spec, flat, device
+        self.arenas = {}
+        self.sms = torch.cuda.get_device_properties(device).multi_processor_count
+
+    def arena(self, B: int) -> _Arena:
+        a = self.arenas.get(B)
+        if a is None:
+            a = self.arenas[B] = _Arena(self.device)
+        return a
+
+    # ---- helpers ------------------------------------------------------------------------
+    def _linear_bwd(self, dy, x, wname, dx=None, bias_colsum=True, **dgrad_epi):
+        """dx = dy W (optional), dW += dy^T x, db += colsum(dy).  dy [M,N] bf16, x [M,K] bf16."""
+        f = self.flat
+        W = f.w16(f"{wname}.weight")
+        N, K = W.shape
+        if dx is not None or dgrad_epi.get("out_f32") is not None:
+            ops.gemm(dy, W, b_mn=True, out=dx, **dgrad_epi)
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out_f32=f.g(f"{wname}.weight"), atomic=True,
+                 ksplit=_wgrad_ksplit(N, K, dy.shape[0], self.sms))
+        if bias_colsum:
+            ops.colsum(dy, f.g(f"{wname}.bias"))
+
+    def _block_fwd(self, A, pfx, x_in, x_out, B, S, train):
+        sp, f = self.spec, self.flat
+        M, D, H = x_in.shape[0], sp.d_model, sp.n_heads
+        k = lambda n, shape, dt=BF16: A.buf(f"{pfx}.{n}", shape, dt)
+        xn1 = k("xn1", (M, D))
+        ops.layernorm_fwd(x_in, f.w32(f"{pfx}.ln1.weight"), f.w32(f"{pfx}.ln1.bias"), sp.ln_eps, y=xn1,
+                          mean=k("mean1", (M,), F32), rstd=k("rstd1", (M,), F32))
+        qkv = k("qkv", (M, 3 * D))
+        ops.gemm(xn1, f.w16(f"{pfx}.qkv.weight"), bias=f.w32(f"{pfx}.qkv.bias"), out=qkv)
+        ao = k("ao", (M, D))
+        ops.attn_fwd(qkv, B, S, H, out=ao, lse=k("lse", (M, H), F32))
+        x1 = k("x1", (M, D))
+        ops.gemm(ao, f.w16(f"{pfx}.proj.weight"), bias=f.w32(f"{pfx}.proj.bias"), resid=x_in, out=x1)
+        xn2 = k("xn2", (M, D))
+        ops.layernorm_fwd(x1, f.w32(f"{pfx}.ln2.weight"), f.w32(f"{pfx}.ln2.bias"), sp.ln_eps, y=xn2,
+                          mean=k("mean2", (M,), F32), rstd=k("rstd2", (M,), F32))
+        h = k("h", (M, sp.d_mlp))
+        hpre = k("hpre", (M, sp.d_mlp)) if train else None
+        ops.gemm(xn2, f.w16(f"{pfx}.fc1.weight"), bias=f.w32(f"{pfx}.fc1.bias"), act="gelu", aux_out=hpre, out=h)
+        ops.gemm(h, f.w16(f"{pfx}.fc2.weight"), bias=f.w32(f"{pfx}.fc2.bias"), resid=x1, out=x_out)
+
+    def _block_bwd(self, A, pfx, x_in, dx_out, dx_in, prev_bias_grad, B, S):
+        """dx_out: grad wrt block output [M,D] (its column sums were already added to fc2.bias grad by the
+        producer).  Writes dx_in; adds colsum(dx_in) to `prev_bias_grad` (bias of whatever produced x_in)."""
+        sp, f = self.spec, self.flat
+        M, D, H = x_in.shape[0], sp.d_model, sp.n_heads
+        k = lambda n: A[f"{pfx}.{n}"]
+        s = lambda n, shape, dt=BF16: A.buf(f"scratch.{n}.{shape[0]}", shape, dt)   # shared across blocks
+        # ---- MLP ----
+        dhpre = s("dh", (M, sp.d_mlp))
+        self._linear_bwd(dx_out, k("h"), f"{pfx}.fc2", dx=dhpre, bias_colsum=False, aux_in=k("hpre"))
+        dxn2 = s("dxn", (M, D))
+        self._linear_bwd(dhpre, k("xn2"), f"{pfx}.fc1", dx=dxn2)
+        dx1 = s("dx1", (M, D))
+        ops.layernorm_bwd(dxn2, k("x1"), k("mean2"), k("rstd2"), f.w32(f"{pfx}.ln2.weight"),
+                          f.g(f"{pfx}.ln2.weight"), f.g(f"{pfx}.ln2.bias"), dres=dx_out, dx=dx1,
+                          colsum=f.g(f"{pfx}.proj.bias"))
+        # ---- attention ----
+        dao = s("dao", (M, D))
+        self._linear_bwd(dx1, k("ao"), f"{pfx}.proj", dx=dao, bias_colsum=False)
+        dqkv = s("dqkv", (M, 3 * D))
+        ops.attn_bwd(k("qkv"), k("ao"), dao, k("lse"), B, S, H, dqkv=dqkv)
+        dxn1 = s("dxn", (M, D))
+        self._linear_bwd(dqkv, k("xn1"), f"{pfx}.qkv", dx=dxn1)
+        ops.layernorm_bwd(dxn1, x_in, k("mean1"), k("rstd1"), f.w32(f"{pfx}.ln1.weight"),
+                          f.g(f"{pfx}.ln1.weight"), f.g(f"{pfx}.ln1.bias"), dres=dx1, dx=dx_in,
+                          colsum=prev_bias_grad)
+
+    # ---- forward --------------------------------------------------------------------------
+    def forward(self, cam, bev, snr_db, channel, seed, noise, fading, sample_offset, train, want_aux=False):
+        sp, f = self.spec, self.flat
+        B = cam.shape[0]
+        A = self.arena(B)
+        D, S, C = sp.d_model, sp.cam_tokens, sp.c_sym
+        k_sym = sp.k_sym
+        z_mm = A.buf("z_mm", (2, B, k_sym), F32)                       # modality-major symbols
+        for mi, (enc, img, patch) in enumerate((("cam_enc", cam, sp.cam_patch), ("bev_enc", bev, sp.bev_patch))):
+            M = B * S
+            tok = ops.patchify(img, patch, out=A.buf(f"{enc}.tok", (M, img.shape[1] * patch * patch)))
+            xs = [A.buf(f"{enc}.x{l}", (M, D)) for l in range(sp.enc_layers + 1)]
+            ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
+                     rowadd=f.w32(f"{enc}.pos"), out=xs[0])
+            for l in range(sp.enc_layers):
+                self._block_fwd(A, f"{enc}.blocks.{l}", xs[l], xs[l + 1], B, S, train)
+            t = A.buf(f"{enc}.t", (M, D))
+            ops.layernorm_fwd(xs[-1], f.w32(f"{enc}.norm.weight"), f.w32(f"{enc}.norm.bias"), sp.ln_eps, y=t,
+                              mean=A.buf(f"{enc}.mean", (M,), F32), rstd=A.buf(f"{enc}.rstd", (M,), F32))
+            ops.gemm(t, f.w16(f"{enc}.sym.weight"), bias=f.w32(f"{enc}.sym.bias"), out_f32=z_mm[mi].view(M, C))
+        # ---- channel ----
+        y16 = A.buf("y16", (B, 2, k_sym))
+        y32 = A.buf("y32", (B, 2, k_sym), F32) if want_aux else None
+        scale = A.buf("scale", (B, 2), F32)
+        ops.pnorm_channel_fwd(z_mm, channel, snr_db, seed=seed or 0, sample_offset=sample_offset, noise=noise,
+                              fading=fading, eps=sp.pnorm_eps, y_f32=y32, y_bf16=y16, scale=scale,
+                              z_strides=(k_sym, B * k_sym, B, k_sym))
+        # ---- decoder ----
+        Sd = sp.dec_tokens
+        Md = B * Sd
+        xd = [A.buf(f"dec.x{l}", (Md, D)) for l in range(sp.dec_layers + 1)]
+        ops.gemm(y16.view(Md, C), f.w16("dec.in_proj.weight"), bias=f.w32("dec.in_proj.bias"),
+                 rowadd=f.w32("dec.pos"), out=xd[0])
+        for l in range(sp.dec_layers):
+            self._block_fwd(A, f"dec.blocks.{l}", xd[l], xd[l + 1], B, Sd, train)
+        tn = A.buf("dec.tn", (Md, D))
+        ops.layernorm_fwd(xd[-1], f.w32("dec.norm.weight"), f.w32("dec.norm.bias"), sp.ln_eps, y=tn,
+                          mean=A.buf("dec.mean", (Md,), F32), rstd=A.buf("dec.rstd", (Md,), F32))
+        feat = ops.meanpool_fwd(tn.view(B, Sd, D), out_bf16=A.buf("dec.f", (B, D)))
+        recon = A.buf("dec.recon", (Md, D))
+        ops.gemm(tn, f.w16("dec.recon.weight"), bias=f.w32("dec.recon.bias"), out=recon)
+        # ---- heads ----
+        trunk = A.buf("ac.trunk", (B, D))
+        ops.gemm(feat, f.w16("ac.trunk.weight"), bias=f.w32("ac.trunk.bias"), act="tanh", out=trunk)
+        ho = ops.heads_fwd(trunk, f.w32("ac.head.weight"), f.w32("ac.head.bias"),
+                           out=A.buf("ac.ho", (B, sp.n_actions + 1), F32))
+        return ho, A
+
+    def l_sem(self, A, B, loss_accum, grad_coef=None):
+        """loss_accum[0] += mean((recon - t)^2).  With grad_coef (= d loss / d l_sem) also writes
+        d loss / d recon = 2 (recon - t) * grad_coef / numel (bf16) for the backward pass."""
+        sp = self.spec
+        recon = A["dec.recon"]
+        dr = A.buf("dec.drecon", tuple(recon.shape)) if grad_coef is not None else None
+        gs = grad_coef / recon.numel() if grad_coef is not None else 0.0
+        ops.mse_fwd_bwd(recon.view(B, sp.dec_tokens, sp.d_model), A["cam_enc.t"], loss_accum, dr=dr,
+                        grad_scale=gs, t1=A["bev_enc.t"], seg_rows=sp.cam_tokens)
+
+    # ---- backward -------------------------------------------------------------------------
+    def backward(self, A, B, dho, cam_unused, channel, snr_db, seed, fading, sample_offset):
+        """dho: fp32 [B, A+1] = d loss / d head_out.  `dec.drecon` must hold d loss / d recon (l_sem()).
+        Accumulates into flat.g32."""
+        sp, f = self.spec, self.flat
+        D, S, C, Sd = sp.d_model, sp.cam_tokens, sp.c_sym, sp.dec_tokens
+        Md = B * Sd
+        # heads + trunk
+        dtrunk = ops.heads_bwd(dho, A["ac.trunk"], f.w32("ac.head.weight"), f.g("ac.head.weight"),
+                               f.g("ac.head.bias"), dtrunk_pre=A.buf("ac.dtrunk", (B, D)))
+        df = A.buf("dec.df", (B, D), F32)
+        self._linear_bwd(dtrunk, A["dec.f"], "ac.trunk", out_f32=df)
+        # recon head; d tn = d recon W_rec + (1/Sd) d f   (mean-pool backward fused as a row-group add)
+        dtn = A.buf("scratch.dxn.%d" % Md, (Md, D))
+        self._linear_bwd(A["dec.drecon"], A["dec.tn"], "dec.recon", dx=dtn, rowgrp=df, rowgrp_size=Sd,
+                         rowgrp_scale=1.0 / Sd)
+        L = sp.dec_layers
+        dxa = A.buf("scratch.dxa.%d" % Md, (Md, D))
+        dxb = A.buf("scratch.dxb.%d" % Md, (Md, D))
+        ops.layernorm_bwd(dtn, A[f"dec.x{L}"], A["dec.mean"], A["dec.rstd"], f.w32("dec.norm.weight"),
+                          f.g("dec.norm.weight"), f.g("dec.norm.bias"), dx=dxa,
+                          colsum=f.g(f"dec.blocks.{L - 1}.fc2.bias"))
+        cur, nxt = dxa, dxb
+        for l in range(L - 1, -1, -1):
+            prev_bias = f.g(f"dec.blocks.{l - 1}.fc2.bias") if l > 0 else f.g("dec.in_proj.bias")
+            self._block_bwd(A, f"dec.blocks.{l}", A[f"dec.x{l}"], cur, nxt, prev_bias, B, Sd)
+            cur, nxt = nxt, cur
+        # decoder input projection: cur = d xd0
+        ops.colsum(cur.view(B, Sd * D), f.g("dec.pos").view(-1))
+        dy = A.buf("dy", (B, 2, sp.k_sym), F32)
+        self._linear_bwd(cur, A["y16"].view(Md, C), "dec.in_proj", bias_colsum=False, out_f32=dy.view(Md, C))
+        # channel
+        dz_mm = A.buf("dz_mm", (2, B, sp.k_sym))
+        ops.pnorm_channel_bwd(dy, A["z_mm"], A["scale"], channel, snr_db, seed=seed or 0,
+                              sample_offset=sample_offset, fading=fading, dz_bf16=dz_mm,
+                              z_strides=(sp.k_sym, B * sp.k_sym, B, sp.k_sym))
+        # encoders
+        M = B * S
+        for mi, enc in enumerate(("cam_enc", "bev_enc")):
+            dz = dz_mm[mi].view(M, C)
+            dt = A.buf("scratch.dxn.%d" % M, (M, D))
+            self._linear_bwd(dz, A[f"{enc}.t"], f"{enc}.sym", dx=dt)
+            Le = sp.enc_layers
+            dxa = A.buf("scratch.dxa.%d" % M, (M, D))
+            dxb = A.buf("scratch.dxb.%d" % M, (M, D))
+            ops.layernorm_bwd(dt, A[f"{enc}.x{Le}"], A[f"{enc}.mean"], A[f"{enc}.rstd"], f.w32(f"{enc}.norm.weight"),
+                              f.g(f"{enc}.norm.weight"), f.g(f"{enc}.norm.bias"), dx=dxa,
+                              colsum=f.g(f"{enc}.blocks.{Le - 1}.fc2.bias"))
+            cur, nxt = dxa, dxb
+            for l in range(Le - 1, -1, -1):
+                prev_bias = f.g(f"{enc}.blocks.{l - 1}.fc2.bias") if l > 0 else f.g(f"{enc}.patch_embed.bias")
+                self._block_bwd(A, f"{enc}.blocks.{l}", A[f"{enc}.x{l}"], cur, nxt, prev_bias, B, S)
+                cur, nxt = nxt, cur
+            ops.colsum(cur.view(B, S * D), f.g(f"{enc}.pos").view(-1))
+            self._linear_bwd(cur, A[f"{enc}.tok"], f"{enc}.patch_embed", bias_colsum=False)
+
+
+# ----------------------------------------------------------------------------------------------
+# nn.Module facade
+# ----------------------------------------------------------------------------------------------
+class _PolicyFn(torch.autograd.Function):
+    """one autograd node around the whole engine (generic API path; PPOAgent bypasses it)."""
+
+    @staticmethod
+    def forward(ctx, policy, cam, bev, kw, *params):
+        eng = policy.engine
+        B = cam.shape[0]
+        ho, A = eng.forward(cam, bev, kw["snr_db"], kw["channel"], kw["seed"], kw["noise"], kw["fading"],
+                            kw["sample_offset"], train=True, want_aux=True)
+        lsem = torch.zeros(1, device=cam.device)
+        eng.l_sem(A, B, lsem)
+        ctx.policy, ctx.kw, ctx.B, ctx.A = policy, kw, B, A
+        return ho.clone(), lsem
+
+    @staticmethod
+    def backward(ctx, dho, dlsem):
+        policy, kw, B, A = ctx.policy, ctx.kw, ctx.B, ctx.A
+        eng, flat = policy.engine, policy.flat
+        saved = flat.g32
+        flat.g32 = torch.zeros_like(saved)                  # scratch bucket for this backward
+        try:
+            eng.l_sem(A, B, torch.zeros(1, device=dho.device), grad_coef=float(dlsem))
+            eng.backward(A, B, dho.contiguous().float(), None, kw["channel"], kw["snr_db"], kw["seed"],
+                         kw["fading"], kw["sample_offset"])
+            grads = [flat.g(n).clone() for n in flat.shapes]
+        finally:
+            flat.g32 = saved
+        return (None, None, None, None, *grads)
+
+
+class SemComPolicy(nn.Module):
+    def __init__(self, spec: SpecV0 = SpecV0(), device=None, init_std: float | None = None, seed: int = 0):
+        super().__init__()
+        _lib.require_device()
+        self.spec = spec
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.flat = FlatParams(spec, self.device)
+        _init_flat(self.flat, spec, spec.init_std if init_std is None else init_std, seed)
+        self.engine = Engine(spec, self.flat, self.device)
+        for name in self.flat.shapes:                       # nested parameter tree -> oracle state_dict keys
+            mod = self
+            parts = name.split(".")
+            for part in parts[:-1]:
+                if not hasattr(mod, part):
+                    mod.add_module(part, nn.Module())
+                mod = getattr(mod, part)
+            mod.register_parameter(parts[-1], nn.Parameter(self.flat.w32(name)))
+
+    # weights changed through torch (load_state_dict, manual edits): refresh the bf16 shadow
+    def sync(self):
+        self.flat.sync_shadow()
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        r = super().load_state_dict(state_dict, strict=strict, assign=False)
+        self.sync()
+        return r
+
+    def _kw(self, snr_db, channel, seed, noise, fading, sample_offset):
+        if channel != "none" and seed is None and noise is None:
+            raise ValueError("channel needs seed= or noise=")
+        if channel == "rayleigh" and seed is None and fading is None:
+            raise ValueError("rayleigh channel needs seed= or fading=")
+        if torch.is_tensor(snr_db):
+            snr_db = snr_db.to(self.device, F32).contiguous()
+            if snr_db.dim() == 0:
+                snr_db = float(snr_db)
+        return dict(snr_db=snr_db, channel=channel, seed=seed,
+                    noise=None if noise is None else noise.to(self.device, F32).contiguous(),
+                    fading=None if fading is None else fading.to(self.device, F32).contiguous(),
+                    sample_offset=sample_offset)
+
+    def forward(self, cam, bev, snr_db, *, channel: str = "awgn", seed=None, noise=None, fading=None,
+                sample_offset: int = 0):
+        kw = self._kw(snr_db, channel, seed, noise, fading, sample_offset)
+        cam = cam.to(self.device, F32).contiguous()
+        bev = bev.to(self.device, F32).contiguous()
+        B, A_ = cam.shape[0], self.spec.n_actions
+        if torch.is_grad_enabled():
+            ho, lsem = _PolicyFn.apply(self, cam, bev, kw, *self.parameters())
+            arena = self.engine.arena(B)
+        else:
+            ho, arena = self.engine.forward(cam, bev, kw["snr_db"], channel, seed, kw["noise"], kw["fading"],
+                                            sample_offset, train=False, want_aux=True)
+            ho = ho.clone()
+            lsem = torch.zeros(1, device=self.device)
+            self.engine.l_sem(arena, B, lsem)
+        zn = (arena["z_mm"] * arena["scale"].t().unsqueeze(-1)).permute(1, 0, 2)      # API view only
+        return ho[:, :A_], ho[:, A_], {"l_sem": lsem[0], "z": zn, "y": arena["y32"].clone()}
+
+    @torch.no_grad()
+    def act(self, cam, bev, snr_db, u, **kw):
+        logits, value, _ = self.forward(cam, bev, snr_db, **kw)
+        ho = torch.cat([logits, value[:, None]], dim=1).contiguous()
+        a, logp = ops.sample_action(ho, u.to(self.device, F32).contiguous(), self.spec.n_actions)
+        return a, logp, value

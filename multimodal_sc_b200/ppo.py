@@ -1,0 +1,123 @@
+"""Native PPO update: GAE scan, fused loss, explicit backward, flat all-reduce, fused Adam.
+
+Drop-in for `oracle/ppo.py: PPOAgent` (same constructor arguments, `update(rollout) -> stats`,
+`minibatch_step(...)`; upstream /root/reference/README.md:1-2 has no
+trainer).  One optimizer step is a fixed kernel schedule on the current stream:
+
+    memset(flat grad, stats) -> Engine.forward -> sc_mse_fwd_bwd -> sc_ppo_loss -> Engine.backward
+      -> [NCCL all-reduce of the flat fp32 bucket, data-parallel only] -> sc_adam_flat
+
+Data parallelism: every rank holds whole trajectories; the only data-path
+collectives are the flat-gradient all-reduce (one per optimizer step) and a 2-double all-reduce
+of (sum A, sum A^2) per rollout for the global advantage normalisation.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .model import SemComPolicy
+from .spec import SpecV0
+
+F32 = torch.float32
+
+
+class PPOAgent:
+    def __init__(self, policy: SemComPolicy, spec: SpecV0 = SpecV0(), *, epochs: int = 1, minibatch: int = 4096,
+                 snr_db: float = 10.0, channel: str = "awgn", seed: int = 1234, process_group=None):
+        self.policy, self.spec = policy, spec
+        self.epochs, self.minibatch = epochs, minibatch
+        self.snr_db, self.channel, self.seed = snr_db, channel, seed
+        self.step_count = 0
+        self.gen = torch.Generator().manual_seed(seed)
+        self.pg = process_group
+        self.world = 1
+        self.rank = 0
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        dev = policy.device
+        self.stats = torch.zeros(8, device=dev, dtype=F32)      # pi, v, ent, kl, clipfrac, l_sem, -, -
+        self.sums = torch.zeros(2, device=dev, dtype=torch.float64)
+
+    # ---- one optimizer step on one (local) minibatch ---------------------------------------------
+    def minibatch_step(self, cam, bev, actions, logp_old, adv, values_unused, ret, sample_offset: int = 0,
+                       sync_stats: bool = True):
+        """cam/bev fp32, actions int64, logp_old/adv/ret fp32 — all on the policy's device.
+        With world_size > 1 the arguments are this rank's shard of the global minibatch and
+        `sample_offset` is its first global sample index (noise counters are global)."""
+        sp, pol = self.spec, self.policy
+        eng, flat = pol.engine, pol.flat
+        Bl = cam.shape[0]
+        Bg = Bl * self.world
+        flat.g32.zero_()
+        self.stats.zero_()
+        seed = self.seed + self.step_count
+        ho, A = eng.forward(cam, bev, self.snr_db, self.channel, seed, None, None, sample_offset, train=True)
+        # l_sem is a mean over the GLOBAL minibatch: each rank contributes its share
+        eng.l_sem(A, Bl, self.stats[5:6], grad_coef=sp.c_sem / self.world)
+        dho = A.buf("ac.dho", tuple(ho.shape), F32)
+        ops.ppo_loss(ho, actions, logp_old, adv, ret, sp.n_actions, sp.clip_eps, sp.c_v, sp.c_ent, 1.0 / Bg,
+                     dho=dho, stats=self.stats)
+        eng.backward(A, Bl, dho, None, self.channel, self.snr_db, seed, None, sample_offset)
+        if self.world > 1:
+            torch.distributed.all_reduce(flat.g32, group=self.pg)
+        self.step_count += 1
+        ops.adam_flat(flat.p32, flat.g32, flat.m, flat.v, flat.p16, sp.lr, sp.beta1, sp.beta2, sp.adam_eps,
+                      self.step_count, grad_scale=1.0)
+        if not sync_stats:
+            return None
+        return self.read_stats()
+
+    def read_stats(self) -> dict:
+        st = self.stats.clone()
+        if self.world > 1:
+            st[5] /= self.world
+            torch.distributed.all_reduce(st, group=self.pg)
+        s = st.cpu().tolist()                                     # the step's device->host read
+        out = {"pi": s[0], "v": s[1], "ent": s[2], "kl": s[3], "clipfrac": s[4], "l_sem": s[5]}
+        sp = self.spec
+        out["total"] = out["pi"] + sp.c_v * out["v"] - sp.c_ent * out["ent"] + sp.c_sem * out["l_sem"]
+        return out
+
+    # ---- advantages ----------------------------------------------------------------------------------
+    def compute_advantages(self, rewards, values, dones, last_value):
+        sp = self.spec
+        self.sums.zero_()
+        adv, ret = ops.gae(rewards, values, dones, last_value, sp.gamma, sp.lam, sums=self.sums)
+        count = adv.numel()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.sums, group=self.pg)
+            count *= self.world
+        ops.adv_normalize(adv, self.sums, count, sp.adv_eps)
+        return adv, ret
+
+    # ---- full update over a rollout ----------------------------------------------------------------
+    def update(self, rollout: dict) -> dict:
+        dev = self.policy.device
+        to = lambda x, dt=F32: x.to(dev, dt, non_blocking=True).contiguous()
+        rewards, values, dones = to(rollout["rewards"]), to(rollout["values"]), to(rollout["dones"])
+        T, N = rewards.shape
+        adv, ret = self.compute_advantages(rewards, values, dones, to(rollout["last_value"]))
+        n = T * N
+        cam_h, bev_h = rollout["cam"].reshape(n, *rollout["cam"].shape[2:]), rollout["bev"].reshape(n, *rollout["bev"].shape[2:])
+        act = to(rollout["actions"], torch.int64).reshape(n)
+        lp = to(rollout["logp"]).reshape(n)
+        adv, ret = adv.reshape(n), ret.reshape(n)
+        mb = min(self.minibatch, n)
+        tot, cnt = {}, 0
+        for _ in range(self.epochs):
+            perm = torch.randperm(n, generator=self.gen)            # host, seeded: bit-exact with the oracle
+            for i in range(0, n - mb + 1, mb):
+                idx = perm[i:i + mb]
+                idx_d = idx.to(dev)
+                if cam_h.is_cuda:
+                    cam, bev = cam_h[idx_d], bev_h[idx_d]
+                else:
+                    cam, bev = to(cam_h[idx]), to(bev_h[idx])       # host gather, then H2D of the minibatch
+                s = self.minibatch_step(cam.float(), bev.float(), act[idx_d], lp[idx_d], adv[idx_d], None,
+                                        ret[idx_d], sample_offset=self.rank * mb)
+                for k, v in s.items():
+                    tot[k] = tot.get(k, 0.0) + v
+                cnt += 1
+        return {k: v / max(cnt, 1) for k, v in tot.items()}
