@@ -15,6 +15,73 @@ from ._lib import GemmEpilogue, SC_ACT, SC_CH, check, ptr, stream_ptr
 BF16 = torch.bfloat16
 F32 = torch.float32
 
+# ---- optional per-launch timing (bench.py's roofline pass): CUDA events on the launching stream ----
+_PROF = None
+
+
+class profile:
+    """with ops.profile() as prof: ...   -> prof.records = [(kernel, ms, flops, bytes)]"""
+
+    def __enter__(self):
+        global _PROF
+        self.pending = []
+        self.records = []
+        _PROF = self
+        return self
+
+    def __exit__(self, *exc):
+        global _PROF
+        _PROF = None
+        torch.cuda.synchronize()
+        self.records = [(n, e0.elapsed_time(e1), fl, by) for n, e0, e1, fl, by in self.pending]
+        self.pending = []
+        return False
+
+    def summary(self):
+        out = {}
+        for n, ms, fl, by in self.records:
+            d = out.setdefault(n, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += ms
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+def _profiled(name):
+    def deco(fn):
+        def wrapper(*a, **k):
+            if _PROF is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            nm, fl, by = name, 0.0, 0.0
+            if name == "gemm":
+                A, B = a[0], a[1]
+                a_mn, b_mn = k.get("a_mn", False), k.get("b_mn", False)
+                K, M = (A.shape if a_mn else A.shape[::-1])
+                N = B.shape[1] if b_mn else B.shape[0]
+                nm = "gemm_" + ("wgrad" if a_mn else ("dgrad" if b_mn else "fwd"))
+                fl = 2.0 * M * N * K
+                by = 2.0 * (M * K + N * K) + (4.0 if k.get("out_f32") is not None and k.get("out") is None else 2.0) * M * N
+                for extra in ("resid", "aux_in", "aux_out"):
+                    if k.get(extra) is not None:
+                        by += 2.0 * M * N
+            elif name in ("attn_fwd", "attn_bwd"):
+                qkv, Bn, S, H = a[0], a[-3] if name == "attn_bwd" else a[1], a[-2] if name == "attn_bwd" else a[2], a[-1] if name == "attn_bwd" else a[3]
+                Sk = 128            # every item is a 128-row tile (two sequences share one when S = 64)
+                items = (Bn * S + 127) // 128 * H
+                fl = items * (2 if name == "attn_fwd" else 5) * 2.0 * 128 * Sk * 64
+                by = qkv.numel() * 2.0 * (4.0 / 3.0 if name == "attn_fwd" else 7.0 / 3.0)
+            _PROF.pending.append((nm, e0, e1, fl, by))
+            return r
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
 
 def _cuda(*ts):
     for t in ts:
@@ -22,6 +89,7 @@ def _cuda(*ts):
             raise _lib.SemcomError("semcom ops need CUDA tensors (no CPU fallback)")
 
 
+@_profiled("gemm")
 def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, rowgrp_size=0,
          rowgrp_scale=1.0, alpha=1.0, resid=None, aux_in=None, aux_out=None, out=None,
          out_f32=None, act=None, atomic=False, ksplit=1):
@@ -67,6 +135,7 @@ def debug_set(key: str, value: int):
     check(_lib.load().sc_debug_set(key.encode(), value), "sc_debug_set")
 
 
+@_profiled("patchify")
 def patchify(img, patch: int, out=None):
     """img fp32 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P]"""
     _cuda(img)
@@ -79,6 +148,7 @@ def patchify(img, patch: int, out=None):
     return out
 
 
+@_profiled("layernorm_fwd")
 def layernorm_fwd(x, gamma, beta, eps, y=None, mean=None, rstd=None):
     _cuda(x, gamma, beta)
     assert x.is_contiguous() and x.dtype in (BF16, F32)
@@ -91,6 +161,7 @@ def layernorm_fwd(x, gamma, beta, eps, y=None, mean=None, rstd=None):
     return y
 
 
+@_profiled("layernorm_bwd")
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, dx=None, colsum=None):
     _cuda(dy, x)
     assert dy.is_contiguous() and x.is_contiguous() and dy.dtype == x.dtype
@@ -104,6 +175,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, dx=None, c
     return dx
 
 
+@_profiled("colsum")
 def colsum(x, out):
     """out[n] += sum_m x[m, n]; x bf16 [M,N] (row stride allowed)"""
     _cuda(x, out)
@@ -113,6 +185,7 @@ def colsum(x, out):
     return out
 
 
+@_profiled("pnorm_channel_fwd")
 def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, fading=None, eps=1e-12,
                       y_f32=None, y_bf16=None, scale=None, z_strides=None, y_strides=None):
     """z fp32 logical [B,2,k] addressed with z_strides=(sb, sm) (default: contiguous [B,2,k]).
@@ -141,6 +214,7 @@ def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, f
     return y_f32, y_bf16, scale
 
 
+@_profiled("pnorm_channel_bwd")
 def pnorm_channel_bwd(dy, z, scale, kind, snr_db, *, seed=0, sample_offset=0, fading=None, dz_f32=None,
                       dz_bf16=None, z_strides=None, y_strides=None):
     _cuda(dy, z, scale)
@@ -170,6 +244,7 @@ def philox_words(n_quads, stream_id, seed, quad_offset=0, device="cuda"):
     return out
 
 
+@_profiled("meanpool_fwd")
 def meanpool_fwd(x, out_bf16=None, out_f32=None):
     _cuda(x)
     assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 3
@@ -181,6 +256,7 @@ def meanpool_fwd(x, out_bf16=None, out_f32=None):
     return out_bf16 if out_bf16 is not None else out_f32
 
 
+@_profiled("mse_fwd_bwd")
 def mse_fwd_bwd(r, t, loss_accum, dr=None, grad_scale=1.0, t1=None, seg_rows=0):
     """loss_accum[0] += mean((r-t)^2); dr = bf16(2 (r-t) grad_scale).
     With t1: r is [samples, 2*seg_rows, D]; t / t1 are the per-modality targets [samples*seg_rows, D]."""
@@ -193,6 +269,7 @@ def mse_fwd_bwd(r, t, loss_accum, dr=None, grad_scale=1.0, t1=None, seg_rows=0):
     return dr
 
 
+@_profiled("cast_f32_bf16")
 def cast_f32_bf16(src, dst=None):
     _cuda(src)
     assert src.dtype == F32 and src.is_contiguous()
@@ -202,6 +279,7 @@ def cast_f32_bf16(src, dst=None):
     return dst
 
 
+@_profiled("attn_fwd")
 def attn_fwd(qkv, B, S, H, out=None, lse=None):
     """qkv bf16 [B*S, 3*H*64] -> out bf16 [B*S, H*64], lse fp32 [B*S, H] (log2 domain)"""
     _cuda(qkv)
@@ -214,6 +292,7 @@ def attn_fwd(qkv, B, S, H, out=None, lse=None):
     return out, lse
 
 
+@_profiled("attn_bwd")
 def attn_bwd(qkv, out, dout, lse, B, S, H, dqkv=None):
     _cuda(qkv, dout, lse)
     assert qkv.dtype == BF16 and dout.dtype == BF16 and qkv.is_contiguous() and dout.is_contiguous()
@@ -224,6 +303,7 @@ def attn_bwd(qkv, out, dout, lse, B, S, H, dqkv=None):
     return dqkv
 
 
+@_profiled("heads_fwd")
 def heads_fwd(trunk, W, bias, out=None):
     """trunk bf16 [B,D], W fp32 [A1,D], bias fp32 [A1] -> fp32 [B,A1]"""
     _cuda(trunk, W, bias)
@@ -236,6 +316,7 @@ def heads_fwd(trunk, W, bias, out=None):
     return out
 
 
+@_profiled("heads_bwd")
 def heads_bwd(dho, trunk, W, dW, dbias, dtrunk_pre=None):
     _cuda(dho, trunk, W, dW, dbias)
     B, D = trunk.shape
@@ -248,6 +329,7 @@ def heads_bwd(dho, trunk, W, dW, dbias, dtrunk_pre=None):
     return dtrunk_pre
 
 
+@_profiled("sample_action")
 def sample_action(head_out, u, n_actions, action=None, logp=None):
     _cuda(head_out, u)
     B, ld = head_out.shape
@@ -261,6 +343,7 @@ def sample_action(head_out, u, n_actions, action=None, logp=None):
     return action, logp
 
 
+@_profiled("gae")
 def gae(rewards, values, dones, last_value, gamma, lam, adv=None, ret=None, sums=None):
     _cuda(rewards, values, dones, last_value)
     T, N = rewards.shape
@@ -277,6 +360,7 @@ def gae(rewards, values, dones, last_value, gamma, lam, adv=None, ret=None, sums
     return adv, ret
 
 
+@_profiled("adv_normalize")
 def adv_normalize(adv, sums, count, eps):
     _cuda(adv, sums)
     assert adv.dtype == F32 and adv.is_contiguous() and sums.dtype == torch.float64
@@ -285,6 +369,7 @@ def adv_normalize(adv, sums, count, eps):
     return adv
 
 
+@_profiled("ppo_loss")
 def ppo_loss(head_out, actions, logp_old, adv, ret, n_actions, clip_eps, c_v, c_ent, inv_m, dho=None, stats=None):
     """fused PPO loss fwd+bwd. stats[0:5] += (pi, v, ent, kl, clipfrac) * inv_m"""
     _cuda(head_out, actions, logp_old, adv, ret)
@@ -300,6 +385,7 @@ def ppo_loss(head_out, actions, logp_old, adv, ret, n_actions, clip_eps, c_v, c_
     return dho, stats
 
 
+@_profiled("adam_flat")
 def adam_flat(p, g, m, v, p_bf16, lr, beta1, beta2, eps, step, grad_scale=1.0):
     _cuda(p, g, m, v)
     n = p.numel()
