@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import dp, ops
 from .model import SemComPolicy
 from .spec import SpecV0
 
@@ -31,11 +31,7 @@ class PPOAgent:
         self.step_count = 0
         self.gen = torch.Generator().manual_seed(seed)
         self.pg = process_group
-        self.world = 1
-        self.rank = 0
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
-            self.rank = torch.distributed.get_rank(process_group)
+        self.world, self.rank = dp.world_info(process_group)
         dev = policy.device
         self.stats = torch.zeros(8, device=dev, dtype=F32)      # pi, v, ent, kl, clipfrac, l_sem, -, -
         self.sums = torch.zeros(2, device=dev, dtype=torch.float64)
@@ -49,19 +45,18 @@ class PPOAgent:
         sp, pol = self.spec, self.policy
         eng, flat = pol.engine, pol.flat
         Bl = cam.shape[0]
-        Bg = Bl * self.world
         flat.g32.zero_()
         self.stats.zero_()
         seed = self.seed + self.step_count
         ho, A = eng.forward(cam, bev, self.snr_db, self.channel, seed, None, None, sample_offset, train=True)
         # l_sem is a mean over the GLOBAL minibatch: each rank contributes its share
-        eng.l_sem(A, Bl, self.stats[5:6], grad_coef=sp.c_sem / self.world)
+        inv_m, sem_coef = dp.loss_scales(Bl, self.world, sp.c_sem)
+        eng.l_sem(A, Bl, self.stats[5:6], grad_coef=sem_coef)
         dho = A.buf("ac.dho", tuple(ho.shape), F32)
-        ops.ppo_loss(ho, actions, logp_old, adv, ret, sp.n_actions, sp.clip_eps, sp.c_v, sp.c_ent, 1.0 / Bg,
+        ops.ppo_loss(ho, actions, logp_old, adv, ret, sp.n_actions, sp.clip_eps, sp.c_v, sp.c_ent, inv_m,
                      dho=dho, stats=self.stats)
         eng.backward(A, Bl, dho, None, self.channel, self.snr_db, seed, None, sample_offset)
-        if self.world > 1:
-            torch.distributed.all_reduce(flat.g32, group=self.pg)
+        dp.allreduce_flat_grads(flat.g32, self.pg)
         self.step_count += 1
         ops.adam_flat(flat.p32, flat.g32, flat.m, flat.v, flat.p16, sp.lr, sp.beta1, sp.beta2, sp.adam_eps,
                       self.step_count, grad_scale=1.0)
@@ -85,10 +80,7 @@ class PPOAgent:
         sp = self.spec
         self.sums.zero_()
         adv, ret = ops.gae(rewards, values, dones, last_value, sp.gamma, sp.lam, sums=self.sums)
-        count = adv.numel()
-        if self.world > 1:
-            torch.distributed.all_reduce(self.sums, group=self.pg)
-            count *= self.world
+        _, count = dp.global_adv_moments(self.sums, adv.numel(), self.pg)
         ops.adv_normalize(adv, self.sums, count, sp.adv_eps)
         return adv, ret
 

@@ -1,0 +1,95 @@
+"""world_size-2 gloo test of the data-parallel host logic (multimodal_sc_b200/dp.py) on CPU.
+
+Invariant: with per-sample terms scaled by 1/global_batch, L_sem by 1/world,
+noise counters on the global sample index and advantage moments all-reduced, the SUM over ranks
+of the shard gradients equals the 1-rank gradient on the concatenated minibatch.  The arithmetic
+is done by the oracle here (CPU); the native agent uses the same dp.py helpers around its kernels."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from multimodal_sc_b200 import dp, synthetic
+from multimodal_sc_b200.spec import SpecV0
+
+SPEC = SpecV0()
+
+
+def _grads(policy, mb, lo, hi, inv_m, sem_coef, seed):
+    from oracle.ppo import ppo_loss
+    import dataclasses
+    policy.zero_grad(set_to_none=True)
+    sl = slice(lo, hi)
+    logits, value, aux = policy(mb["cam"][sl], mb["bev"][sl], 10.0, channel="rayleigh", seed=seed, sample_offset=lo)
+    sp1 = dataclasses.replace(SPEC, c_sem=0.0)
+    out = ppo_loss(logits, mb["actions"][sl], mb["logp_old"][sl], mb["adv"][sl], value, mb["ret"][sl],
+                   torch.tensor(0.0), sp1)
+    n_local = hi - lo
+    total = out["total"] * (n_local * inv_m) + sem_coef * aux["l_sem"]     # means -> sums / global batch
+    total.backward()
+    return torch.cat([p.grad.flatten() for p in policy.parameters()])
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        from oracle.model import SemComPolicy
+        from oracle import ppo as oppo
+        assert dp.world_info() == (world, rank)
+        B = 6
+        mb = synthetic.minibatch(SPEC, B, seed=0)
+        pol = SemComPolicy(SPEC)
+        pol.reset_parameters(std=0.05, seed=1)
+        lo, hi = dp.shard_bounds(B, world, rank)
+        inv_m, sem_coef = dp.loss_scales(hi - lo, world, SPEC.c_sem)
+        g = _grads(pol, mb, lo, hi, inv_m, sem_coef, seed=42)
+        dp.allreduce_flat_grads(g)
+        # advantage moments
+        ro = synthetic.rollout(SPEC, 8, 4, seed=3)
+        elo, ehi = dp.shard_bounds(4, world, rank)
+        adv, _ = oppo.gae(ro["rewards"][:, elo:ehi], ro["values"][:, elo:ehi], ro["dones"][:, elo:ehi],
+                          ro["last_value"][elo:ehi], SPEC.gamma, SPEC.lam)
+        sums = torch.tensor([adv.double().sum(), adv.double().pow(2).sum()])
+        sums, count = dp.global_adv_moments(sums, adv.numel())
+        if rank == 0:
+            q.put((g.numpy(), sums.numpy(), count))   # by value: the worker exits right after
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_dp_equals_single_rank():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g2, sums, count = q.get(timeout=600)
+    g2, sums = torch.from_numpy(g2), torch.from_numpy(sums)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    from oracle.model import SemComPolicy
+    from oracle import ppo as oppo
+    torch.set_num_threads(4)
+    mb = synthetic.minibatch(SPEC, 6, seed=0)
+    pol = SemComPolicy(SPEC)
+    pol.reset_parameters(std=0.05, seed=1)
+    g1 = _grads(pol, mb, 0, 6, 1.0 / 6, SPEC.c_sem, seed=42)
+    assert torch.allclose(g2, g1, rtol=2e-4, atol=2e-6), float((g2 - g1).abs().max())
+    ro = synthetic.rollout(SPEC, 8, 4, seed=3)
+    adv, _ = oppo.gae(ro["rewards"], ro["values"], ro["dones"], ro["last_value"], SPEC.gamma, SPEC.lam)
+    assert count == adv.numel()
+    assert torch.allclose(sums, torch.tensor([adv.double().sum(), adv.double().pow(2).sum()]), rtol=1e-9)
+
+
+def test_shard_bounds_cover_everything():
+    for n in (1, 7, 8, 4096):
+        for w in (1, 2, 3, 8):
+            spans = [dp.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
