@@ -24,24 +24,7 @@ constexpr int kThreads = 192;
 constexpr int kTile = 128 * 64 * 2;                 // one 128x64 bf16 tile = 16 KB
 constexpr float kLog2e = 1.4426950408889634f;
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src_smem), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-// address of 16-byte piece `pc` (0..7) of row r in a [128 x 128 B] SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t sw128(uint32_t base, int r, int pc) {
-  return base + r * 128 + ((pc ^ (r & 7)) << 4);
-}
 
 // write 32 fp32 values (columns j0 .. j0+31 of row r) as bf16 into a 128x128 K-major SW128 operand
 // made of two 64-column k-blocks of 16 KB each.
@@ -228,7 +211,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (threadIdx.x == 64) {
         tma_store_2d(&tmO, o_buf, h * 64, row0);
         tma_store_commit();
-        tma_store_wait_read();
+        tma_store_wait_read<0>();
       }
     }
     if (threadIdx.x == 64) tma_store_wait_all();
@@ -447,7 +430,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tma_store_2d(&tmDQKV, p_buf + kTile, HD + h * 64, row0);          // dK
         tma_store_2d(&tmDQKV, p_buf + 2 * kTile, h * 64, row0);           // dQ
         tma_store_commit();
-        tma_store_wait_read();
+        tma_store_wait_read<0>();
       }
     }
     if (threadIdx.x == 64) tma_store_wait_all();

@@ -5,10 +5,12 @@
 //   rows a1/a2/a5 and their dgrad / wgrad forms.
 //
 // Structure (one CTA per SM, 256 threads):
-//   warp 0 / lane 0 : TMA producer     — cp.async.bulk.tensor.2d into a 4-stage smem ring
+//   warp 0 / lane 0 : TMA producer     — cp.async.bulk.tensor.2d into a 3-stage smem ring
 //   warp 1 / lane 0 : MMA issuer       — tcgen05.mma.cta_group::1.kind::f16, 128x256x16
 //   warp 2          : TMEM allocator   — 512 columns = two 128x256 fp32 accumulators
-//   warps 4..7      : epilogue         — tcgen05.ld 32x32b, fused math, 16-byte stores
+//   warps 4..7      : epilogue         — tcgen05.ld 32x32b, fused math; bf16 tiles staged in a per-warp
+//                                        SWIZZLE_128B smem ring and moved by TMA store / TMA load
+//                                        (fp32 / ragged outputs: direct 16-byte stores)
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 // The accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -25,12 +27,27 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;                 // 16384
 constexpr int B_BYTES = BN * BK * 2;                 // 32768
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 49152
 constexpr int CHUNK_BYTES = 64 * BK * 2;             // 8192: one 64-wide MN-major chunk
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+constexpr int EPI_SLOT_BYTES = 32 * 128;              // 32 rows x 64 bf16 columns, SWIZZLE_128B
+constexpr int EPI_SLOTS = 4;                         // ring per epilogue warp
+constexpr int EPI_RING_BYTES = 4 * EPI_SLOTS * EPI_SLOT_BYTES;   // 64 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_RING_BYTES + 1024;
+// staged-epilogue modes
+constexpr int EPI_GENERIC = 0;                       // direct register -> global stores (fp32 / ragged outputs)
+constexpr int EPI_OUT1 = 1;                          // bf16 out via smem + TMA store
+constexpr int EPI_OUT2 = 2;                          // bf16 out + bf16 pre-activation copy (two TMA stores per chunk)
+constexpr int EPI_IN = 3;                            // bf16 out, one bf16 input tile (residual or GELU' operand) by TMA load
+// compile-time specialisations of the staged epilogue math (small hot loops -> fit the L0 I-cache)
+constexpr int KIND_GEN = 0;                          // everything decided at run time
+constexpr int KIND_PLAIN = 1;                        // bf16(acc)
+constexpr int KIND_BIAS = 2;                         // + bias
+constexpr int KIND_FC1 = 3;                          // + bias, pre-activation copy, tanh-GELU
+constexpr int KIND_RESID = 4;                        // + bias + residual tile
+constexpr int KIND_DGELU = 5;                        // * GELU'(pre-activation tile)
 constexpr int NUM_THREADS = 256;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -54,6 +71,8 @@ struct GemmParams {
   int act;
   int atomic;
   int vec_ok;
+  int epi_mode;
+  int epi_kind;
   // UMMA descriptor fields (bytes); defaults set by the host, overridable for bring-up
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
 };
@@ -168,15 +187,144 @@ __device__ __forceinline__ void epilogue_scalar(const GemmParams& p, float a, in
   }
 }
 
+// 8 columns of one row for the staged epilogue: math only, results packed to bf16.
+// KIND != KIND_GEN turns every feature test into a compile-time constant.
+template <int KIND>
+__device__ __forceinline__ void epilogue_math8(const GemmParams& p, const uint32_t* acc, int col, uint32_t row_mod,
+                                               uint32_t row_grp, const uint4& in, uint32_t (&outp)[4],
+                                               uint32_t (&auxp)[4]) {
+  constexpr bool G = (KIND == KIND_GEN);
+  const bool has_bias = G ? (p.bias != nullptr) : (KIND == KIND_BIAS || KIND == KIND_FC1 || KIND == KIND_RESID);
+  const bool want_aux = G ? (p.aux_out != nullptr) : (KIND == KIND_FC1);
+  const int act = G ? p.act : (KIND == KIND_FC1 ? SC_ACT_GELU : SC_ACT_NONE);
+  const bool in_dgelu = G ? (p.aux_in != nullptr) : (KIND == KIND_DGELU);
+  const bool in_resid = G ? (p.resid != nullptr) : (KIND == KIND_RESID);
+  float x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(acc[j]);
+  if (G) {
+    if (p.alpha != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] *= p.alpha;
+    }
+  }
+  if (has_bias) {
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+  }
+  if (G) {
+    if (p.rowadd) {
+      const float* ra = p.rowadd + static_cast<int64_t>(row_mod) * p.N + col;
+      float4 b0 = __ldg(reinterpret_cast<const float4*>(ra));
+      float4 b1 = __ldg(reinterpret_cast<const float4*>(ra + 4));
+      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    }
+    if (p.rowgrp) {
+      const float* rg = p.rowgrp + static_cast<int64_t>(row_grp) * p.N + col;
+      float4 b0 = __ldg(reinterpret_cast<const float4*>(rg));
+      float4 b1 = __ldg(reinterpret_cast<const float4*>(rg + 4));
+      const float s = p.rowgrp_scale;
+      x[0] = fmaf(b0.x, s, x[0]); x[1] = fmaf(b0.y, s, x[1]); x[2] = fmaf(b0.z, s, x[2]);
+      x[3] = fmaf(b0.w, s, x[3]); x[4] = fmaf(b1.x, s, x[4]); x[5] = fmaf(b1.y, s, x[5]);
+      x[6] = fmaf(b1.z, s, x[6]); x[7] = fmaf(b1.w, s, x[7]);
+    }
+  }
+  if (want_aux) {
+    auxp[0] = pack_bf16(x[0], x[1]); auxp[1] = pack_bf16(x[2], x[3]);
+    auxp[2] = pack_bf16(x[4], x[5]); auxp[3] = pack_bf16(x[6], x[7]);
+  }
+  if (act == SC_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = gelu_fwd<true>(x[j]);
+  } else if (G && act == SC_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = tanh_fast(x[j]);
+  }
+  if (in_dgelu || in_resid) {
+    const float2 a0 = unpack_bf16(in.x), a1 = unpack_bf16(in.y), a2 = unpack_bf16(in.z), a3 = unpack_bf16(in.w);
+    if (in_dgelu) {
+      x[0] *= gelu_bwd<true>(a0.x); x[1] *= gelu_bwd<true>(a0.y); x[2] *= gelu_bwd<true>(a1.x);
+      x[3] *= gelu_bwd<true>(a1.y); x[4] *= gelu_bwd<true>(a2.x); x[5] *= gelu_bwd<true>(a2.y);
+      x[6] *= gelu_bwd<true>(a3.x); x[7] *= gelu_bwd<true>(a3.y);
+    } else {
+      x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
+      x[4] += a2.x; x[5] += a2.y; x[6] += a3.x; x[7] += a3.y;
+    }
+  }
+  outp[0] = pack_bf16(x[0], x[1]); outp[1] = pack_bf16(x[2], x[3]);
+  outp[2] = pack_bf16(x[4], x[5]); outp[3] = pack_bf16(x[6], x[7]);
+}
+
+// One 128x256 accumulator tile of the staged epilogue for one warp (32 rows): four 64-column chunks, each
+// drained in 16-column steps (tcgen05.ld.x16 -> math -> st.shared into the SWIZZLE_128B slot) and then
+// written with one (two for KIND_FC1) TMA store.
+template <int KIND>
+__device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmAux,
+                                            uint32_t t_addr, uint32_t ring, uint32_t in_bar0, uint32_t in_parity,
+                                            int lane, int n0, int row0, uint32_t row_mod, uint32_t row_grp) {
+  const bool has_in = (p.epi_mode == EPI_IN);
+  const bool two_out = (p.epi_mode == EPI_OUT2);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int col0 = n0 + c * 64;
+    if (col0 >= p.N) break;
+    const uint32_t slot_o = ring + (two_out ? ((2 * c + 1) & 3) : c) * EPI_SLOT_BYTES;
+    const uint32_t slot_a = ring + ((2 * c) & 3) * EPI_SLOT_BYTES;          // pre-activation copy (EPI_OUT2)
+    if (has_in) {
+      mbar_wait(in_bar0 + c * 8, in_parity);
+    } else if (lane == 0) {
+      // the TMA store that last read these slots must have drained them
+      if (two_out) tma_store_wait_read<2>(); else tma_store_wait_read<3>();
+    }
+    __syncwarp();
+    const uint32_t row_o = slot_o + lane * 128, row_a = slot_a + lane * 128;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_addr + c * 64 + h * 16, v);
+      const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+      uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
+      if (has_in) {
+        i0 = ld_shared_v4(row_o + pa);
+        i1 = ld_shared_v4(row_o + pb);
+      }
+      tmem_ld_wait();
+      uint32_t o[4], a[4];
+      epilogue_math8<KIND>(p, &v[0], col0 + h * 16, row_mod, row_grp, i0, o, a);
+      st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
+      if (two_out) st_shared_v4(row_a + pa, a[0], a[1], a[2], a[3]);
+      epilogue_math8<KIND>(p, &v[8], col0 + h * 16 + 8, row_mod, row_grp, i1, o, a);
+      st_shared_v4(row_o + pb, o[0], o[1], o[2], o[3]);
+      if (two_out) st_shared_v4(row_a + pb, a[0], a[1], a[2], a[3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (two_out) {
+        tma_store_2d(tmAux, slot_a, col0, row0);
+        tma_store_commit();
+      }
+      tma_store_2d(tmOut, slot_o, col0, row0);
+      tma_store_commit();
+    }
+  }
+}
+
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
+                    const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t epi_in_bar[4][EPI_SLOTS];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms: 1 KB aligned
@@ -192,6 +340,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
     }
+    for (int w = 0; w < 4; ++w)
+      for (int s = 0; s < EPI_SLOTS; ++s) mbar_init(smem_u32(&epi_in_bar[w][s]), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -272,45 +422,102 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp - 4;                                    // == warp % 4: TMEM lane quarter
     int as = 0;
     uint32_t aphase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
-      const int64_t row = static_cast<int64_t>(it.m_blk) * BM + q * 32 + lane;
-      const int n0 = it.n_blk * BN;
-      const bool row_ok = row < p.M;
-      uint32_t row_mod = 0, row_grp = 0;
-      if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
-      if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
-      mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
-      __syncwarp();
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+    if (p.epi_mode == EPI_GENERIC) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        const int64_t row = static_cast<int64_t>(it.m_blk) * BM + q * 32 + lane;
+        const int n0 = it.n_blk * BN;
+        const bool row_ok = row < p.M;
+        uint32_t row_mod = 0, row_grp = 0;
+        if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
+        if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
+        mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_addr + c * 32, v);
-        tmem_ld_wait();
-        if (row_ok) {
-          if (p.vec_ok) {
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            if (p.vec_ok) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col < p.N) epilogue_vec8(p, &v[g * 8], row, col, row_mod, row_grp);
-            }
-          } else {
+              for (int g = 0; g < 4; ++g) {
+                const int col = col0 + g * 8;
+                if (col < p.N) epilogue_vec8(p, &v[g * 8], row, col, row_mod, row_grp);
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              if (col < p.N) epilogue_scalar(p, __uint_as_float(v[j]), row, col, row_mod, row_grp);
+              for (int j = 0; j < 32; ++j) {
+                const int col = col0 + j;
+                if (col < p.N) epilogue_scalar(p, __uint_as_float(v[j]), row, col, row_mod, row_grp);
+              }
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty_bar[as]));
-      as ^= 1;
-      if (as == 0) aphase ^= 1u;
+    } else {
+      // ---- staged epilogue: 64-column chunks through a per-warp ring of SWIZZLE_128B slots,
+      //      outputs by TMA store (box 64 x 32), the optional bf16 input tile by TMA load ----
+      const uint32_t ring = smem_base + STAGES * STAGE_BYTES + q * (EPI_SLOTS * EPI_SLOT_BYTES);
+      const bool has_in = (p.epi_mode == EPI_IN);
+      int n = 0;
+      if (has_in && lane == 0 && static_cast<int>(blockIdx.x) < num_items) {
+        const Item it = decode_item(p, blockIdx.x);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t ib = smem_u32(&epi_in_bar[q][c]);
+          mbar_arrive_expect_tx(ib, EPI_SLOT_BYTES);
+          tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib, it.n_blk * BN + c * 64, it.m_blk * BM + q * 32);
+        }
+      }
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const Item it = decode_item(p, item);
+        const int row0 = it.m_blk * BM + q * 32;
+        const int64_t row = min(static_cast<int64_t>(row0) + lane, p.M - 1);   // tail rows: TMA clips the store
+        const int n0 = it.n_blk * BN;
+        uint32_t row_mod = 0, row_grp = 0;
+        if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
+        if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
+        mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+        const uint32_t ib0 = smem_u32(&epi_in_bar[q][0]);
+        const uint32_t ipar = static_cast<uint32_t>(n & 1);
+        switch (p.epi_kind) {
+          case KIND_PLAIN: staged_tile<KIND_PLAIN>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
+          case KIND_BIAS:  staged_tile<KIND_BIAS>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
+          case KIND_FC1:   staged_tile<KIND_FC1>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
+          case KIND_RESID: staged_tile<KIND_RESID>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
+          case KIND_DGELU: staged_tile<KIND_DGELU>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
+          default:         staged_tile<KIND_GEN>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+        // prefetch the next tile's input chunks into the ring once the stores have drained it
+        const int next = item + static_cast<int>(gridDim.x);
+        if (has_in && lane == 0 && next < num_items) {
+          tma_store_wait_read<0>();
+          const Item nt = decode_item(p, next);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t ib = smem_u32(&epi_in_bar[q][c]);
+            mbar_arrive_expect_tx(ib, EPI_SLOT_BYTES);
+            tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib, nt.n_blk * BN + c * 64, nt.m_blk * BM + q * 32);
+          }
+        }
+      }
+      if (lane == 0) tma_store_wait_all();
     }
   }
 
@@ -323,12 +530,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 struct DebugOverrides {
-  int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0;
+  int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0;
 };
 DebugOverrides g_dbg;
 
 template <int A_MN, int B_MN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAux,
+           const CUtensorMap& tmIn, const GemmParams& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
   auto kern = gemm_tcgen05_kernel<A_MN, B_MN>;
   if (!attr_set) {
@@ -339,7 +547,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
     }
     attr_set = true;
   }
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmOut, tmAux, tmIn, p);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_gemm_bf16");
   return SC_OK;
@@ -356,6 +564,7 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "b_sbo")) g_dbg.b_sbo = value;
   else if (!strcmp(key, "b_kstep")) g_dbg.b_kstep = value;
   else if (!strcmp(key, "max_ctas")) g_dbg.max_ctas = value;
+  else if (!strcmp(key, "generic_epi")) g_dbg.generic_epi = value;
   else if (!strcmp(key, "reset")) g_dbg = DebugOverrides();
   else {
     sc_set_error("sc_debug_set: unknown key %s", key);
@@ -436,13 +645,41 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   else           rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK);
   if (rc != SC_OK) return rc;
 
+  // staged (TMA) epilogue whenever the output is a plain aligned bf16 matrix with at most one bf16 input tile
+  CUtensorMap tmOut, tmAux, tmIn;
+  memset(&tmOut, 0, sizeof(tmOut)); memset(&tmAux, 0, sizeof(tmAux)); memset(&tmIn, 0, sizeof(tmIn));
+  p.epi_mode = EPI_GENERIC;
+  const bool one_in = (epi->resid != nullptr) != (epi->aux_in != nullptr);
+  const bool no_in = !epi->resid && !epi->aux_in;
+  if (!g_dbg.generic_epi && p.vec_ok && epi->out_bf16 && !epi->out_f32 && p.ksplit == 1 && (no_in || one_in) &&
+      !(one_in && epi->aux_out) && N % BN == 0) {
+    p.epi_mode = one_in ? EPI_IN : (epi->aux_out ? EPI_OUT2 : EPI_OUT1);
+    p.epi_kind = KIND_GEN;
+    if (epi->alpha == 1.0f && !epi->rowadd && !epi->rowgrp) {
+      const bool b = epi->bias != nullptr;
+      if (!b && epi->act == SC_ACT_NONE && !epi->aux_out && no_in) p.epi_kind = KIND_PLAIN;
+      else if (b && epi->act == SC_ACT_NONE && !epi->aux_out && no_in) p.epi_kind = KIND_BIAS;
+      else if (b && epi->act == SC_ACT_GELU && epi->aux_out && no_in) p.epi_kind = KIND_FC1;
+      else if (b && epi->act == SC_ACT_NONE && epi->resid) p.epi_kind = KIND_RESID;
+      else if (!b && epi->act == SC_ACT_NONE && epi->aux_in) p.epi_kind = KIND_DGELU;
+    }
+    const uint64_t ldb_bytes = (uint64_t)epi->ldo * 2;
+    if ((rc = sc_encode_tmap_2d_bf16(&tmOut, epi->out_bf16, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
+    if (epi->aux_out &&
+        (rc = sc_encode_tmap_2d_bf16(&tmAux, epi->aux_out, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
+    if (one_in) {
+      const void* in = epi->resid ? epi->resid : epi->aux_in;
+      if ((rc = sc_encode_tmap_2d_bf16(&tmIn, in, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
+    }
+  }
+
   const long long items = 1LL * p.tiles_m * p.tiles_n * p.ksplit;
   int grid = sc_num_sms();
   if (g_dbg.max_ctas > 0 && grid > g_dbg.max_ctas) grid = (int)g_dbg.max_ctas;
   if (items < grid) grid = (int)items;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a_mn == 0 && b_mn == 0) return launch<0, 0>(tmA, tmB, p, grid, st);
-  if (a_mn == 0 && b_mn == 1) return launch<0, 1>(tmA, tmB, p, grid, st);
-  if (a_mn == 1 && b_mn == 1) return launch<1, 1>(tmA, tmB, p, grid, st);
-  return launch<1, 0>(tmA, tmB, p, grid, st);
+  if (a_mn == 0 && b_mn == 0) return launch<0, 0>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st);
+  if (a_mn == 0 && b_mn == 1) return launch<0, 1>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st);
+  if (a_mn == 1 && b_mn == 1) return launch<1, 1>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st);
+  return launch<1, 0>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st);
 }

@@ -191,6 +191,61 @@ def _():
     return r
 
 
+@case("staged_tail_rows")
+def _():
+    """staged epilogue with an M tail (TMA clips), residual input and row-group add"""
+    import torch
+    from multimodal_sc_b200 import ops
+    M, N, K = 1000, 512, 256
+    A, B = _mk(M, N, K, False, False, scale=0.3)
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda").bfloat16()
+    grp = torch.randn((M + 127) // 128, N, device="cuda")
+    out = torch.full((M + 8, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, resid=resid, rowgrp=grp, rowgrp_size=128, rowgrp_scale=0.25, out=out[:M])
+    ref = ref_gemm(A, B, False, False) + bias + resid.float() + 0.25 * grp.repeat_interleave(128, 0)[:M]
+    r = _report("staged_tail_rows", out[:M], ref)
+    r["guard_rows_untouched"] = bool((out[M:] == 7.0).all())
+    r["ok"] = r["ok"] and r["guard_rows_untouched"]
+    return r
+
+
+@case("staged_many_tiles")
+def _():
+    """more tiles than CTAs so the slot ring / input prefetch wraps many times; all three staged modes"""
+    import torch
+    from multimodal_sc_b200 import ops
+    M, K = 128 * 700, 256
+    oks, rels = [], {}
+    for nm, N, kw in (("out1", 768, {}), ("out2", 1024, {"act": "gelu", "aux": True}), ("in_resid", 256, {"resid": True}),
+                      ("in_dgelu", 1024, {"aux_in": True})):
+        A, B = _mk(M, N, K, False, False, scale=0.3)
+        bias = torch.randn(N, device="cuda")
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ref = ref_gemm(A, B, False, False) + bias
+        if kw.get("aux"):
+            pre = torch.empty_like(out)
+            ops.gemm(A, B, bias=bias, act="gelu", aux_out=pre, out=out)
+            r1 = _report(nm + ".pre", pre, ref)
+            ref = gelu_tanh(ref)
+            oks.append(r1["ok"])
+        elif kw.get("resid"):
+            res = torch.randn(M, N, device="cuda").bfloat16()
+            ops.gemm(A, B, bias=bias, resid=res, out=out)
+            ref = ref + res.float()
+        elif kw.get("aux_in"):
+            pre = torch.randn(M, N, device="cuda").bfloat16()
+            ops.gemm(A, B, bias=bias, aux_in=pre, out=out)
+            ref = ref * dgelu_tanh(pre.float())
+        else:
+            ops.gemm(A, B, bias=bias, out=out)
+        r = _report(nm, out, ref)
+        oks.append(r["ok"])
+        rels[nm] = r["max_rel_err"]
+        del A, B, out, ref
+    return {"case": "staged_many_tiles", "ok": all(oks), "rels": rels}
+
+
 @case("timing")
 def _():
     import torch
@@ -233,7 +288,19 @@ def _():
         ev1.record()
         torch.cuda.synchronize()
         ms_cublas = ev0.elapsed_time(ev1) / n
-        res["shapes"].append({"name": nm, "M": M, "N": N, "K": K, "ms": ms, "tflops": flops / ms / 1e9,
+        ms_generic = None
+        if ks == 1:
+            ops.debug_set("generic_epi", 1)
+            for _ in range(2):
+                ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, **kw)
+            ev0.record()
+            for _ in range(n):
+                ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, **kw)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_generic = ev0.elapsed_time(ev1) / n
+            ops.debug_set("generic_epi", 0)
+        res["shapes"].append({"name": nm, "ms_generic_epi": ms_generic, "M": M, "N": N, "K": K, "ms": ms, "tflops": flops / ms / 1e9,
                               "gbs": byts / ms / 1e6, "ms_cublas": ms_cublas})
         del A, B, out
     return res
