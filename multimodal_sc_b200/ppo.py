@@ -22,6 +22,41 @@ from .spec import SpecV0
 F32 = torch.float32
 
 
+class HostMinibatchFeeder:
+    """Double-buffered pinned-host -> device staging of minibatches on a dedicated copy stream, so the
+    H2D transfer of step i+1 overlaps the kernels of step i.  submit() enqueues the copies and returns
+    (device tensors, ready event); the consumer stream must wait on the event before reading and call
+    release() after its last use so the slot can be overwritten."""
+
+    def __init__(self, device, slots: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.bufs = [dict() for _ in range(slots)]
+        self.free_ev = [None] * slots
+        self.i = 0
+
+    def submit(self, host_mb: dict):
+        k = self.i % len(self.bufs)
+        self.i += 1
+        buf = self.bufs[k]
+        with torch.cuda.stream(self.stream):
+            if self.free_ev[k] is not None:
+                self.stream.wait_event(self.free_ev[k])          # consumer finished with this slot
+            for name, src in host_mb.items():
+                dst = buf.get(name)
+                if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
+                    dst = buf[name] = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                dst.copy_(src, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return buf, ready, k
+
+    def release(self, k: int):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free_ev[k] = ev
+
+
 class PPOAgent:
     def __init__(self, policy: SemComPolicy, spec: SpecV0 = SpecV0(), *, epochs: int = 1, minibatch: int = 4096,
                  snr_db: float = 10.0, channel: str = "awgn", seed: int = 1234, process_group=None):
@@ -92,7 +127,10 @@ class PPOAgent:
         T, N = rewards.shape
         adv, ret = self.compute_advantages(rewards, values, dones, to(rollout["last_value"]))
         n = T * N
-        cam_h, bev_h = rollout["cam"].reshape(n, *rollout["cam"].shape[2:]), rollout["bev"].reshape(n, *rollout["bev"].shape[2:])
+        # observations go to the device once (pinned or pageable host tensors both work); minibatches are
+        # gathered on the device — a host-side gather of 870 MB per step would dominate the update
+        cam_h = to(rollout["cam"]).reshape(n, *rollout["cam"].shape[2:])
+        bev_h = to(rollout["bev"]).reshape(n, *rollout["bev"].shape[2:])
         act = to(rollout["actions"], torch.int64).reshape(n)
         lp = to(rollout["logp"]).reshape(n)
         adv, ret = adv.reshape(n), ret.reshape(n)
@@ -103,11 +141,8 @@ class PPOAgent:
             for i in range(0, n - mb + 1, mb):
                 idx = perm[i:i + mb]
                 idx_d = idx.to(dev)
-                if cam_h.is_cuda:
-                    cam, bev = cam_h[idx_d], bev_h[idx_d]
-                else:
-                    cam, bev = to(cam_h[idx]), to(bev_h[idx])       # host gather, then H2D of the minibatch
-                s = self.minibatch_step(cam.float(), bev.float(), act[idx_d], lp[idx_d], adv[idx_d], None,
+                cam, bev = cam_h[idx_d], bev_h[idx_d]
+                s = self.minibatch_step(cam, bev, act[idx_d], lp[idx_d], adv[idx_d], None,
                                         ret[idx_d], sample_offset=self.rank * mb)
                 for k, v in s.items():
                     tot[k] = tot.get(k, 0.0) + v
