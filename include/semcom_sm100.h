@@ -64,7 +64,7 @@ int64_t sc_launch_count(void);
  * epilogue, applied per element in this order (null pointer / zero = skipped):
  *   v = alpha * acc
  *   v += bias[n]                                    fp32 [N]
- *   v += rowadd[(m % rowadd_period) * N + n]        fp32 [period, N]     (pos-embed)
+ *   v += rowadd[(m % rowadd_period) * N + n]        fp32 [period, N]     (pos-embed; or rowadd_bf16)
  *   v += rowgrp[(m / rowgrp_size) * N + n] * rowgrp_scale   fp32          (mean-pool bwd)
  *   aux_out[m*ldo + n] = bf16(v)                    pre-activation copy   (GELU fwd)
  *   v = act(v)
@@ -91,6 +91,8 @@ typedef struct sc_gemm_epilogue {
   int64_t ldo;
   int32_t act;
   int32_t atomic;
+  const void* rowadd_bf16; /* bf16 [rowadd_period, N]: same add as `rowadd`, but fetched as a TMA tile
+                              (needs bf16 output, N % 256 == 0, period % 32 == 0, no resid / aux_in) */
 } sc_gemm_epilogue;
 
 int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn,

@@ -37,6 +37,7 @@ class GemmEpilogue(C.Structure):
         ("ldo", C.c_int64),
         ("act", C.c_int32),
         ("atomic", C.c_int32),
+        ("rowadd_bf16", C.c_void_p),
     ]
 
 

@@ -4,11 +4,11 @@
 //   include/semcom_sm100.h: sc_gemm_bf16).  Implements every dense contraction of SPEC v0
 //   rows a1/a2/a5 and their dgrad / wgrad forms.
 //
-// Structure (one CTA per SM, 256 threads):
+// Structure (one CTA per SM, 384 threads):
 //   warp 0 / lane 0 : TMA producer     — cp.async.bulk.tensor.2d into a 3-stage smem ring
 //   warp 1 / lane 0 : MMA issuer       — tcgen05.mma.cta_group::1.kind::f16, 128x256x16
 //   warp 2          : TMEM allocator   — 512 columns = two 128x256 fp32 accumulators
-//   warps 4..7      : epilogue         — tcgen05.ld 32x32b, fused math; bf16 tiles staged in a per-warp
+//   warps 4..11     : epilogue (two warpgroups, one per accumulator stage)         — tcgen05.ld 32x32b, fused math; bf16 tiles staged in a per-warp
 //                                        SWIZZLE_128B smem ring and moved by TMA store / TMA load
 //                                        (fp32 / ragged outputs: direct 16-byte stores)
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
@@ -33,8 +33,9 @@ constexpr int B_BYTES = BN * BK * 2;                 // 32768
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 49152
 constexpr int CHUNK_BYTES = 64 * BK * 2;             // 8192: one 64-wide MN-major chunk
 constexpr int EPI_SLOT_BYTES = 32 * 128;              // 32 rows x 64 bf16 columns, SWIZZLE_128B
-constexpr int EPI_SLOTS = 4;                         // ring per epilogue warp
-constexpr int EPI_RING_BYTES = 4 * EPI_SLOTS * EPI_SLOT_BYTES;   // 64 KB
+constexpr int EPI_WARPS = 8;                         // two epilogue warpgroups, one per accumulator stage
+constexpr int EPI_SLOTS = 2;                         // slots per epilogue warp
+constexpr int EPI_RING_BYTES = EPI_WARPS * EPI_SLOTS * EPI_SLOT_BYTES;   // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_RING_BYTES + 1024;
 // staged-epilogue modes
 constexpr int EPI_GENERIC = 0;                       // direct register -> global stores (fp32 / ragged outputs)
@@ -48,7 +49,7 @@ constexpr int KIND_BIAS = 2;                         // + bias
 constexpr int KIND_FC1 = 3;                          // + bias, pre-activation copy, tanh-GELU
 constexpr int KIND_RESID = 4;                        // + bias + residual tile
 constexpr int KIND_DGELU = 5;                        // * GELU'(pre-activation tile)
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;   // 384
 constexpr uint32_t TMEM_COLS = 512;
 
 struct GemmParams {
@@ -73,6 +74,7 @@ struct GemmParams {
   int vec_ok;
   int epi_mode;
   int epi_kind;
+  int in_row_period;            // > 0: the TMA input tile is a [period, N] table indexed by row % period
   // UMMA descriptor fields (bytes); defaults set by the host, overridable for bring-up
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
 };
@@ -169,7 +171,7 @@ __device__ __forceinline__ void epilogue_vec8(const GemmParams& p, const uint32_
 }
 
 // scalar path for ragged N / unaligned leading dimensions
-__device__ __forceinline__ void epilogue_scalar(const GemmParams& p, float a, int64_t row, int col,
+__device__ __noinline__ void epilogue_scalar(const GemmParams& p, float a, int64_t row, int col,
                                                 uint32_t row_mod, uint32_t row_grp) {
   float x = a * p.alpha;
   if (p.bias) x += __ldg(p.bias + col);
@@ -198,7 +200,7 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, const uint32
   const bool want_aux = G ? (p.aux_out != nullptr) : (KIND == KIND_FC1);
   const int act = G ? p.act : (KIND == KIND_FC1 ? SC_ACT_GELU : SC_ACT_NONE);
   const bool in_dgelu = G ? (p.aux_in != nullptr) : (KIND == KIND_DGELU);
-  const bool in_resid = G ? (p.resid != nullptr) : (KIND == KIND_RESID);
+  const bool in_resid = G ? (p.epi_mode == EPI_IN && p.aux_in == nullptr) : (KIND == KIND_RESID);
   float x[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(acc[j]);
@@ -259,25 +261,29 @@ __device__ __forceinline__ void epilogue_math8(const GemmParams& p, const uint32
 }
 
 // One 128x256 accumulator tile of the staged epilogue for one warp (32 rows): four 64-column chunks, each
-// drained in 16-column steps (tcgen05.ld.x16 -> math -> st.shared into the SWIZZLE_128B slot) and then
-// written with one (two for KIND_FC1) TMA store.
+// drained in 16-column steps (tcgen05.ld.x16 -> math -> st.shared into a SWIZZLE_128B slot) and then written
+// with one (two for EPI_OUT2) TMA store.  Two slots per warp: chunk c uses slot c & 1.  In EPI_IN mode the slot
+// first receives the bf16 input tile by TMA load (chunks 0,1 prefetched before the tile, chunks 2,3 as soon as
+// the store of chunk c-2 has drained the slot) and is overwritten in place with the result.
 template <int KIND>
 __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmAux,
-                                            uint32_t t_addr, uint32_t ring, uint32_t in_bar0, uint32_t in_parity,
-                                            int lane, int n0, int row0, uint32_t row_mod, uint32_t row_grp) {
+                                            const CUtensorMap* tmIn, uint32_t t_addr, uint32_t ring, uint32_t in_bar0,
+                                            int lane, int n0, int row0, int in_row0, uint32_t row_mod,
+                                            uint32_t row_grp) {
   const bool has_in = (p.epi_mode == EPI_IN);
   const bool two_out = (p.epi_mode == EPI_OUT2);
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const int col0 = n0 + c * 64;
     if (col0 >= p.N) break;
-    const uint32_t slot_o = ring + (two_out ? ((2 * c + 1) & 3) : c) * EPI_SLOT_BYTES;
-    const uint32_t slot_a = ring + ((2 * c) & 3) * EPI_SLOT_BYTES;          // pre-activation copy (EPI_OUT2)
+    const int s = c & 1;
+    const uint32_t slot_o = ring + (two_out ? 1 : s) * EPI_SLOT_BYTES;
+    const uint32_t slot_a = ring;                                            // pre-activation copy (EPI_OUT2)
     if (has_in) {
-      mbar_wait(in_bar0 + c * 8, in_parity);
+      mbar_wait(in_bar0 + s * 8, static_cast<uint32_t>(c >> 1) & 1u);        // slot s: use 2t + (c >> 1) of this barrier
     } else if (lane == 0) {
-      // the TMA store that last read these slots must have drained them
-      if (two_out) tma_store_wait_read<2>(); else tma_store_wait_read<3>();
+      // the TMA store that last read the slot(s) must have drained them
+      if (two_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
     }
     __syncwarp();
     const uint32_t row_o = slot_o + lane * 128, row_a = slot_a + lane * 128;
@@ -304,12 +310,14 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      if (two_out) {
-        tma_store_2d(tmAux, slot_a, col0, row0);
-        tma_store_commit();
-      }
+      if (two_out) tma_store_2d(tmAux, slot_a, col0, row0);
       tma_store_2d(tmOut, slot_o, col0, row0);
       tma_store_commit();
+      if (has_in && c < 2) {                                                 // refill the slot with chunk c + 2's input
+        tma_store_wait_read<0>();
+        mbar_arrive_expect_tx(in_bar0 + s * 8, EPI_SLOT_BYTES);
+        tma_load_2d(slot_o, tmIn, in_bar0 + s * 8, col0 + 128, in_row0);
+      }
     }
   }
 }
@@ -324,7 +332,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ __align__(8) uint64_t epi_in_bar[4][EPI_SLOTS];
+  __shared__ __align__(8) uint64_t epi_in_bar[EPI_WARPS][EPI_SLOTS];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms: 1 KB aligned
@@ -340,7 +348,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
     }
-    for (int w = 0; w < 4; ++w)
+    for (int w = 0; w < EPI_WARPS; ++w)
       for (int s = 0; s < EPI_SLOTS; ++s) mbar_init(smem_u32(&epi_in_bar[w][s]), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -419,11 +427,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;                                    // == warp % 4: TMEM lane quarter
-    int as = 0;
-    uint32_t aphase = 0;
+    // two warpgroups: warps 4-7 drain accumulator stage 0 (even tiles), warps 8-11 stage 1 (odd tiles)
+    const int ew = warp - 4;                                   // 0..7
+    const int wg = ew >> 2;
+    const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+    const int as = wg;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+    const int stride2 = 2 * static_cast<int>(gridDim.x);
+    const int first = static_cast<int>(blockIdx.x) + wg * static_cast<int>(gridDim.x);
     if (p.epi_mode == EPI_GENERIC) {
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int t = 0;
+      for (int item = first; item < num_items; item += stride2, ++t) {
         const Item it = decode_item(p, item);
         const int64_t row = static_cast<int64_t>(it.m_blk) * BM + q * 32 + lane;
         const int n0 = it.n_blk * BN;
@@ -431,10 +445,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t row_mod = 0, row_grp = 0;
         if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
         if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
-        mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+        mbar_wait(smem_u32(&tmem_full_bar[as]), static_cast<uint32_t>(t & 1));
         __syncwarp();
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int col0 = n0 + c * 32;
@@ -460,25 +473,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty_bar[as]));
-        as ^= 1;
-        if (as == 0) aphase ^= 1u;
       }
     } else {
-      // ---- staged epilogue: 64-column chunks through a per-warp ring of SWIZZLE_128B slots,
-      //      outputs by TMA store (box 64 x 32), the optional bf16 input tile by TMA load ----
-      const uint32_t ring = smem_base + STAGES * STAGE_BYTES + q * (EPI_SLOTS * EPI_SLOT_BYTES);
+      // ---- staged epilogue: 64-column chunks through per-warp SWIZZLE_128B slots, outputs by TMA store
+      //      (box 64 x 32), the optional bf16 input tile (residual / GELU' operand / pos table) by TMA load ----
+      const uint32_t ring = smem_base + STAGES * STAGE_BYTES + ew * (EPI_SLOTS * EPI_SLOT_BYTES);
       const bool has_in = (p.epi_mode == EPI_IN);
-      int n = 0;
-      if (has_in && lane == 0 && static_cast<int>(blockIdx.x) < num_items) {
-        const Item it = decode_item(p, blockIdx.x);
+      const uint32_t ib0 = smem_u32(&epi_in_bar[ew][0]);
+      auto in_row = [&](int row0) { return p.in_row_period > 0 ? row0 % p.in_row_period : row0; };
+      if (has_in && lane == 0 && first < num_items) {
+        const Item it = decode_item(p, first);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t ib = smem_u32(&epi_in_bar[q][c]);
-          mbar_arrive_expect_tx(ib, EPI_SLOT_BYTES);
-          tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib, it.n_blk * BN + c * 64, it.m_blk * BM + q * 32);
+        for (int c = 0; c < 2; ++c) {
+          mbar_arrive_expect_tx(ib0 + c * 8, EPI_SLOT_BYTES);
+          tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib0 + c * 8, it.n_blk * BN + c * 64, in_row(it.m_blk * BM + q * 32));
         }
       }
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+      int t = 0;
+      for (int item = first; item < num_items; item += stride2, ++t) {
         const Item it = decode_item(p, item);
         const int row0 = it.m_blk * BM + q * 32;
         const int64_t row = min(static_cast<int64_t>(row0) + lane, p.M - 1);   // tail rows: TMA clips the store
@@ -486,34 +498,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t row_mod = 0, row_grp = 0;
         if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
         if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
-        mbar_wait(smem_u32(&tmem_full_bar[as]), aphase);
+        mbar_wait(smem_u32(&tmem_full_bar[as]), static_cast<uint32_t>(t & 1));
         __syncwarp();
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-        const uint32_t ib0 = smem_u32(&epi_in_bar[q][0]);
-        const uint32_t ipar = static_cast<uint32_t>(n & 1);
+        const int ir0 = in_row(row0);
         switch (p.epi_kind) {
-          case KIND_PLAIN: staged_tile<KIND_PLAIN>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
-          case KIND_BIAS:  staged_tile<KIND_BIAS>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
-          case KIND_FC1:   staged_tile<KIND_FC1>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
-          case KIND_RESID: staged_tile<KIND_RESID>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
-          case KIND_DGELU: staged_tile<KIND_DGELU>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
-          default:         staged_tile<KIND_GEN>(p, &tmOut, &tmAux, t_addr, ring, ib0, ipar, lane, n0, row0, row_mod, row_grp); break;
+          case KIND_PLAIN: staged_tile<KIND_PLAIN>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
+          case KIND_BIAS:  staged_tile<KIND_BIAS>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
+          case KIND_FC1:   staged_tile<KIND_FC1>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
+          case KIND_RESID: staged_tile<KIND_RESID>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
+          case KIND_DGELU: staged_tile<KIND_DGELU>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
+          default:         staged_tile<KIND_GEN>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty_bar[as]));
-        as ^= 1;
-        if (as == 0) aphase ^= 1u;
-        // prefetch the next tile's input chunks into the ring once the stores have drained it
-        const int next = item + static_cast<int>(gridDim.x);
+        // prefetch the first two input chunks of this warpgroup's next tile once the stores have drained the slots
+        const int next = item + stride2;
         if (has_in && lane == 0 && next < num_items) {
           tma_store_wait_read<0>();
           const Item nt = decode_item(p, next);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t ib = smem_u32(&epi_in_bar[q][c]);
-            mbar_arrive_expect_tx(ib, EPI_SLOT_BYTES);
-            tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib, nt.n_blk * BN + c * 64, nt.m_blk * BM + q * 32);
+          for (int c = 0; c < 2; ++c) {
+            mbar_arrive_expect_tx(ib0 + c * 8, EPI_SLOT_BYTES);
+            tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib0 + c * 8, nt.n_blk * BN + c * 64, in_row(nt.m_blk * BM + q * 32));
           }
         }
       }
@@ -649,10 +656,16 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   CUtensorMap tmOut, tmAux, tmIn;
   memset(&tmOut, 0, sizeof(tmOut)); memset(&tmAux, 0, sizeof(tmAux)); memset(&tmIn, 0, sizeof(tmIn));
   p.epi_mode = EPI_GENERIC;
-  const bool one_in = (epi->resid != nullptr) != (epi->aux_in != nullptr);
-  const bool no_in = !epi->resid && !epi->aux_in;
-  if (!g_dbg.generic_epi && p.vec_ok && epi->out_bf16 && !epi->out_f32 && p.ksplit == 1 && (no_in || one_in) &&
+  const bool pos16 = epi->rowadd_bf16 != nullptr && epi->rowadd_period % 32 == 0;
+  const int n_in = (epi->resid != nullptr) + (epi->aux_in != nullptr) + (pos16 ? 1 : 0);
+  const bool one_in = n_in == 1;
+  const bool no_in = n_in == 0;
+  SC_REQUIRE(!(epi->rowadd && epi->rowadd_bf16), SC_E_SHAPE, "sc_gemm_bf16: pass rowadd or rowadd_bf16, not both");
+  SC_REQUIRE(!epi->rowadd_bf16 || epi->rowadd_period > 0, SC_E_SHAPE, "sc_gemm_bf16: rowadd_period must be > 0");
+  bool staged_ok = false;
+  if (!g_dbg.generic_epi && p.vec_ok && sc_aligned16(epi->rowadd_bf16) && epi->out_bf16 && !epi->out_f32 && p.ksplit == 1 && (no_in || one_in) &&
       !(one_in && epi->aux_out) && N % BN == 0) {
+    staged_ok = true;
     p.epi_mode = one_in ? EPI_IN : (epi->aux_out ? EPI_OUT2 : EPI_OUT1);
     p.epi_kind = KIND_GEN;
     if (epi->alpha == 1.0f && !epi->rowadd && !epi->rowgrp) {
@@ -660,18 +673,25 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
       if (!b && epi->act == SC_ACT_NONE && !epi->aux_out && no_in) p.epi_kind = KIND_PLAIN;
       else if (b && epi->act == SC_ACT_NONE && !epi->aux_out && no_in) p.epi_kind = KIND_BIAS;
       else if (b && epi->act == SC_ACT_GELU && epi->aux_out && no_in) p.epi_kind = KIND_FC1;
-      else if (b && epi->act == SC_ACT_NONE && epi->resid) p.epi_kind = KIND_RESID;
+      else if (b && epi->act == SC_ACT_NONE && (epi->resid || pos16)) p.epi_kind = KIND_RESID;
       else if (!b && epi->act == SC_ACT_NONE && epi->aux_in) p.epi_kind = KIND_DGELU;
     }
     const uint64_t ldb_bytes = (uint64_t)epi->ldo * 2;
     if ((rc = sc_encode_tmap_2d_bf16(&tmOut, epi->out_bf16, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
     if (epi->aux_out &&
         (rc = sc_encode_tmap_2d_bf16(&tmAux, epi->aux_out, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
-    if (one_in) {
+    if (one_in && pos16) {
+      p.in_row_period = (int)epi->rowadd_period;
+      if ((rc = sc_encode_tmap_2d_bf16(&tmIn, epi->rowadd_bf16, (uint64_t)N, (uint64_t)epi->rowadd_period,
+                                       (uint64_t)N * 2, 64, 32)) != SC_OK) return rc;
+    } else if (one_in) {
       const void* in = epi->resid ? epi->resid : epi->aux_in;
       if ((rc = sc_encode_tmap_2d_bf16(&tmIn, in, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
     }
   }
+  SC_REQUIRE(staged_ok || !epi->rowadd_bf16, SC_E_SHAPE,
+             "sc_gemm_bf16: rowadd_bf16 needs the staged epilogue (bf16 output, N %% 256 == 0, period %% 32 == 0, "
+             "no other bf16 input tile)");
 
   const long long items = 1LL * p.tiles_m * p.tiles_n * p.ksplit;
   int grid = sc_num_sms();

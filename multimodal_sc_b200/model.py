@@ -223,7 +223,7 @@ class Engine:
             tok = ops.patchify(img, patch, out=A.buf(f"{enc}.tok", (M, img.shape[1] * patch * patch)))
             xs = [A.buf(f"{enc}.x{l}", (M, D)) for l in range(sp.enc_layers + 1)]
             ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
-                     rowadd=f.w32(f"{enc}.pos"), out=xs[0])
+                     rowadd=f.w16(f"{enc}.pos"), out=xs[0])
             for l in range(sp.enc_layers):
                 self._block_fwd(A, f"{enc}.blocks.{l}", xs[l], xs[l + 1], B, S, train)
             t = A.buf(f"{enc}.t", (M, D))
@@ -242,7 +242,7 @@ class Engine:
         Md = B * Sd
         xd = [A.buf(f"dec.x{l}", (Md, D)) for l in range(sp.dec_layers + 1)]
         ops.gemm(y16.view(Md, C), f.w16("dec.in_proj.weight"), bias=f.w32("dec.in_proj.bias"),
-                 rowadd=f.w32("dec.pos"), out=xd[0])
+                 rowadd=f.w16("dec.pos"), out=xd[0])
         for l in range(sp.dec_layers):
             self._block_fwd(A, f"dec.blocks.{l}", xd[l], xd[l + 1], B, Sd, train)
         tn = A.buf("dec.tn", (Md, D))

@@ -64,6 +64,8 @@ def _profiled(name):
                 K, M = (A.shape if a_mn else A.shape[::-1])
                 N = B.shape[1] if b_mn else B.shape[0]
                 nm = "gemm_" + ("wgrad" if a_mn else ("dgrad" if b_mn else "fwd"))
+                if getattr(_PROF, "detail", False):
+                    nm += f"[{M}x{N}x{K}]"
                 fl = 2.0 * M * N * K
                 by = 2.0 * (M * K + N * K) + (4.0 if k.get("out_f32") is not None and k.get("out") is None else 2.0) * M * N
                 for extra in ("resid", "aux_in", "aux_out"):
@@ -120,8 +122,11 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, r
         assert out.dtype == BF16
     if out_f32 is not None:
         assert out_f32.dtype == F32
+    rowadd_f32 = rowadd if (rowadd is not None and rowadd.dtype == F32) else None
+    rowadd_b16 = rowadd if (rowadd is not None and rowadd.dtype == BF16) else None
     epi = GemmEpilogue(
-        bias=ptr(bias), rowadd=ptr(rowadd), rowadd_period=(rowadd.shape[0] if rowadd is not None else 0),
+        bias=ptr(bias), rowadd=ptr(rowadd_f32), rowadd_bf16=ptr(rowadd_b16),
+        rowadd_period=(rowadd.shape[0] if rowadd is not None else 0),
         rowgrp=ptr(rowgrp), rowgrp_size=rowgrp_size, rowgrp_scale=rowgrp_scale, alpha=alpha,
         resid=ptr(resid), aux_in=ptr(aux_in), aux_out=ptr(aux_out), out_bf16=ptr(out),
         out_f32=ptr(out_f32), ldo=ldo, act=SC_ACT[act], atomic=int(atomic))

@@ -210,6 +210,24 @@ def _():
     return r
 
 
+@case("staged_pos_bf16")
+def _():
+    """pos-embed add through the TMA input-tile path (bf16 table, row % period)"""
+    import torch
+    from multimodal_sc_b200 import ops
+    oks, rels = [], {}
+    for nm, M, N, K, period in (("cam", 64 * 37, 256, 768, 64), ("dec", 128 * 21, 256, 16, 128)):
+        A, B = _mk(M, N, K, False, False, scale=0.2)
+        bias = torch.randn(N, device="cuda")
+        pos = torch.randn(period, N, device="cuda").bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(A, B, bias=bias, rowadd=pos, out=out)
+        ref = ref_gemm(A, B, False, False) + bias + pos.float().repeat(M // period, 1)
+        r = _report(nm, out, ref)
+        oks.append(r["ok"]); rels[nm] = r["max_rel_err"]
+    return {"case": "staged_pos_bf16", "ok": all(oks), "rels": rels}
+
+
 @case("staged_many_tiles")
 def _():
     """more tiles than CTAs so the slot ring / input prefetch wraps many times; all three staged modes"""
