@@ -60,10 +60,30 @@ patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int64_t g
 }
 
 // ------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, lane owns NCH chunks of 8 contiguous elements (D = 256*NCH)
+// LayerNorm: one warp per row, lane owns NCH chunks of 8 contiguous elements (D = 256*NCH).
+// Each warp handles R rows per iteration and issues all of their 16-byte loads before touching any
+// of them: with 1 row in flight per warp the kernels sat at ~3 TB/s (latency-bound), R rows put
+// R x more bytes in flight per SM.
 // ------------------------------------------------------------------------------------------
-template <typename T, int NCH>
-__global__ void __launch_bounds__(kThreads)
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { uint4 v; };
+template <> struct Raw8<float> { float4 a, b; };
+
+__device__ __forceinline__ void ld_raw(const bf16* p, Raw8<bf16>& r) { r.v = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void ld_raw(const float* p, Raw8<float>& r) {
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void cvt_raw(const Raw8<bf16>& r, float (&x)[8]) {
+  float2 a = unpack_bf16(r.v.x), b = unpack_bf16(r.v.y), c = unpack_bf16(r.v.z), d = unpack_bf16(r.v.w);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+}
+__device__ __forceinline__ void cvt_raw(const Raw8<float>& r, float (&x)[8]) {
+  x[0] = r.a.x; x[1] = r.a.y; x[2] = r.a.z; x[3] = r.a.w; x[4] = r.b.x; x[5] = r.b.y; x[6] = r.b.z; x[7] = r.b.w;
+}
+
+template <typename T, int NCH, int R>
+__global__ void __launch_bounds__(kThreads, 3)
 layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int64_t M, float eps) {
@@ -77,43 +97,55 @@ layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
     load8(gamma + c * 256 + lane * 8, g[c]);
     load8(beta + c * 256 + lane * 8, bta[c]);
   }
-  for (int64_t row = warp0; row < M; row += nwarps) {
-    float v[NCH][8];
-    float s = 0.f;
+  for (int64_t base = warp0 * R; base < M; base += nwarps * R) {
+    Raw8<T> raw[R][NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      load8(x + row * D + c * 256 + lane * 8, v[c]);
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = min(base + r, M - 1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[c][j];
+      for (int c = 0; c < NCH; ++c) ld_raw(x + row * D + c * 256 + lane * 8, raw[r][c]);
     }
-    const float mean = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = base + r;
+      if (row >= M) break;
+      float v[NCH][8];
+      float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[c][j] - mean;
-        q = fmaf(d, d, q);
+      for (int c = 0; c < NCH; ++c) {
+        cvt_raw(raw[r][c], v[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[c][j];
       }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+      const float mean = warp_sum(s) * (1.0f / D);
+      float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      float o[8];
+      for (int c = 0; c < NCH; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[c][j] - mean) * rstd, g[c][j], bta[c][j]);
-      store8(y + row * D + c * 256 + lane * 8, o);
-    }
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[c][j] - mean;
+          q = fmaf(d, d, q);
+        }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((v[c][j] - mean) * rstd, g[c][j], bta[c][j]);
+        store8(y + row * D + c * 256 + lane * 8, o);
+      }
+      if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+      }
     }
   }
 }
 
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; colsum += sum_rows dx
-template <typename T, int NCH>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int NCH, int R>
+__global__ void __launch_bounds__(kThreads, 2)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                      const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma,
@@ -133,43 +165,61 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 #pragma unroll
     for (int j = 0; j < 8; ++j) a_dg[c][j] = a_db[c][j] = a_cs[c][j] = 0.f;
   }
-  for (int64_t row = warp0; row < M; row += nwarps) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NCH][8], g[NCH][8];
-    float s1 = 0.f, s2 = 0.f;
+  for (int64_t base = warp0 * R; base < M; base += nwarps * R) {
+    Raw8<T> rx[R][NCH], rdy[R][NCH], rres[R][NCH];
+    float mu[R], rs[R];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      float xv[8], dyv[8];
-      load8(x + row * D + c * 256 + lane * 8, xv);
-      load8(dy + row * D + c * 256 + lane * 8, dyv);
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = min(base + r, M - 1);
+      mu[r] = mean[row];
+      rs[r] = rstd[row];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xh[c][j] = (xv[j] - mu) * rs;
-        g[c][j] = dyv[j] * gm[c][j];
-        s1 += g[c][j];
-        s2 = fmaf(g[c][j], xh[c][j], s2);
-        a_dg[c][j] = fmaf(dyv[j], xh[c][j], a_dg[c][j]);
-        a_db[c][j] += dyv[j];
+      for (int c = 0; c < NCH; ++c) {
+        const int64_t off = row * D + c * 256 + lane * 8;
+        ld_raw(x + off, rx[r][c]);
+        ld_raw(dy + off, rdy[r][c]);
+        if (dres) ld_raw(dres + off, rres[r][c]);
       }
     }
-    const float m1 = warp_sum(s1) * (1.0f / D);
-    const float m2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      float o[8];
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = base + r;
+      if (row >= M) break;
+      float xh[NCH][8], g[NCH][8];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - m1 - xh[c][j] * m2);
-      if (dres) {
-        float r[8];
-        load8(dres + row * D + c * 256 + lane * 8, r);
+      for (int c = 0; c < NCH; ++c) {
+        float xv[8], dyv[8];
+        cvt_raw(rx[r][c], xv);
+        cvt_raw(rdy[r][c], dyv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += r[j];
+        for (int j = 0; j < 8; ++j) {
+          xh[c][j] = (xv[j] - mu[r]) * rs[r];
+          g[c][j] = dyv[j] * gm[c][j];
+          s1 += g[c][j];
+          s2 = fmaf(g[c][j], xh[c][j], s2);
+          a_dg[c][j] = fmaf(dyv[j], xh[c][j], a_dg[c][j]);
+          a_db[c][j] += dyv[j];
+        }
       }
-      store8(dx + row * D + c * 256 + lane * 8, o);
-      if (colsum) {
-        // accumulate what was actually written (bf16-rounded for T = bf16) — matches a later colsum(dx)
+      const float m1 = warp_sum(s1) * (1.0f / D);
+      const float m2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a_cs[c][j] += o[j];
+      for (int c = 0; c < NCH; ++c) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs[r] * (g[c][j] - m1 - xh[c][j] * m2);
+        if (dres) {
+          float rr[8];
+          cvt_raw(rres[r][c], rr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rr[j];
+        }
+        store8(dx + row * D + c * 256 + lane * 8, o);
+        if (colsum) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a_cs[c][j] += o[j];
+        }
       }
     }
   }
@@ -341,14 +391,14 @@ int sc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
              "sc_layernorm_fwd: M=%lld D=%d (D must be 256, 512 or 1024)", (long long)M, D);
   SC_REQUIRE(sc_aligned16(x) && sc_aligned16(y) && sc_aligned16(gamma) && sc_aligned16(beta), SC_E_ALIGN,
              "sc_layernorm_fwd: unaligned pointer");
-  const int grid = persistent_blocks((M + 7) / 8, 8);
+  const int grid = persistent_blocks((M + 8 * 4 - 1) / (8 * 4), 3);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD(T, NCH) \
-  layernorm_fwd_kernel<T, NCH><<<grid, kThreads, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, M, eps)
+#define LN_FWD(T, NCH, R) \
+  layernorm_fwd_kernel<T, NCH, R><<<grid, kThreads, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, M, eps)
   if (io_f32) {
-    if (D == 256) LN_FWD(float, 1); else if (D == 512) LN_FWD(float, 2); else LN_FWD(float, 4);
+    if (D == 256) LN_FWD(float, 1, 4); else if (D == 512) LN_FWD(float, 2, 1); else LN_FWD(float, 4, 1);
   } else {
-    if (D == 256) LN_FWD(bf16, 1); else if (D == 512) LN_FWD(bf16, 2); else LN_FWD(bf16, 4);
+    if (D == 256) LN_FWD(bf16, 1, 8); else if (D == 512) LN_FWD(bf16, 2, 2); else LN_FWD(bf16, 4, 1);
   }
 #undef LN_FWD
   sc_count_launch(1);
@@ -366,15 +416,15 @@ int sc_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
              "sc_layernorm_bwd: M=%lld D=%d (D must be 256, 512 or 1024)", (long long)M, D);
   SC_REQUIRE(sc_aligned16(dy) && sc_aligned16(x) && sc_aligned16(dx) && sc_aligned16(dres) && sc_aligned16(gamma),
              SC_E_ALIGN, "sc_layernorm_bwd: unaligned pointer");
-  const int grid = persistent_blocks((M + 7) / 8, 4);
+  const int grid = persistent_blocks((M + 8 * 4 - 1) / (8 * 4), 2);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD(T, NCH)                                                                                   \
-  layernorm_bwd_kernel<T, NCH><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma,  \
-                                                          (const T*)dres, (T*)dx, dgamma, dbeta, colsum, M)
+#define LN_BWD(T, NCH, R)                                                                                  \
+  layernorm_bwd_kernel<T, NCH, R><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, \
+                                                             (const T*)dres, (T*)dx, dgamma, dbeta, colsum, M)
   if (io_f32) {
-    if (D == 256) LN_BWD(float, 1); else if (D == 512) LN_BWD(float, 2); else LN_BWD(float, 4);
+    if (D == 256) LN_BWD(float, 1, 2); else if (D == 512) LN_BWD(float, 2, 1); else LN_BWD(float, 4, 1);
   } else {
-    if (D == 256) LN_BWD(bf16, 1); else if (D == 512) LN_BWD(bf16, 2); else LN_BWD(bf16, 4);
+    if (D == 256) LN_BWD(bf16, 1, 4); else if (D == 512) LN_BWD(bf16, 2, 1); else LN_BWD(bf16, 4, 1);
   }
 #undef LN_BWD
   sc_count_launch(1);
