@@ -93,6 +93,9 @@ typedef struct sc_gemm_epilogue {
   int32_t atomic;
   const void* rowadd_bf16; /* bf16 [rowadd_period, N]: same add as `rowadd`, but fetched as a TMA tile
                               (needs bf16 output, N % 256 == 0, period % 32 == 0, no resid / aux_in) */
+  float* colsum;           /* a_mn = 1 (wgrad form) only: colsum[m] += sum_k A(m,k), i.e. the bias gradient
+                              sum_tokens dy[token, m], computed by one extra tcgen05.mma per K-slice against
+                              an all-ones shared-memory tile (no extra memory traffic) */
 } sc_gemm_epilogue;
 
 int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn,

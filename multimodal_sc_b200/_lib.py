@@ -38,6 +38,7 @@ class GemmEpilogue(C.Structure):
         ("act", C.c_int32),
         ("atomic", C.c_int32),
         ("rowadd_bf16", C.c_void_p),
+        ("colsum", C.c_void_p),
     ]
 
 

@@ -74,6 +74,7 @@ struct GemmParams {
   int vec_ok;
   int epi_mode;
   int epi_kind;
+  float* colsum;                // a_mn = 1 only: colsum[m] += sum_k A(m,k) via an extra MMA against an all-ones tile
   int in_row_period;            // > 0: the TMA input tile is a [period, N] table indexed by row % period
   // UMMA descriptor fields (bytes); defaults set by the host, overridable for bring-up
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
@@ -355,12 +356,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
+  // bias-gradient mode: 4 KB of bf16 ones in the (otherwise unused) epilogue ring = the B operand of the
+  // extra row-sum MMA; its layout is irrelevant because every element is 1.0
+  const uint32_t ones_tile = smem_base + STAGES * STAGE_BYTES;
+  if (p.colsum) {
+    for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
+      st_shared_v4(ones_tile + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   const int num_items = p.tiles_m * p.tiles_n * p.ksplit;
+  const bool single_acc = (p.colsum != nullptr);       // stage 1's columns hold the row-sum accumulator
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -416,13 +426,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t ad = umma_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
             const uint64_t bd = umma_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
             umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > it.kb_begin || k > 0) ? 1u : 0u);
+            if (single_acc && it.n_blk == 0) {
+              constexpr uint32_t idesc_ones = umma_idesc_bf16(BM, 16, A_MN, 1);
+              umma_bf16_ss(tmem_base + BN, ad, umma_smem_desc(ones_tile, CHUNK_BYTES, 1024), idesc_ones,
+                           (kb > it.kb_begin || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&empty_bar[stage]));            // smem slot reusable when MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(smem_u32(&tmem_full_bar[as]));             // accumulator complete
-        as ^= 1;
-        if (as == 0) aphase ^= 1u;
+        if (single_acc) {
+          aphase ^= 1u;
+        } else {
+          as ^= 1;
+          if (as == 0) aphase ^= 1u;
+        }
       }
     }
   } else if (warp >= 4) {
@@ -437,7 +456,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int first = static_cast<int>(blockIdx.x) + wg * static_cast<int>(gridDim.x);
     if (p.epi_mode == EPI_GENERIC) {
       int t = 0;
-      for (int item = first; item < num_items; item += stride2, ++t) {
+      const int g_first = single_acc ? static_cast<int>(blockIdx.x) : first;
+      const int g_stride = single_acc ? static_cast<int>(gridDim.x) : stride2;
+      for (int item = (single_acc && wg == 1) ? num_items : g_first; item < num_items; item += g_stride, ++t) {
         const Item it = decode_item(p, item);
         const int64_t row = static_cast<int64_t>(it.m_blk) * BM + q * 32 + lane;
         const int n0 = it.n_blk * BN;
@@ -470,6 +491,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
+        }
+        if (single_acc && it.n_blk == 0) {
+          uint32_t rs;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(rs) : "r"(t_addr + BN) : "memory");
+          tmem_ld_wait();
+          if (row_ok) atomicAdd(p.colsum + row, __uint_as_float(rs));
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty_bar[as]));
@@ -630,6 +657,9 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   p.ldo = epi->ldo;
   p.act = epi->act;
   p.atomic = epi->atomic;
+  p.colsum = epi->colsum;
+  SC_REQUIRE(!epi->colsum || (a_mn == 1 && epi->out_f32 && !epi->out_bf16), SC_E_SHAPE,
+             "sc_gemm_bf16: colsum needs a_mn = 1 and an fp32-only output (the wgrad form)");
   p.vec_ok = (N % 8 == 0) && (epi->ldo % 8 == 0) && sc_aligned16(epi->bias) && sc_aligned16(epi->rowadd) &&
              sc_aligned16(epi->rowgrp) && sc_aligned16(epi->resid) && sc_aligned16(epi->aux_in) &&
              sc_aligned16(epi->aux_out) && sc_aligned16(epi->out_bf16) && sc_aligned16(epi->out_f32);

@@ -157,10 +157,10 @@ class Engine:
         N, K = W.shape
         if dx is not None or dgrad_epi.get("out_f32") is not None:
             ops.gemm(dy, W, b_mn=True, out=dx, **dgrad_epi)
+        # the bias gradient (column sums of dy) rides on the wgrad GEMM as one extra MMA per K-slice
         ops.gemm(dy, x, a_mn=True, b_mn=True, out_f32=f.g(f"{wname}.weight"), atomic=True,
-                 ksplit=_wgrad_ksplit(N, K, dy.shape[0], self.sms))
-        if bias_colsum:
-            ops.colsum(dy, f.g(f"{wname}.bias"))
+                 ksplit=_wgrad_ksplit(N, K, dy.shape[0], self.sms),
+                 colsum=f.g(f"{wname}.bias") if bias_colsum else None)
 
     def _block_fwd(self, A, pfx, x_in, x_out, B, S, train):
         sp, f = self.spec, self.flat

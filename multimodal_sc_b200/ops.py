@@ -94,7 +94,7 @@ def _cuda(*ts):
 @_profiled("gemm")
 def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, rowgrp_size=0,
          rowgrp_scale=1.0, alpha=1.0, resid=None, aux_in=None, aux_out=None, out=None,
-         out_f32=None, act=None, atomic=False, ksplit=1):
+         out_f32=None, act=None, atomic=False, ksplit=1, colsum=None):
     """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of sc_gemm_bf16.
 
     a_mn=False: A is [M,K]; a_mn=True: A is [K,M].  b_mn=False: B is [N,K]; b_mn=True: B is [K,N].
@@ -129,7 +129,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, r
         rowadd_period=(rowadd.shape[0] if rowadd is not None else 0),
         rowgrp=ptr(rowgrp), rowgrp_size=rowgrp_size, rowgrp_scale=rowgrp_scale, alpha=alpha,
         resid=ptr(resid), aux_in=ptr(aux_in), aux_out=ptr(aux_out), out_bf16=ptr(out),
-        out_f32=ptr(out_f32), ldo=ldo, act=SC_ACT[act], atomic=int(atomic))
+        out_f32=ptr(out_f32), ldo=ldo, act=SC_ACT[act], atomic=int(atomic), colsum=ptr(colsum))
     rc = _lib.load().sc_gemm_bf16(ptr(A), ptr(B), M, N, K, int(a_mn), int(b_mn), A.stride(0),
                                   B.stride(0), C.byref(epi), ksplit, stream_ptr())
     check(rc, "sc_gemm_bf16")

@@ -210,6 +210,27 @@ def _():
     return r
 
 
+@case("wgrad_colsum")
+def _():
+    """bias gradient fused into the wgrad GEMM (ones-tile MMA), several shapes incl. ragged rows"""
+    import torch
+    from multimodal_sc_b200 import ops
+    oks, rels = [], {}
+    for nm, Nl, Kl, T, ks in (("fc1", 1024, 256, 8192, 9), ("sym", 16, 256, 4096, 8), ("qkv", 768, 256, 5000, 5),
+                              ("patchlidar", 256, 64, 4096, 3), ("nosplit", 256, 256, 512, 1)):
+        g = torch.Generator(device="cuda").manual_seed(1)
+        dy = torch.randn(T, Nl, generator=g, device="cuda").bfloat16()
+        x = torch.randn(T, Kl, generator=g, device="cuda").bfloat16()
+        dW = torch.zeros(Nl, Kl, device="cuda")
+        db = torch.ones(Nl, device="cuda")
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out_f32=dW, atomic=True, ksplit=ks, colsum=db)
+        r1 = _report(nm + ".dW", dW, dy.float().t() @ x.float())
+        r2 = _report(nm + ".db", db, 1.0 + dy.float().sum(0), tol=2e-3)
+        oks += [r1["ok"], r2["ok"]]
+        rels[nm] = (r1["max_rel_err"], r2["max_rel_err"])
+    return {"case": "wgrad_colsum", "ok": all(oks), "rels": rels}
+
+
 @case("staged_pos_bf16")
 def _():
     """pos-embed add through the TMA input-tile path (bf16 table, row % period)"""
