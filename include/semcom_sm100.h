@@ -117,9 +117,10 @@ int sc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
 /* ---------------------------------------------------------------------------------------
  * Memory-bound fused kernels.
  * ------------------------------------------------------------------------------------- */
-/* a1/a2: img fp32 [B,C,H,W] -> patch tokens bf16 [B*(H/P)*(W/P), C*P*P], feature order (c,py,px) */
-int sc_patchify_bf16(const float* img, void* out, int64_t B, int C, int H, int W, int P,
-                     void* stream);
+/* a1/a2: img [B,C,H,W] (fp32, or bf16 when img_is_bf16 != 0) -> patch tokens bf16
+ * [B*(H/P)*(W/P), C*P*P], feature order (c,py,px); the fp32 -> bf16 cast is fused here. */
+int sc_patchify_bf16(const void* img, int img_is_bf16, void* out, int64_t B, int C, int H, int W,
+                     int P, void* stream);
 
 /* LayerNorm over the last dim D (D % 256 == 0, D <= 1024).  io_f32: 0 = bf16 x/y, 1 = fp32 x/y.
  * mean/rstd: fp32 [M] saved for backward (may be null in fwd for inference). */

@@ -21,10 +21,12 @@
 namespace {
 
 constexpr int kThreads = 192;
+constexpr int kBwdThreads = 64 + 256;              // producer + MMA warps, two compute warpgroups
 constexpr int kTile = 128 * 64 * 2;                 // one 128x64 bf16 tile = 16 KB
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void compute_barrier256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // write 32 fp32 values (columns j0 .. j0+31 of row r) as bf16 into a 128x128 K-major SW128 operand
 // made of two 64-column k-blocks of 16 KB each.
@@ -63,15 +65,18 @@ struct FwdParams {
 // forward
 // ---------------------------------------------------------------------------------------------
 constexpr int kFwdStage = 3 * kTile;                       // Q, K, V
-constexpr int kFwdSmem = 2 * kFwdStage + 2 * kTile + kTile + 1024;   // + P (32 KB) + O staging (16 KB)
+constexpr int fwd_smem(int stages) { return stages * kFwdStage + 2 * kTile + kTile + 1024; }   // + P (32 KB) + O staging (16 KB)
 
-__global__ void __launch_bounds__(kThreads, 1)
+// STAGES = 1: 97 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM; the second CTA's TMA
+// loads and MMAs overlap the first one's softmax (and vice versa).  STAGES = 2: one CTA per SM with prefetch.
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, STAGES == 1 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], s_full, p_full, o_full;
   __shared__ uint32_t tmem_slot;
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t p_buf = smem + 2 * kFwdStage;
+  const uint32_t p_buf = smem + STAGES * kFwdStage;
   const uint32_t o_buf = p_buf + 2 * kTile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -96,8 +101,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     if (lane == 0) {
       int n = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-        const int stage = n & 1;
-        const uint32_t ph = (n >> 1) & 1;
+        const int stage = n % STAGES;
+        const uint32_t ph = (n / STAGES) & 1;
         const int h = item % p.H, row0 = (item / p.H) * 128;
         const uint32_t fb = smem_u32(&full_bar[stage]);
         mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
@@ -114,7 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       int n = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-        const int stage = n & 1;
+        const int stage = n % STAGES;
         const uint32_t st = smem + stage * kFwdStage;
         if (n == 0) {
           mbar_wait(smem_u32(&full_bar[0]), 0);
@@ -132,9 +137,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         umma_commit(smem_u32(&o_full));
         umma_commit(smem_u32(&empty_bar[stage]));
         if (item + static_cast<int>(gridDim.x) < p.num_items) {
-          const int ns = (n + 1) & 1;
+          const int ns = (n + 1) % STAGES;
           const uint32_t nst = smem + ns * kFwdStage;
-          mbar_wait(smem_u32(&full_bar[ns]), ((n + 1) >> 1) & 1);
+          mbar_wait(smem_u32(&full_bar[ns]), ((n + 1) / STAGES) & 1);
           tc_fence_after();
           mma_kk_64(tm_s, nst, nst + kTile, idesc_s, false);
           umma_commit(smem_u32(&s_full));
@@ -238,12 +243,13 @@ struct BwdParams {
 constexpr int kBwdStage = 4 * kTile;                       // Q, K, V, dO
 constexpr int kBwdSmem = 2 * kBwdStage + 4 * kTile + 1024; // + P (32 KB) + dS (32 KB)
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQKV, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], sdp_full, ds_full, grads_full;
   __shared__ uint32_t tmem_slot;
+  __shared__ float delta_part[2][128];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t p_buf = smem + 2 * kBwdStage;
   const uint32_t ds_buf = p_buf + 2 * kTile;
@@ -252,7 +258,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(&sdp_full), 1);
-    mbar_init(smem_u32(&ds_full), 128);
+    mbar_init(smem_u32(&ds_full), 256);
     mbar_init(smem_u32(&grads_full), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQKV);
@@ -335,12 +341,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else {
+    // two compute warpgroups: WG g owns score columns [64 g, 64 g + 64) in both passes, partial row sums of
+    // P o dP are exchanged through shared memory; the gradient tiles are drained half each.
     const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const bool two_seq = (p.S == 64);
-    const int c_lo = two_seq ? (r >> 6) * 2 : 0;
-    const int c_hi = two_seq ? c_lo + 2 : 4;
+    const bool active = !two_seq || (r >> 6) == g;          // S = 64: a row only attends its own sequence's 64 keys
     int n = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
       const int h = item % p.H, row0 = (item / p.H) * 128;
@@ -348,16 +356,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(smem_u32(&sdp_full), n & 1);
       __syncwarp();
       tc_fence_after();
-      compute_barrier();                       // previous item's TMA stores have finished reading p_buf / ds_buf
-      // pass 1: P (bf16 -> smem, kept packed in registers) and delta = rowsum(P o dP)
-      uint32_t pk[64];
+      compute_barrier256();                    // previous item's TMA stores have finished reading p_buf / ds_buf
+      // pass 1: P (bf16 -> smem, kept packed in registers) and this warpgroup's part of delta = rowsum(P o dP)
+      uint32_t pk[32];
       float delta = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < c_lo || c >= c_hi) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * g + cc;
+        if (!active) {
           store_row_chunk_zero(p_buf, r, c * 32);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[c * 16 + j] = 0u;
+          for (int j = 0; j < 16; ++j) pk[cc * 16 + j] = 0u;
           continue;
         }
         uint32_t sv[32], dv[32];
@@ -371,13 +380,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           delta = fmaf(x[j], __uint_as_float(dv[j]), delta);
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pk[c * 16 + j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+        for (int j = 0; j < 16; ++j) pk[cc * 16 + j] = pack_bf16(x[2 * j], x[2 * j + 1]);
         store_row_chunk_bf16(p_buf, r, c * 32, x);
       }
+      delta_part[g][r] = delta;
+      compute_barrier256();
+      delta = delta_part[0][r] + delta_part[1][r];
       // pass 2: dS = P o (dP - delta) / sqrt(d)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < c_lo || c >= c_hi) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * g + cc;
+        if (!active) {
           store_row_chunk_zero(ds_buf, r, c * 32);
           continue;
         }
@@ -387,7 +400,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         float x[32];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float2 pp = unpack_bf16(pk[c * 16 + j]);
+          const float2 pp = unpack_bf16(pk[cc * 16 + j]);
           x[2 * j] = pp.x * (__uint_as_float(dv[2 * j]) - delta) * p.scale;
           x[2 * j + 1] = pp.y * (__uint_as_float(dv[2 * j + 1]) - delta) * p.scale;
         }
@@ -396,14 +409,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(&ds_full));
-      // drain dV, dK, dQ -> bf16 -> staging (aliases p_buf / ds_buf once the MMAs are complete)
+      // drain: WG0 takes dV and the first 32 columns of dQ, WG1 takes dK and the last 32 columns of dQ;
+      // staging aliases p_buf / ds_buf once the MMAs are complete
       mbar_wait(smem_u32(&grads_full), n & 1);
       __syncwarp();
       tc_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < 3; ++t) {
-        const uint32_t src = (t == 0 ? tm_dv : (t == 1 ? tm_dk : tm_dq)) + lane_off;
-        const uint32_t dst = p_buf + t * kTile;
+      {
+        const uint32_t src = (g == 0 ? tm_dv : tm_dk) + lane_off;
+        const uint32_t dst = p_buf + g * kTile;
         uint32_t o0[32], o1[32];
         tmem_ld_32x32b_x32(src, o0);
         tmem_ld_32x32b_x32(src + 32, o1);
@@ -421,10 +434,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                        pack_bf16(__uint_as_float(o1[8 * i + 4]), __uint_as_float(o1[8 * i + 5])),
                        pack_bf16(__uint_as_float(o1[8 * i + 6]), __uint_as_float(o1[8 * i + 7])));
         }
+        uint32_t oq[32];
+        tmem_ld_32x32b_x32(tm_dq + lane_off + g * 32, oq);
+        tmem_ld_wait();
+        const uint32_t dq_dst = p_buf + 2 * kTile;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(sw128(dq_dst, r, 4 * g + i),
+                       pack_bf16(__uint_as_float(oq[8 * i]), __uint_as_float(oq[8 * i + 1])),
+                       pack_bf16(__uint_as_float(oq[8 * i + 2]), __uint_as_float(oq[8 * i + 3])),
+                       pack_bf16(__uint_as_float(oq[8 * i + 4]), __uint_as_float(oq[8 * i + 5])),
+                       pack_bf16(__uint_as_float(oq[8 * i + 6]), __uint_as_float(oq[8 * i + 7])));
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      compute_barrier();
+      compute_barrier256();
       if (threadIdx.x == 64) {
         tma_store_2d(&tmDQKV, p_buf, 2 * HD + h * 64, row0);              // dV
         tma_store_2d(&tmDQKV, p_buf + kTile, HD + h * 64, row0);          // dK
@@ -443,6 +467,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
 }
 
+int g_attn_fwd_stages = 1;
+
 int check_shape(const char* nm, int64_t B, int S, int H) {
   SC_REQUIRE(B > 0 && (S == 64 || S == 128) && H >= 1 && H <= 16, SC_E_SHAPE,
              "%s: B=%lld S=%d H=%d (S must be 64 or 128, d_head is fixed at 64)", nm, (long long)B, S, H);
@@ -451,6 +477,8 @@ int check_shape(const char* nm, int64_t B, int S, int H) {
 }
 
 }  // namespace
+
+void sc_attn_debug_set_fwd_stages(int v) { g_attn_fwd_stages = v; }
 
 extern "C" {
 
@@ -471,12 +499,20 @@ int sc_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int S, int H,
   p.scale_log2 = kLog2e * 0.125f;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(1));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(2));
     SC_REQUIRE(e == cudaSuccess, SC_E_LAUNCH, "sc_attn_fwd: smem attribute: %s", cudaGetErrorString(e));
     attr = true;
   }
-  const int grid = p.num_items < sc_num_sms() ? p.num_items : sc_num_sms();
-  attn_fwd_kernel<<<grid, kThreads, kFwdSmem, (cudaStream_t)stream>>>(tmQKV, tmO, p);
+  if (g_attn_fwd_stages == 2) {
+    const int grid = p.num_items < sc_num_sms() ? p.num_items : sc_num_sms();
+    attn_fwd_kernel<2><<<grid, kThreads, fwd_smem(2), (cudaStream_t)stream>>>(tmQKV, tmO, p);
+  } else {
+    const int cap = 2 * sc_num_sms();
+    const int grid = p.num_items < cap ? p.num_items : cap;
+    attn_fwd_kernel<1><<<grid, kThreads, fwd_smem(1), (cudaStream_t)stream>>>(tmQKV, tmO, p);
+  }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_attn_fwd");
   return SC_OK;
@@ -508,7 +544,7 @@ int sc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
     attr = true;
   }
   const int grid = p.num_items < sc_num_sms() ? p.num_items : sc_num_sms();
-  attn_bwd_kernel<<<grid, kThreads, kBwdSmem, (cudaStream_t)stream>>>(tmQKV, tmDO, tmDQKV, p);
+  attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(tmQKV, tmDO, tmDQKV, p);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_attn_bwd");
   return SC_OK;

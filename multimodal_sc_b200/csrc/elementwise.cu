@@ -35,8 +35,9 @@ inline int persistent_blocks(int64_t work_blocks, int per_sm) {
 // ------------------------------------------------------------------------------------------
 // patchify + cast: one thread per 8 output features (always inside one image row)
 // ------------------------------------------------------------------------------------------
+template <typename TI>
 __global__ void __launch_bounds__(kThreads)
-patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int64_t groups, int C, int H,
+patchify_kernel(const TI* __restrict__ img, bf16* __restrict__ out, int64_t groups, int C, int H,
                 int W, int P) {
   const int Wt = W / P, Ht = H / P;
   const int K = C * P * P;
@@ -52,7 +53,7 @@ patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int64_t g
     const int tx = static_cast<int>(tok % Wt);
     const int ty = static_cast<int>((tok / Wt) % Ht);
     const int64_t b = tok / (Wt * Ht);
-    const float* src = img + ((b * C + c) * H + (ty * P + py)) * static_cast<int64_t>(W) + tx * P + px0;
+    const TI* src = img + ((b * C + c) * H + (ty * P + py)) * static_cast<int64_t>(W) + tx * P + px0;
     float x[8];
     load8(src, x);
     store8(out + g * 8, x);
@@ -366,7 +367,7 @@ cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
 
 extern "C" {
 
-int sc_patchify_bf16(const float* img, void* out, int64_t B, int C, int H, int W, int P, void* stream) {
+int sc_patchify_bf16(const void* img, int img_is_bf16, void* out, int64_t B, int C, int H, int W, int P, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(img && out, SC_E_SHAPE, "sc_patchify_bf16: null pointer");
@@ -376,7 +377,10 @@ int sc_patchify_bf16(const float* img, void* out, int64_t B, int C, int H, int W
   SC_REQUIRE(sc_aligned16(img) && sc_aligned16(out), SC_E_ALIGN, "sc_patchify_bf16: unaligned pointer");
   const int64_t groups = B * C * H * (int64_t)W / 8;
   const int grid = persistent_blocks((groups + kThreads - 1) / kThreads, 8);
-  patchify_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img, (bf16*)out, groups, C, H, W, P);
+  if (img_is_bf16)
+    patchify_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const bf16*)img, (bf16*)out, groups, C, H, W, P);
+  else
+    patchify_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float*)img, (bf16*)out, groups, C, H, W, P);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_patchify_bf16");
   return SC_OK;

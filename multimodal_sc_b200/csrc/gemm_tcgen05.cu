@@ -589,8 +589,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
 
 }  // namespace
 
+void sc_attn_debug_set_fwd_stages(int v);
+
 extern "C" int sc_debug_set(const char* key, int64_t value) {
   if (!key) return SC_E_SHAPE;
+  if (!strcmp(key, "attn_fwd_stages")) { sc_attn_debug_set_fwd_stages((int)value); return SC_OK; }
   if (!strcmp(key, "a_lbo")) g_dbg.a_lbo = value;
   else if (!strcmp(key, "a_sbo")) g_dbg.a_sbo = value;
   else if (!strcmp(key, "a_kstep")) g_dbg.a_kstep = value;

@@ -402,8 +402,9 @@ class SemComPolicy(nn.Module):
     def forward(self, cam, bev, snr_db, *, channel: str = "awgn", seed=None, noise=None, fading=None,
                 sample_offset: int = 0):
         kw = self._kw(snr_db, channel, seed, noise, fading, sample_offset)
-        cam = cam.to(self.device, F32).contiguous()
-        bev = bev.to(self.device, F32).contiguous()
+        # observations may be fp32 or bf16 (the first kernel casts to bf16 either way)
+        cam = cam.to(self.device, cam.dtype if cam.dtype == BF16 else F32).contiguous()
+        bev = bev.to(self.device, bev.dtype if bev.dtype == BF16 else F32).contiguous()
         B, A_ = cam.shape[0], self.spec.n_actions
         if torch.is_grad_enabled():
             ho, lsem = _PolicyFn.apply(self, cam, bev, kw, *self.parameters())

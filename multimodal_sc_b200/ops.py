@@ -142,14 +142,14 @@ def debug_set(key: str, value: int):
 
 @_profiled("patchify")
 def patchify(img, patch: int, out=None):
-    """img fp32 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P]"""
+    """img fp32 or bf16 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P]"""
     _cuda(img)
-    assert img.dtype == F32 and img.is_contiguous()
+    assert img.dtype in (F32, BF16) and img.is_contiguous()
     B, Cc, H, W = img.shape
     T = (H // patch) * (W // patch)
     if out is None:
         out = torch.empty(B * T, Cc * patch * patch, device=img.device, dtype=BF16)
-    check(_lib.load().sc_patchify_bf16(ptr(img), ptr(out), B, Cc, H, W, patch, stream_ptr()), "sc_patchify_bf16")
+    check(_lib.load().sc_patchify_bf16(ptr(img), int(img.dtype == BF16), ptr(out), B, Cc, H, W, patch, stream_ptr()), "sc_patchify_bf16")
     return out
 
 

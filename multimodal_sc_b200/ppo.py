@@ -129,8 +129,9 @@ class PPOAgent:
         n = T * N
         # observations go to the device once (pinned or pageable host tensors both work); minibatches are
         # gathered on the device — a host-side gather of 870 MB per step would dominate the update
-        cam_h = to(rollout["cam"]).reshape(n, *rollout["cam"].shape[2:])
-        bev_h = to(rollout["bev"]).reshape(n, *rollout["bev"].shape[2:])
+        obs_dt = lambda x: x.dtype if x.dtype == torch.bfloat16 else F32
+        cam_h = to(rollout["cam"], obs_dt(rollout["cam"])).reshape(n, *rollout["cam"].shape[2:])
+        bev_h = to(rollout["bev"], obs_dt(rollout["bev"])).reshape(n, *rollout["bev"].shape[2:])
         act = to(rollout["actions"], torch.int64).reshape(n)
         lp = to(rollout["logp"]).reshape(n)
         adv, ret = adv.reshape(n), ret.reshape(n)

@@ -7,8 +7,10 @@ import torch
 from .spec import SpecV0
 
 
-def minibatch(spec: SpecV0, batch: int, seed: int = 0, device="cpu", pin: bool = False) -> dict:
-    """one PPO minibatch: cam, bev, actions, logp_old, adv, ret (fp32 / int64)."""
+def minibatch(spec: SpecV0, batch: int, seed: int = 0, device="cpu", pin: bool = False,
+              obs_dtype=torch.float32) -> dict:
+    """one PPO minibatch: cam, bev, actions, logp_old, adv, ret (fp32 / int64).  obs_dtype=bfloat16 gives the
+    'fp32 -> bf16 once, outside' form of SURVEY.md section 8d (cast on the host, before any timed region)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     cam = torch.rand(batch, spec.cam_ch, spec.cam_hw, spec.cam_hw, generator=g)
     occ = torch.rand(batch, spec.bev_ch, spec.bev_hw, spec.bev_hw, generator=g) < 0.1
@@ -20,6 +22,7 @@ def minibatch(spec: SpecV0, batch: int, seed: int = 0, device="cpu", pin: bool =
         adv=torch.randn(batch, generator=g),
         ret=torch.randn(batch, generator=g),
     )
+    out["cam"], out["bev"] = out["cam"].to(obs_dtype), out["bev"].to(obs_dtype)
     if pin:
         out = {k: v.pin_memory() for k, v in out.items()}
     if device != "cpu":

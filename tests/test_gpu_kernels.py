@@ -105,6 +105,8 @@ def test_patchify(cuda_lib):
         ref = o_patchify(img, P).reshape(-1, C * P * P).bfloat16()
         got = ops.patchify(img.cuda(), P)
         assert torch.equal(got.cpu(), ref)
+        got16 = ops.patchify(img.bfloat16().cuda(), P)                  # bf16 observations: same tokens
+        assert torch.equal(got16.cpu(), ref)
 
 
 @pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
