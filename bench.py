@@ -230,9 +230,19 @@ def run_native(a):
     g_n = sum(v["launches"] for v in gemm.values())
     step_ms_prof = sum(v["ms"] for v in summ.values())
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    g_by = sum(v["bytes"] for v in gemm.values())
+    traffic = None                  # DRAM bytes per launch from the committed ncu capture of this same command
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
+    if os.path.exists(tpath) and B == MB_PER_GPU:
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
     roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all operand-major variants)",
             "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tf_sustained"], "traffic": None,
+            "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
+            "algorithmic_bytes_per_launch": g_by / max(g_n, 1),
+            "hbm_view": {"note": "the D=256 GEMMs sit below the ridge point (AI 128-205 FLOP/B < 214), so their "
+                                 "attainable bound is the HBM roofline; same launches, algorithmic bytes / time",
+                         "achieved_gbs": g_by / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0, "peak_gbs": peaks["hbm_gbs"],
+                         "frac": (g_by / (g_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if g_ms > 0 else 0.0},
             "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
             "launches_per_step": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / max(step_ms_prof, 1e-9),
             "algorithmic_flops_per_step": g_fl,

@@ -1,0 +1,50 @@
+"""Secondary BASELINE.json configs (parity-test cases, not bench lines): measured for the record.
+  cfg2: camera + LiDAR-BEV encoder -> AWGN 10 dB -> decoder forward, batch 256
+  cfg4: Rayleigh fading, SNR sweep -5..20 dB with semantic-distortion loss, batch 1024 (fwd + L_sem + bwd)
+Writes gpurun_out/secondary_configs.json"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multimodal_sc_b200 import _lib, synthetic
+from multimodal_sc_b200.model import SemComPolicy
+from multimodal_sc_b200.spec import SpecV0
+
+sp = SpecV0()
+pol = SemComPolicy(sp)
+eng = pol.engine
+out = {}
+
+def timeit(fn, n=20, warm=5):
+    for _ in range(warm): fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+# cfg2: forward only, B = 256, AWGN 10 dB
+B = 256
+mb = synthetic.minibatch(sp, B, seed=5, device="cuda", obs_dtype=torch.bfloat16)
+l0 = _lib.launch_count()
+ms = timeit(lambda: eng.forward(mb["cam"], mb["bev"], 10.0, "awgn", 77, None, None, 0, train=False))
+out["cfg2_fwd_b256_awgn10"] = {"ms": ms, "samples_per_s": B / ms * 1e3, "launches_per_fwd": (_lib.launch_count() - l0) // 25}
+
+# cfg4: Rayleigh sweep, B = 1024, fwd + L_sem + bwd of the semantic loss only
+B = 1024
+mb = synthetic.minibatch(sp, B, seed=6, device="cuda", obs_dtype=torch.bfloat16)
+snrs = [-5.0, 0.0, 5.0, 10.0, 15.0, 20.0]
+lsem = torch.zeros(1, device="cuda")
+dho = torch.zeros(B, sp.n_actions + 1, device="cuda")
+res = {}
+for snr in snrs:
+    def step():
+        pol.flat.g32.zero_(); lsem.zero_()
+        ho, A = eng.forward(mb["cam"], mb["bev"], snr, "rayleigh", 1234, None, None, 0, train=True)
+        eng.l_sem(A, B, lsem, grad_coef=1.0)
+        eng.backward(A, B, dho, None, "rayleigh", snr, 1234, None, 0)
+    ms = timeit(step, n=10, warm=3)
+    res[str(snr)] = {"ms": ms, "samples_per_s": B / ms * 1e3, "l_sem": float(lsem)}
+out["cfg4_rayleigh_sweep_b1024_fwd_bwd"] = res
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/secondary_configs.json", "w"), indent=1)
+print(json.dumps(out, indent=1))

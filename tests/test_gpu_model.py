@@ -151,3 +151,68 @@ def test_update_runs_and_learns_value(cuda_lib):
         s1 = ag.update(ro)
     assert all(v == v and abs(v) < 1e6 for v in s1.values()), s1
     assert s1["v"] < s0["v"], (s0["v"], s1["v"])
+
+
+def test_dp_shards_equal_full_batch_on_gpu(cuda_lib):
+    """§8e on the native path: the sum of two 'rank' shards' gradients (global noise counters via
+    sample_offset, per-sample terms scaled by 1/global_batch, L_sem by 1/world) equals the gradient of
+    the full minibatch — the two ranks are emulated sequentially on one GPU through the same engine."""
+    from multimodal_sc_b200 import dp, ops
+    from multimodal_sc_b200.model import SemComPolicy
+    pol = SemComPolicy(SPEC, init_std=0.05, seed=2)
+    eng, flat = pol.engine, pol.flat
+    B = 8
+    cam, bev = _inputs(B, seed=3)
+    cam, bev = cam.cuda(), bev.cuda()
+    g = torch.Generator().manual_seed(1)
+    act = torch.randint(0, SPEC.n_actions, (B,), generator=g).cuda()
+    lp = (torch.full((B,), -2.2) + 0.1 * torch.randn(B, generator=g)).cuda()
+    adv, ret = torch.randn(B, generator=g).cuda(), torch.randn(B, generator=g).cuda()
+
+    def run(lo, hi, world):
+        n = hi - lo
+        inv_m, sem_coef = dp.loss_scales(n, world, SPEC.c_sem)
+        stats = torch.zeros(8, device="cuda")
+        ho, A = eng.forward(cam[lo:hi].contiguous(), bev[lo:hi].contiguous(), 8.0, "rayleigh", 99, None, None, lo,
+                            train=True)
+        eng.l_sem(A, n, stats[5:6], grad_coef=sem_coef)
+        dho = torch.empty_like(ho)
+        ops.ppo_loss(ho, act[lo:hi].contiguous(), lp[lo:hi].contiguous(), adv[lo:hi].contiguous(),
+                     ret[lo:hi].contiguous(), SPEC.n_actions, SPEC.clip_eps, SPEC.c_v, SPEC.c_ent, inv_m, dho=dho,
+                     stats=stats)
+        eng.backward(A, n, dho, None, "rayleigh", 8.0, 99, None, lo)
+        return stats
+
+    flat.g32.zero_()
+    s_full = run(0, B, 1)
+    g_full = flat.g32.clone()
+    flat.g32.zero_()
+    s_a = run(0, B // 2, 2)
+    s_b = run(B // 2, B, 2)
+    g_dp = flat.g32.clone()
+    cos = float((g_full.double() @ g_dp.double()) / (g_full.double().norm() * g_dp.double().norm()))
+    assert cos > 0.9999, cos
+    assert abs(float(g_dp.norm() / g_full.norm()) - 1.0) < 2e-3
+    s_sum = s_a + s_b
+    s_sum[5] = s_sum[5] / 2
+    assert torch.allclose(s_sum[:6].cpu(), s_full[:6].cpu(), rtol=2e-3, atol=1e-5), (s_sum, s_full)
+
+
+def test_forward_single_sample_and_large_batch_properties(cuda_lib):
+    """edge sizes: B = 1 runs; at B = 2048 the channel keeps unit power and the requested SNR."""
+    from multimodal_sc_b200.model import SemComPolicy
+    from oracle import channel as och
+    pol = SemComPolicy(SPEC, init_std=0.05, seed=4)
+    cam, bev = _inputs(1, seed=7)
+    with torch.no_grad():
+        l, v, aux = pol(cam.cuda(), bev.cuda(), 10.0, seed=3)
+    assert l.shape == (1, SPEC.n_actions) and torch.isfinite(l).all() and torch.isfinite(v).all()
+    B = 2048
+    g = torch.Generator(device="cuda").manual_seed(0)
+    camb = torch.rand(B, 3, 128, 128, generator=g, device="cuda", dtype=torch.float32).bfloat16()
+    bevb = torch.rand(B, 1, 64, 64, generator=g, device="cuda", dtype=torch.float32).bfloat16()
+    with torch.no_grad():
+        l, v, aux = pol(camb, bevb, 5.0, channel="awgn", seed=11)
+    assert torch.isfinite(l).all()
+    assert abs(float(aux["z"].pow(2).mean()) - 1.0) < 1e-3
+    assert abs(och.empirical_snr_db(aux["z"].cpu(), aux["y"].cpu()) - 5.0) < 0.1
