@@ -30,6 +30,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
 __device__ __forceinline__ float u32_to_uniform(uint32_t x) {
   return (static_cast<float>(x >> 9) + 0.5f) * 1.1920928955078125e-07f;   // 2^-23, exact
 }
+// Box-Muller with the accurate logf / sincospif: an SFU version (lg2.approx, sin/cos.approx) was ~20 % faster
+// but broke the fp32 parity tolerance (rtol 1e-5 + atol 2e-5) on 2 of 131072 Rayleigh outputs, and parity is the
+// first gate.  With the accurate functions the forward kernel is ALU-bound (~0.3-0.4 of the HBM roofline at large
+// B, profiles/r1_microbench.json); backward needs no noise and runs at 0.58-0.92 of HBM.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
   const float r = sqrtf(-2.0f * logf(u32_to_uniform(a)));
   float s, c;
@@ -212,6 +216,121 @@ __global__ void philox_words_kernel(uint32_t* out, int64_t n_quads, uint32_t str
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// warp-per-row variants (k <= 2048): the row lives in one warp's registers, the reduction is pure
+// shuffles, and 8 independent rows are in flight per CTA — no block barrier on the critical path.
+// ------------------------------------------------------------------------------------------
+constexpr int kWarpV = 16;                    // float4 per lane -> k <= 2048
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads)
+pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = a.k / 4;
+  for (int64_t row = warp0; row < a.B * 2; row += nwarps) {
+    const int64_t b = row >> 1;
+    const int m = static_cast<int>(row & 1);
+    const float* zr = a.z + b * a.z_sb + m * a.z_sm;
+    float4 v[NV];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + i * 32;
+      if (q < nv) {
+        v[i] = *reinterpret_cast<const float4*>(zr + q * 4);
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    }
+    ss = warp_sum(ss);
+    const float scale = rsqrtf(ss / static_cast<float>(a.k) + a.eps);
+    if (lane == 0 && a.scale) a.scale[row] = scale;
+    float sigma = 0.f, hr = 1.f, hi = 0.f, inv_den = 1.f;
+    if (a.kind != SC_CH_NONE) sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
+    if (a.kind == SC_CH_RAYLEIGH) {
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, a.key0, a.key1);
+      hr = h.x; hi = h.y;
+      inv_den = 1.0f / (hr * hr + hi * hi + sigma * sigma);
+    }
+    const uint64_t quad0 = (static_cast<uint64_t>(a.sample_offset + b) * 2 + m) * static_cast<uint64_t>(nv);
+    float* yf = a.y_f32 ? a.y_f32 + b * a.y_sb + m * a.y_sm : nullptr;
+    bf16* yb = a.y_bf16 ? a.y_bf16 + b * a.y_sb + m * a.y_sm : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + i * 32;
+      if (q < nv) {
+        float4 s = make_float4(v[i].x * scale, v[i].y * scale, v[i].z * scale, v[i].w * scale);
+        float4 o = s;
+        if (a.kind != SC_CH_NONE) {
+          float4 n;
+          if (a.noise) n = *reinterpret_cast<const float4*>(a.noise + row * a.k + q * 4);
+          else n = normal4(quad0 + q, 0u, a.key0, a.key1);
+          if (a.kind == SC_CH_AWGN) {
+            o = make_float4(fmaf(sigma, n.x, s.x), fmaf(sigma, n.y, s.y), fmaf(sigma, n.z, s.z), fmaf(sigma, n.w, s.w));
+          } else {
+            const float r0r = hr * s.x - hi * s.y + sigma * n.x, r0i = hr * s.y + hi * s.x + sigma * n.y;
+            const float r1r = hr * s.z - hi * s.w + sigma * n.z, r1i = hr * s.w + hi * s.z + sigma * n.w;
+            o = make_float4((hr * r0r + hi * r0i) * inv_den, (hr * r0i - hi * r0r) * inv_den,
+                            (hr * r1r + hi * r1i) * inv_den, (hr * r1i - hi * r1r) * inv_den);
+          }
+        }
+        if (yf) *reinterpret_cast<float4*>(yf + q * 4) = o;
+        if (yb) *reinterpret_cast<uint2*>(yb + q * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads)
+pnorm_channel_bwd_warp_kernel(const ChanBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = a.k / 4;
+  for (int64_t row = warp0; row < a.B * 2; row += nwarps) {
+    const int64_t b = row >> 1;
+    const int m = static_cast<int>(row & 1);
+    const float* zr = a.z + b * a.z_sb + m * a.z_sm;
+    const float* gr = a.dy + b * a.y_sb + m * a.y_sm;
+    const float scale = a.scale[row];
+    float gain = 1.f;
+    if (a.kind == SC_CH_RAYLEIGH) {
+      const float sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, a.key0, a.key1);
+      const float h2 = h.x * h.x + h.y * h.y;
+      gain = h2 / (h2 + sigma * sigma);
+    }
+    float4 zn[NV], g[NV];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + i * 32;
+      if (q < nv) {
+        const float4 zv = *reinterpret_cast<const float4*>(zr + q * 4);
+        const float4 gv = *reinterpret_cast<const float4*>(gr + q * 4);
+        zn[i] = make_float4(zv.x * scale, zv.y * scale, zv.z * scale, zv.w * scale);
+        g[i] = make_float4(gv.x * gain, gv.y * gain, gv.z * gain, gv.w * gain);
+        dot += g[i].x * zn[i].x + g[i].y * zn[i].y + g[i].z * zn[i].z + g[i].w * zn[i].w;
+      }
+    }
+    dot = warp_sum(dot) / static_cast<float>(a.k);
+    float* df = a.dz_f32 ? a.dz_f32 + b * a.z_sb + m * a.z_sm : nullptr;
+    bf16* db = a.dz_bf16 ? a.dz_bf16 + b * a.z_sb + m * a.z_sm : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + i * 32;
+      if (q < nv) {
+        const float4 o = make_float4(scale * (g[i].x - zn[i].x * dot), scale * (g[i].y - zn[i].y * dot),
+                                     scale * (g[i].z - zn[i].z * dot), scale * (g[i].w - zn[i].w * dot));
+        if (df) *reinterpret_cast<float4*>(df + q * 4) = o;
+        if (db) *reinterpret_cast<uint2*>(db + q * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
 int check_common(const char* nm, int64_t B, int k, int kind, int64_t sb, int64_t sm) {
   SC_REQUIRE(B > 0 && k > 0 && k % 4 == 0 && k <= kMaxV * kThreads * 4, SC_E_SHAPE,
              "%s: B=%lld k=%d (need k %% 4 == 0 and k <= %d)", nm, (long long)B, k, kMaxV * kThreads * 4);
@@ -244,9 +363,16 @@ int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f3
   a.key0 = (uint32_t)(seed & 0xffffffffu); a.key1 = (uint32_t)(seed >> 32);
   a.sample_offset = sample_offset; a.noise = noise; a.fading = fading; a.eps = eps;
   const int64_t rows = B * 2;
-  const int64_t cap = (int64_t)sc_num_sms() * 8;
-  const int grid = (int)(rows < cap ? rows : cap);
-  pnorm_channel_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  if (k <= 1024) {                               // warp per row, 8 rows per CTA
+    const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 8;
+    pnorm_channel_fwd_warp_kernel<8><<<(int)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  } else if (k <= kWarpV * 128) {
+    const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 4;
+    pnorm_channel_fwd_warp_kernel<kWarpV><<<(int)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    const int64_t cap = (int64_t)sc_num_sms() * 8;
+    pnorm_channel_fwd_kernel<<<(int)(rows < cap ? rows : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_pnorm_channel_fwd");
   return SC_OK;
@@ -271,9 +397,16 @@ int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const floa
   a.key0 = (uint32_t)(seed & 0xffffffffu); a.key1 = (uint32_t)(seed >> 32);
   a.sample_offset = sample_offset; a.fading = fading;
   const int64_t rows = B * 2;
-  const int64_t cap = (int64_t)sc_num_sms() * 8;
-  const int grid = (int)(rows < cap ? rows : cap);
-  pnorm_channel_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  if (k <= 1024) {
+    const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 6;
+    pnorm_channel_bwd_warp_kernel<8><<<(int)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  } else if (k <= kWarpV * 128) {
+    const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 3;
+    pnorm_channel_bwd_warp_kernel<kWarpV><<<(int)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    const int64_t cap = (int64_t)sc_num_sms() * 8;
+    pnorm_channel_bwd_kernel<<<(int)(rows < cap ? rows : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_pnorm_channel_bwd");
   return SC_OK;

@@ -222,6 +222,59 @@ gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const f
   }
 }
 
+// Large-N form: one thread per environment walks t = T-1 .. 0 (the recurrence is a single FMA per step);
+// loads of 8 timesteps are issued before they are consumed, every access is coalesced across environments.
+// Same arithmetic as the oracle's loop.  Used when N is large enough to fill the machine this way.
+__global__ void __launch_bounds__(128)
+gae_thread_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ done,
+                  const float* __restrict__ last_value, float* __restrict__ adv, float* __restrict__ ret,
+                  double* __restrict__ sums, int T, int64_t N, float gamma, float lam) {
+  __shared__ double ssum[2];
+  if (threadIdx.x < 2) ssum[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int64_t n = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  double acc_s = 0.0, acc_q = 0.0;
+  if (n < N) {
+    float next_v = last_value[n], A = 0.f;
+    constexpr int U = 8;
+    for (int t_hi = T; t_hi > 0; t_hi -= U) {
+      float r[U], v[U], d[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int t = t_hi - 1 - j;
+        if (t >= 0) {
+          const int64_t o = static_cast<int64_t>(t) * N + n;
+          r[j] = rew[o]; v[j] = val[o]; d[j] = done[o];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int t = t_hi - 1 - j;
+        if (t >= 0) {
+          const float nd = 1.f - d[j];
+          const float delta = r[j] + gamma * next_v * nd - v[j];
+          A = delta + gamma * lam * nd * A;
+          const int64_t o = static_cast<int64_t>(t) * N + n;
+          adv[o] = A;
+          ret[o] = A + v[j];
+          acc_s += A;
+          acc_q += static_cast<double>(A) * A;
+          next_v = v[j];
+        }
+      }
+    }
+  }
+  if (sums) {
+    for (int o = 16; o > 0; o >>= 1) {
+      acc_s += __shfl_xor_sync(0xffffffffu, acc_s, o);
+      acc_q += __shfl_xor_sync(0xffffffffu, acc_q, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&ssum[0], acc_s); atomicAdd(&ssum[1], acc_q); }
+    __syncthreads();
+    if (threadIdx.x < 2) atomicAdd(sums + threadIdx.x, ssum[threadIdx.x]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 adv_normalize_kernel(float* __restrict__ adv, const double* __restrict__ sums, int64_t count, int64_t n,
                      float eps) {
@@ -402,9 +455,16 @@ int sc_gae(const float* rewards, const float* values, const float* dones, const 
   if (rc != SC_OK) return rc;
   SC_REQUIRE(rewards && values && dones && last_value && adv && ret, SC_E_SHAPE, "sc_gae: null pointer");
   SC_REQUIRE(T > 0 && N > 0, SC_E_SHAPE, "sc_gae: T=%d N=%lld", T, (long long)N);
-  const int grid = (int)((N + 31) / 32);
-  gae_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_value, adv, ret, sums, T, N,
-                                                      gamma, lam);
+  if (N >= 16384) {
+    // enough environments to fill the GPU with one thread each: fully coalesced streaming form
+    gae_thread_kernel<<<(int)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_value,
+                                                                               adv, ret, sums, T, N, gamma, lam);
+  } else {
+    // few environments (the PPO configs: 32..256): parallelise over time with the warp-shuffle scan
+    const int grid = (int)((N + 31) / 32);
+    gae_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_value, adv, ret, sums, T, N,
+                                                        gamma, lam);
+  }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_gae");
   return SC_OK;

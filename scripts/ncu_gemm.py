@@ -7,13 +7,19 @@ from multimodal_sc_b200 import ops
 shape = sys.argv[1] if len(sys.argv) > 1 else "fc1"
 M = 262144
 cfg = {"fc1": (1024, 256, dict(act="gelu", aux=True)), "proj": (256, 256, dict(resid=True)),
-       "fc2": (256, 1024, dict(resid=True)), "qkv": (768, 256, {})}[shape]
+       "fc2": (256, 1024, dict(resid=True)), "qkv": (768, 256, {}), "dgelu": (1024, 256, dict(dgelu=True))}[shape]
 N, K, kw = cfg
 A = torch.randn(M, K, device="cuda").bfloat16()
 B = torch.randn(N, K, device="cuda").bfloat16()
+b_mn = False
+if kw.get("dgelu"):
+    B = torch.randn(K, N, device="cuda").bfloat16()     # dgrad form: W stored [K_red, N_out]
+    b_mn = True
 bias = torch.randn(N, device="cuda")
 out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-args = dict(bias=bias, out=out)
+args = dict(bias=bias, out=out, b_mn=b_mn)
+if kw.get("dgelu"):
+    args = dict(out=out, b_mn=True, aux_in=torch.randn(M, N, device="cuda").bfloat16())
 if kw.get("aux"):
     args.update(act="gelu", aux_out=torch.empty_like(out))
 if kw.get("resid"):

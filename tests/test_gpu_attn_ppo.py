@@ -85,7 +85,7 @@ def test_sample_action_bit_exact(cuda_lib):
     _close(lp, lp_ref, 1e-5, 1e-6, "logp")
 
 
-@pytest.mark.parametrize("T,N", [(128, 32), (128, 256), (1, 1), (37, 5), (200, 33)])
+@pytest.mark.parametrize("T,N", [(128, 32), (128, 256), (1, 1), (37, 5), (200, 33), (21, 16384 + 3)])
 def test_gae(cuda_lib, T, N):
     from multimodal_sc_b200 import ops
     g = torch.Generator().manual_seed(T * N)
