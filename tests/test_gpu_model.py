@@ -216,3 +216,22 @@ def test_forward_single_sample_and_large_batch_properties(cuda_lib):
     assert torch.isfinite(l).all()
     assert abs(float(aux["z"].pow(2).mean()) - 1.0) < 1e-3
     assert abs(och.empirical_snr_db(aux["z"].cpu(), aux["y"].cpu()) - 5.0) < 0.1
+
+
+def test_forward_matches_committed_golden_vectors(cuda_lib):
+    """native forward at the default init / seed 0 / B = 2 against tests/golden/oracle_v0.pt (the frozen
+    oracle outputs of scripts/make_golden.py), bf16 tolerance."""
+    import os
+    from multimodal_sc_b200 import synthetic
+    from multimodal_sc_b200.model import SemComPolicy
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_v0.pt"))
+    pol = SemComPolicy(SPEC)                       # same init rule and host RNG stream as the oracle
+    mb = synthetic.minibatch(SPEC, 2, seed=0)
+    with torch.no_grad():
+        for kind in ("awgn", "rayleigh"):
+            l, v, aux = pol(mb["cam"].cuda(), mb["bev"].cuda(), 10.0, channel=kind, seed=1234)
+            assert _rel(l, g[f"fwd_{kind}_logits"]) < 2e-2, (kind, "logits", _rel(l, g[f"fwd_{kind}_logits"]))
+            assert _rel(v, g[f"fwd_{kind}_value"]) < 2e-2, (kind, "value")
+            assert abs(float(aux["l_sem"]) - float(g[f"fwd_{kind}_l_sem"])) < 2e-2 * float(g[f"fwd_{kind}_l_sem"])
+            assert _rel(aux["y"][:, :, :8], g[f"fwd_{kind}_y_head"]) < 2e-2
+            assert _rel(aux["z"][:, :, :8], g[f"fwd_{kind}_z_head"]) < 2e-2
