@@ -27,16 +27,26 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;                 // 16384
-constexpr int B_BYTES = BN * BK * 2;                 // 32768
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 49152
+// CTA2 = 0: one CTA per tile (cta_group::1), B tile 256 x 64 per stage, 3 stages of 48 KB.
+// CTA2 = 1: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile; each CTA stages its own 128 A rows
+//           and HALF of the B tile (128 x 64) -> 32 KB stages, 4 of them, and half the B shared-memory traffic per SM.
+// NWG = epilogue warpgroups (1 or 2): the second warpgroup costs 32 KB of staging slots = one pipeline stage.
+template <int CTA2, int NWG> struct Geo {
+  static constexpr int STAGES = (CTA2 ? 4 : 3) + (NWG == 1 ? 1 : 0);
+  static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES;
+  static constexpr int RING = NWG * 4 * 2 * (32 * 128);                   // NWG x 4 warps x 2 slots x 4 KB
+  static constexpr int THREADS = 128 + NWG * 128;
+};
 constexpr int CHUNK_BYTES = 64 * BK * 2;             // 8192: one 64-wide MN-major chunk
 constexpr int EPI_SLOT_BYTES = 32 * 128;              // 32 rows x 64 bf16 columns, SWIZZLE_128B
 constexpr int EPI_WARPS = 8;                         // two epilogue warpgroups, one per accumulator stage
 constexpr int EPI_SLOTS = 2;                         // slots per epilogue warp
 constexpr int EPI_RING_BYTES = EPI_WARPS * EPI_SLOTS * EPI_SLOT_BYTES;   // 64 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_RING_BYTES + 1024;
+template <int CTA2, int NWG> constexpr int smem_bytes() { return Geo<CTA2, NWG>::SMEM + Geo<CTA2, NWG>::RING + 1024; }
 // staged-epilogue modes
 constexpr int EPI_GENERIC = 0;                       // direct register -> global stores (fp32 / ragged outputs)
 constexpr int EPI_OUT1 = 1;                          // bf16 out via smem + TMA store
@@ -323,11 +333,14 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
   }
 }
 
-template <int A_MN, int B_MN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int A_MN, int B_MN, int CTA2, int NWG>
+__global__ void __launch_bounds__(128 + NWG * 128, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
                     const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
+  using G = Geo<CTA2, NWG>;
+  constexpr int STAGES = G::STAGES;
+  constexpr int STAGE_BYTES = G::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -339,6 +352,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms: 1 KB aligned
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;       // 0 = MMA leader of the pair
+  const int ncta = CTA2 ? 2 : 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -347,7 +362,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
+      mbar_init(smem_u32(&tmem_empty_bar[s]), 128 * ncta);   // pair: both CTAs' epilogue warpgroups arrive on the leader's
     }
     for (int w = 0; w < EPI_WARPS; ++w)
       for (int s = 0; s < EPI_SLOTS; ++s) mbar_init(smem_u32(&epi_in_bar[w][s]), 1);
@@ -355,10 +370,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
+  if (warp == 2) {
+    if (CTA2) tmem_alloc_2sm<TMEM_COLS>(smem_u32(&tmem_base_slot));
+    else tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
+  }
   // bias-gradient mode: 4 KB of bf16 ones in the (otherwise unused) epilogue ring = the B operand of the
   // extra row-sum MMA; its layout is irrelevant because every element is 1.0
-  const uint32_t ones_tile = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t ones_tile = smem_base + G::SMEM;
   if (p.colsum) {
     for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
       st_shared_v4(ones_tile + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -366,10 +384,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();            // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // CTA2: p.tiles_m counts 256-row tile pairs; this CTA owns 128-row block 2 * pair + rank of each
   const int num_items = p.tiles_m * p.tiles_n * p.ksplit;
+  const int cta_stride = CTA2 ? static_cast<int>(gridDim.x) / 2 : static_cast<int>(gridDim.x);
+  const int cta_first = CTA2 ? static_cast<int>(blockIdx.x) / 2 : static_cast<int>(blockIdx.x);
+  auto get_item = [&](int item) {
+    Item it = decode_item(p, item);
+    if (CTA2) it.m_blk = it.m_blk * 2 + static_cast<int>(rank);
+    return it;
+  };
   const bool single_acc = (p.colsum != nullptr);       // stage 1's columns hold the row-sum accumulator
 
   if (warp == 0) {
@@ -377,27 +404,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const Item it = decode_item(p, item);
-        const int m0 = it.m_blk * BM, n0 = it.n_blk * BN;
+      for (int item = cta_first; item < num_items; item += cta_stride) {
+        const Item it = get_item(item);
+        const int m0 = it.m_blk * BM;
+        const int n0 = it.n_blk * BN + static_cast<int>(rank) * G::B_ROWS;   // pair: this CTA's half of B
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
-          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t fb_local = smem_u32(&full_bar[stage]);
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          mbar_arrive_expect_tx(fb, STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
           const int k0 = kb * BK;
-          if (A_MN == 0) {
-            tma_load_2d(a_dst, &tmA, fb, k0, m0);
-          } else {
+          if (CTA2) {
+            // all bytes of both CTAs are accounted on the LEADER's full barrier
+            const uint32_t fb = mapa_shared(fb_local, 0);
+            if (rank == 0) mbar_arrive_expect_tx(fb_local, 2 * STAGE_BYTES);
+            if (A_MN == 0) {
+              tma_load_2d_2sm(a_dst, &tmA, fb, k0, m0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
-          }
-          if (B_MN == 0) {
-            tma_load_2d(b_dst, &tmB, fb, k0, n0);
-          } else {
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
+            }
+            if (B_MN == 0) {
+              tma_load_2d_2sm(b_dst, &tmB, fb, k0, n0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
+              for (int c = 0; c < G::B_ROWS / 64; ++c)
+                tma_load_2d_2sm(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
+            }
+          } else {
+            const uint32_t fb = fb_local;
+            mbar_arrive_expect_tx(fb, STAGE_BYTES);
+            if (A_MN == 0) {
+              tma_load_2d(a_dst, &tmA, fb, k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
+            }
+            if (B_MN == 0) {
+              tma_load_2d(b_dst, &tmB, fb, k0, n0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -405,14 +453,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && rank == 0) {                              // pair: only the leader CTA issues MMAs
+      constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const Item it = decode_item(p, item);
+      for (int item = cta_first; item < num_items; item += cta_stride) {
+        const Item it = get_item(item);
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -425,17 +473,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = umma_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
             const uint64_t bd = umma_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
-            umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > it.kb_begin || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > it.kb_begin || k > 0) ? 1u : 0u;
+            if (CTA2) umma_bf16_ss_2sm(d_tmem, ad, bd, idesc, acc);
+            else umma_bf16_ss(d_tmem, ad, bd, idesc, acc);
             if (single_acc && it.n_blk == 0) {
-              constexpr uint32_t idesc_ones = umma_idesc_bf16(BM, 16, A_MN, 1);
-              umma_bf16_ss(tmem_base + BN, ad, umma_smem_desc(ones_tile, CHUNK_BYTES, 1024), idesc_ones,
-                           (kb > it.kb_begin || k > 0) ? 1u : 0u);
+              constexpr uint32_t idesc_ones = umma_idesc_bf16(CTA2 ? 2 * BM : BM, 16, A_MN, 1);
+              const uint64_t od = umma_smem_desc(ones_tile, CHUNK_BYTES, 1024);
+              if (CTA2) umma_bf16_ss_2sm(tmem_base + BN, ad, od, idesc_ones, acc);
+              else umma_bf16_ss(tmem_base + BN, ad, od, idesc_ones, acc);
             }
           }
-          umma_commit(smem_u32(&empty_bar[stage]));            // smem slot reusable when MMAs retire
+          // smem slot reusable (in both CTAs of a pair) when the MMAs retire
+          if (CTA2) umma_commit_2sm(smem_u32(&empty_bar[stage])); else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&tmem_full_bar[as]));             // accumulator complete
+        // accumulator complete (published to both CTAs of a pair)
+        if (CTA2) umma_commit_2sm(smem_u32(&tmem_full_bar[as])); else umma_commit(smem_u32(&tmem_full_bar[as]));
         if (single_acc) {
           aphase ^= 1u;
         } else {
@@ -447,26 +500,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // two warpgroups: warps 4-7 drain accumulator stage 0 (even tiles), warps 8-11 stage 1 (odd tiles)
-    const int ew = warp - 4;                                   // 0..7
+    // NWG = 2: warps 4-7 take the even tiles of this CTA, warps 8-11 the odd ones; NWG = 1: warps 4-7 take all.
+    // Tile n of the CTA always uses accumulator stage n & 1 and phase (n >> 1) & 1.
+    const int ew = warp - 4;                                   // 0 .. 4*NWG-1
     const int wg = ew >> 2;
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
-    const int as = wg;
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-    const int stride2 = 2 * static_cast<int>(gridDim.x);
-    const int first = static_cast<int>(blockIdx.x) + wg * static_cast<int>(gridDim.x);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int stride2 = NWG * cta_stride;
+    const int first = cta_first + wg * cta_stride;
+    // pair: the leader's MMA thread waits for BOTH CTAs' epilogues -> arrive on the leader's barrier
+    auto release_acc = [&](int as) {
+      const uint32_t local = smem_u32(&tmem_empty_bar[as]);
+      if (CTA2) mbar_arrive_cluster(mapa_shared(local, 0)); else mbar_arrive(local);
+    };
     if (p.epi_mode == EPI_GENERIC) {
-      int t = 0;
-      const int g_first = single_acc ? static_cast<int>(blockIdx.x) : first;
-      const int g_stride = single_acc ? static_cast<int>(gridDim.x) : stride2;
-      for (int item = (single_acc && wg == 1) ? num_items : g_first; item < num_items; item += g_stride, ++t) {
-        const Item it = decode_item(p, item);
+      const int g_first = single_acc ? cta_first : first;
+      const int g_stride = single_acc ? cta_stride : stride2;
+      int n = single_acc ? 0 : wg;                             // index of the tile within this CTA's sequence
+      const int n_step = single_acc ? 1 : NWG;
+      for (int item = (single_acc && wg == 1) ? num_items : g_first; item < num_items; item += g_stride, n += n_step) {
+        const Item it = get_item(item);
+        const int as = single_acc ? 0 : (n & 1);
+        const uint32_t par = single_acc ? static_cast<uint32_t>(n & 1) : static_cast<uint32_t>((n >> 1) & 1);
+        const uint32_t t_addr = t_lane + static_cast<uint32_t>(as * BN);
         const int64_t row = static_cast<int64_t>(it.m_blk) * BM + q * 32 + lane;
         const int n0 = it.n_blk * BN;
         const bool row_ok = row < p.M;
         uint32_t row_mod = 0, row_grp = 0;
         if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
         if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
-        mbar_wait(smem_u32(&tmem_full_bar[as]), static_cast<uint32_t>(t & 1));
+        mbar_wait(smem_u32(&tmem_full_bar[as]), par);
         __syncwarp();
         tc_fence_after();
 #pragma unroll 1
@@ -499,33 +562,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (row_ok) atomicAdd(p.colsum + row, __uint_as_float(rs));
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        release_acc(as);
       }
     } else {
       // ---- staged epilogue: 64-column chunks through per-warp SWIZZLE_128B slots, outputs by TMA store
       //      (box 64 x 32), the optional bf16 input tile (residual / GELU' operand / pos table) by TMA load ----
-      const uint32_t ring = smem_base + STAGES * STAGE_BYTES + ew * (EPI_SLOTS * EPI_SLOT_BYTES);
+      const uint32_t ring = smem_base + G::SMEM + ew * (EPI_SLOTS * EPI_SLOT_BYTES);
+      static_assert(G::RING == NWG * 4 * EPI_SLOTS * EPI_SLOT_BYTES, "ring size");
       const bool has_in = (p.epi_mode == EPI_IN);
       const uint32_t ib0 = smem_u32(&epi_in_bar[ew][0]);
       auto in_row = [&](int row0) { return p.in_row_period > 0 ? row0 % p.in_row_period : row0; };
       if (has_in && lane == 0 && first < num_items) {
-        const Item it = decode_item(p, first);
+        const Item it = get_item(first);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           mbar_arrive_expect_tx(ib0 + c * 8, EPI_SLOT_BYTES);
           tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib0 + c * 8, it.n_blk * BN + c * 64, in_row(it.m_blk * BM + q * 32));
         }
       }
-      int t = 0;
-      for (int item = first; item < num_items; item += stride2, ++t) {
-        const Item it = decode_item(p, item);
+      int n = wg;
+      for (int item = first; item < num_items; item += stride2, n += NWG) {
+        const Item it = get_item(item);
+        const int as = n & 1;
+        const uint32_t t_addr = t_lane + static_cast<uint32_t>(as * BN);
         const int row0 = it.m_blk * BM + q * 32;
         const int64_t row = min(static_cast<int64_t>(row0) + lane, p.M - 1);   // tail rows: TMA clips the store
         const int n0 = it.n_blk * BN;
         uint32_t row_mod = 0, row_grp = 0;
         if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
         if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
-        mbar_wait(smem_u32(&tmem_full_bar[as]), static_cast<uint32_t>(t & 1));
+        mbar_wait(smem_u32(&tmem_full_bar[as]), static_cast<uint32_t>((n >> 1) & 1));
         __syncwarp();
         tc_fence_after();
         const int ir0 = in_row(row0);
@@ -538,12 +604,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           default:         staged_tile<KIND_GEN>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        release_acc(as);
         // prefetch the first two input chunks of this warpgroup's next tile once the stores have drained the slots
         const int next = item + stride2;
         if (has_in && lane == 0 && next < num_items) {
           tma_store_wait_read<0>();
-          const Item nt = decode_item(p, next);
+          const Item nt = get_item(next);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             mbar_arrive_expect_tx(ib0 + c * 8, EPI_SLOT_BYTES);
@@ -557,31 +623,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();            // nobody tears down while the peer may still signal / read it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (CTA2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
 struct DebugOverrides {
-  int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0;
+  int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0;
 };
 DebugOverrides g_dbg;
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int CTA2, int NWG>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAux,
            const CUtensorMap& tmIn, const GemmParams& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, CTA2, NWG>;
+  constexpr int smem = smem_bytes<CTA2, NWG>();
+  constexpr int threads = Geo<CTA2, NWG>::THREADS;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
-      sc_set_error("sc_gemm_bf16: cannot set %d B dynamic smem: %s", SMEM_BYTES, cudaGetErrorString(e));
+      sc_set_error("sc_gemm_bf16: cannot set %d B dynamic smem: %s", smem, cudaGetErrorString(e));
       return SC_E_LAUNCH;
     }
     attr_set = true;
   }
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmOut, tmAux, tmIn, p);
+  if (CTA2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, tmIn, p);
+    if (e != cudaSuccess) {
+      sc_set_error("sc_gemm_bf16: cluster launch failed: %s", cudaGetErrorString(e));
+      return SC_E_LAUNCH;
+    }
+  } else {
+    kern<<<grid, threads, smem, st>>>(tmA, tmB, tmOut, tmAux, tmIn, p);
+  }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_gemm_bf16");
   return SC_OK;
@@ -602,6 +690,8 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "b_kstep")) g_dbg.b_kstep = value;
   else if (!strcmp(key, "max_ctas")) g_dbg.max_ctas = value;
   else if (!strcmp(key, "generic_epi")) g_dbg.generic_epi = value;
+  else if (!strcmp(key, "cta2")) g_dbg.cta2 = value;
+  else if (!strcmp(key, "nwg")) g_dbg.nwg = value;
   else if (!strcmp(key, "reset")) g_dbg = DebugOverrides();
   else {
     sc_set_error("sc_debug_set: unknown key %s", key);
@@ -633,7 +723,8 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
-  p.tiles_m = static_cast<int>((M + BM - 1) / BM);
+  const bool cta2 = g_dbg.cta2 != 0;
+  p.tiles_m = cta2 ? static_cast<int>((M + 2 * BM - 1) / (2 * BM)) : static_cast<int>((M + BM - 1) / BM);
   p.tiles_n = static_cast<int>((N + BN - 1) / BN);
   p.kb_total = static_cast<int>((K + BK - 1) / BK);
   int ks = ksplit < 1 ? 1 : ksplit;
@@ -681,7 +772,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   if (a_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
   else           rc = sc_encode_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK);
   if (rc != SC_OK) return rc;
-  if (b_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, BN);
+  if (b_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, cta2 ? BN / 2 : BN);
   else           rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK);
   if (rc != SC_OK) return rc;
 
@@ -729,10 +820,24 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   const long long items = 1LL * p.tiles_m * p.tiles_n * p.ksplit;
   int grid = sc_num_sms();
   if (g_dbg.max_ctas > 0 && grid > g_dbg.max_ctas) grid = (int)g_dbg.max_ctas;
-  if (items < grid) grid = (int)items;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a_mn == 0 && b_mn == 0) return launch<0, 0>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st);
-  if (a_mn == 0 && b_mn == 1) return launch<0, 1>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st);
-  if (a_mn == 1 && b_mn == 1) return launch<1, 1>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st);
-  return launch<1, 0>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st);
+  const int nwg = g_dbg.nwg == 2 ? 2 : 1;          // default: one epilogue warpgroup + the extra pipeline stage
+#define SC_LAUNCH(AM, BMJ, C2)                                                                     \
+  (nwg == 2 ? launch<AM, BMJ, C2, 2>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st)                    \
+            : launch<AM, BMJ, C2, 1>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st))
+  if (cta2) {
+    int pairs = grid / 2;
+    if (items < pairs) pairs = (int)items;
+    grid = 2 * pairs;
+    if (a_mn == 0 && b_mn == 0) return SC_LAUNCH(0, 0, 1);
+    if (a_mn == 0 && b_mn == 1) return SC_LAUNCH(0, 1, 1);
+    if (a_mn == 1 && b_mn == 1) return SC_LAUNCH(1, 1, 1);
+    return SC_LAUNCH(1, 0, 1);
+  }
+  if (items < grid) grid = (int)items;
+  if (a_mn == 0 && b_mn == 0) return SC_LAUNCH(0, 0, 0);
+  if (a_mn == 0 && b_mn == 1) return SC_LAUNCH(0, 1, 0);
+  if (a_mn == 1 && b_mn == 1) return SC_LAUNCH(1, 1, 0);
+  return SC_LAUNCH(1, 0, 0);
+#undef SC_LAUNCH
 }

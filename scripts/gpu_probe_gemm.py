@@ -339,7 +339,25 @@ def _():
             torch.cuda.synchronize()
             ms_generic = ev0.elapsed_time(ev1) / n
             ops.debug_set("generic_epi", 0)
-        res["shapes"].append({"name": nm, "ms_generic_epi": ms_generic, "M": M, "N": N, "K": K, "ms": ms, "tflops": flops / ms / 1e9,
+        ms_other = {}
+        for label, key, val, restore in (("nwg2", "nwg", 2, int(os.environ.get("SC_NWG", "1"))),
+                                         ("cta2", "cta2", 1, 1 if os.environ.get("SC_CTA2") else 0),
+                                         ("cta2_nwg2", "both", 0, 0)):
+            if key == "both":
+                ops.debug_set("cta2", 1); ops.debug_set("nwg", 2)
+            else:
+                ops.debug_set(key, val)
+            for _ in range(2):
+                ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, **kw)
+            ev0.record()
+            for _ in range(n):
+                ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, **kw)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_other[label] = ev0.elapsed_time(ev1) / n
+            ops.debug_set("cta2", 1 if os.environ.get("SC_CTA2") else 0)
+            ops.debug_set("nwg", int(os.environ.get("SC_NWG", "1")))
+        res["shapes"].append({"name": nm, "ms_generic_epi": ms_generic, "ms_other_cta_mode": ms_other, "M": M, "N": N, "K": K, "ms": ms, "tflops": flops / ms / 1e9,
                               "gbs": byts / ms / 1e6, "ms_cublas": ms_cublas})
         del A, B, out
     return res
@@ -352,6 +370,11 @@ def run_case(name):
     t0 = time.time()
     fatal = False
     try:
+        from multimodal_sc_b200 import ops as _ops
+        if os.environ.get("SC_CTA2"):
+            _ops.debug_set("cta2", 1)
+        if os.environ.get("SC_NWG"):
+            _ops.debug_set("nwg", int(os.environ["SC_NWG"]))
         rec = CASES[name]()
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001

@@ -155,3 +155,29 @@ def test_adam_matches_torch(cuda_lib):
                       grad_scale=0.5)
     _close(p, pr.detach(), 1e-5, 1e-6, "adam p")
     assert torch.equal(pb.cpu(), p.cpu().bfloat16())
+
+
+@pytest.mark.parametrize("mode", [{"cta2": 1}, {"nwg": 2}, {"cta2": 1, "nwg": 2}])
+def test_gemm_alternative_schedules(cuda_lib, mode):
+    """the cta_group::2 (CTA-pair) and two-epilogue-warpgroup variants of the GEMM stay correct (they are kept
+    as options; the default is one CTA per tile, one epilogue warpgroup, four pipeline stages)."""
+    from multimodal_sc_b200 import ops
+    try:
+        for k, v in mode.items():
+            ops.debug_set(k, v)
+        g = torch.Generator(device="cuda").manual_seed(0)
+        M, N, K = 128 * 301, 1024, 256
+        A = (torch.randn(M, K, generator=g, device="cuda") * 0.3).bfloat16()
+        W = (torch.randn(N, K, generator=g, device="cuda") * 0.3).bfloat16()
+        bias = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda").bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(A, W, bias=bias, resid=res, out=out)
+        _scaled(out, A.float() @ W.float().t() + bias + res.float(), 1e-2, "fwd+resid")
+        dW = torch.zeros(N, K, device="cuda")
+        db = torch.zeros(N, device="cuda")
+        ops.gemm(out, A, a_mn=True, b_mn=True, out_f32=dW, atomic=True, ksplit=9, colsum=db)
+        _close(dW, out.float().t() @ A.float(), 1e-3, 1e-1, "wgrad")
+        _close(db, out.float().sum(0), 1e-3, 1e-1, "bias grad")
+    finally:
+        ops.debug_set("reset", 0)
