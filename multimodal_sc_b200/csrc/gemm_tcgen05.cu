@@ -28,25 +28,33 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;                 // 16384
-// CTA2 = 0: one CTA per tile (cta_group::1), B tile 256 x 64 per stage, 3 stages of 48 KB.
+// CTA2 = 0: one CTA per tile (cta_group::1), B tile 256 x 64 per stage (48 KB stages).
 // CTA2 = 1: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile; each CTA stages its own 128 A rows
-//           and HALF of the B tile (128 x 64) -> 32 KB stages, 4 of them, and half the B shared-memory traffic per SM.
-// NWG = epilogue warpgroups (1 or 2): the second warpgroup costs 32 KB of staging slots = one pipeline stage.
-template <int CTA2, int NWG> struct Geo {
-  static constexpr int STAGES = (CTA2 ? 4 : 3) + (NWG == 1 ? 1 : 0);
+//           and HALF of the B tile (128 x 64) -> 32 KB stages and half the B shared-memory traffic per SM.
+// NWG   = epilogue warpgroups (1 or 2): two warps per scheduler hide each other's dependency stalls.
+// SLOTS = 4 KB staging slots per epilogue warp (2 or 4).  4 slots hold a whole 32 x 256 tile row block, so the
+//         bf16 input tile of the NEXT tile is prefetched a full tile ahead and two-output epilogues double-buffer.
+// The pipeline gets every stage that still fits next to the staging ring and the bias tiles.
+constexpr int SMEM_LIMIT = 232448;                   // 227 KB opt-in maximum per CTA
+constexpr int STATIC_SMEM_RESERVE = 1024;            // mbarriers etc. (static __shared__), rounded up
+constexpr int EPI_SLOT_BYTES = 32 * 128;             // 32 rows x 64 bf16 columns, SWIZZLE_128B
+constexpr int BIAS_TILE_BYTES = BN * 4;              // fp32 bias of the current N tile, one copy per epilogue warpgroup
+template <int CTA2, int NWG, int SLOTS> struct Geo {
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING = NWG * 4 * SLOTS * EPI_SLOT_BYTES;
+  static constexpr int BIAS = NWG * BIAS_TILE_BYTES;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - STATIC_SMEM_RESERVE - RING - BIAS) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int SMEM = STAGES * STAGE_BYTES;
-  static constexpr int RING = NWG * 4 * 2 * (32 * 128);                   // NWG x 4 warps x 2 slots x 4 KB
   static constexpr int THREADS = 128 + NWG * 128;
+  static constexpr int TOTAL = SMEM + RING + BIAS;    // dynamic shared memory (base is 1 KB aligned)
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 constexpr int CHUNK_BYTES = 64 * BK * 2;             // 8192: one 64-wide MN-major chunk
-constexpr int EPI_SLOT_BYTES = 32 * 128;              // 32 rows x 64 bf16 columns, SWIZZLE_128B
-constexpr int EPI_WARPS = 8;                         // two epilogue warpgroups, one per accumulator stage
-constexpr int EPI_SLOTS = 2;                         // slots per epilogue warp
-constexpr int EPI_RING_BYTES = EPI_WARPS * EPI_SLOTS * EPI_SLOT_BYTES;   // 64 KB
-template <int CTA2, int NWG> constexpr int smem_bytes() { return Geo<CTA2, NWG>::SMEM + Geo<CTA2, NWG>::RING + 1024; }
+constexpr int MAX_EPI_WARPS = 8;
+constexpr int MAX_SLOTS = 4;
 // staged-epilogue modes
 constexpr int EPI_GENERIC = 0;                       // direct register -> global stores (fp32 / ragged outputs)
 constexpr int EPI_OUT1 = 1;                          // bf16 out via smem + TMA store
@@ -59,7 +67,6 @@ constexpr int KIND_BIAS = 2;                         // + bias
 constexpr int KIND_FC1 = 3;                          // + bias, pre-activation copy, tanh-GELU
 constexpr int KIND_RESID = 4;                        // + bias + residual tile
 constexpr int KIND_DGELU = 5;                        // * GELU'(pre-activation tile)
-constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;   // 384
 constexpr uint32_t TMEM_COLS = 512;
 
 struct GemmParams {
@@ -88,6 +95,10 @@ struct GemmParams {
   int in_row_period;            // > 0: the TMA input tile is a [period, N] table indexed by row % period
   // UMMA descriptor fields (bytes); defaults set by the host, overridable for bring-up
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+  // bottleneck-isolation switches (sc_debug_set("gemm_dbg", bits); results are WRONG when any bit is set):
+  //   1 = epilogue only releases the accumulator, 2 = epilogue without its TMA stores/loads,
+  //   4 = no MMAs issued, 8 = every tile loads A block 0 (no HBM reads), 16 = B tiles are not loaded
+  int dbg;
 };
 
 struct Item {
@@ -200,156 +211,278 @@ __device__ __noinline__ void epilogue_scalar(const GemmParams& p, float a, int64
   }
 }
 
-// 8 columns of one row for the staged epilogue: math only, results packed to bf16.
-// KIND != KIND_GEN turns every feature test into a compile-time constant.
+// ---- packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ----
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t tanh2(uint64_t u) {
+  float a, b;
+  upk2(u, a, b);
+  return pk2(tanh_fast(a), tanh_fast(b));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(uint64_t v) {
+  float a, b;
+  upk2(v, a, b);
+  return pack_bf16(a, b);
+}
+__device__ __forceinline__ uint64_t unpack2_bf16(uint32_t u) {
+  return pk2u(u << 16, u & 0xFFFF0000u);
+}
+// tanh-form GELU on a pair: u = x (c0 + c0 c1 x^2), 0.5 x (1 + tanh u)
+__device__ __forceinline__ uint64_t gelu_fwd2(uint64_t x) {
+  const uint64_t k0 = pk2(SC_GELU_C0, SC_GELU_C0), k01 = pk2(SC_GELU_C0 * SC_GELU_C1, SC_GELU_C0 * SC_GELU_C1);
+  const uint64_t half = pk2(0.5f, 0.5f);
+  const uint64_t u = mul2(x, fma2(mul2(x, x), k01, k0));
+  const uint64_t hx = mul2(x, half);
+  return fma2(hx, tanh2(u), hx);
+}
+// d/dx of the above: 0.5 (1 + t) + 0.5 x (1 - t^2) c0 (1 + 3 c1 x^2)
+__device__ __forceinline__ uint64_t gelu_bwd2(uint64_t x) {
+  const uint64_t k0 = pk2(SC_GELU_C0, SC_GELU_C0), k01 = pk2(SC_GELU_C0 * SC_GELU_C1, SC_GELU_C0 * SC_GELU_C1);
+  const uint64_t k03 = pk2(3.0f * SC_GELU_C0 * SC_GELU_C1, 3.0f * SC_GELU_C0 * SC_GELU_C1);
+  const uint64_t half = pk2(0.5f, 0.5f), one = pk2(1.0f, 1.0f), neg1 = pk2(-1.0f, -1.0f);
+  const uint64_t x2 = mul2(x, x);
+  const uint64_t t = tanh2(mul2(x, fma2(x2, k01, k0)));
+  const uint64_t du = fma2(x2, k03, k0);
+  const uint64_t a = add2(t, one);                       // 1 + t
+  const uint64_t omt2 = mul2(a, fma2(t, neg1, one));     // (1 + t)(1 - t)
+  const uint64_t w = mul2(mul2(x, half), du);
+  return fma2(w, omt2, mul2(a, half));
+}
+
+// 16 columns of one row for the staged epilogue: math only, results packed to bf16 (8 words out, 8 words of
+// pre-activation copy).  KIND != KIND_GEN turns every feature test into a compile-time constant.  `bv` holds
+// the 16 bias values of these columns (read from the warpgroup's shared-memory bias tile), `in0/in1` are the 16 bf16 values of the TMA input tile.
 template <int KIND>
-__device__ __forceinline__ void epilogue_math8(const GemmParams& p, const uint32_t* acc, int col, uint32_t row_mod,
-                                               uint32_t row_grp, const uint4& in, uint32_t (&outp)[4],
-                                               uint32_t (&auxp)[4]) {
+__device__ __forceinline__ void epilogue_math16(const GemmParams& p, const uint32_t (&acc)[16], const float4 (&bv)[4],
+                                                int col, uint32_t row_mod, uint32_t row_grp, const uint4& in0,
+                                                const uint4& in1, uint32_t (&outp)[8], uint32_t (&auxp)[8]) {
   constexpr bool G = (KIND == KIND_GEN);
   const bool has_bias = G ? (p.bias != nullptr) : (KIND == KIND_BIAS || KIND == KIND_FC1 || KIND == KIND_RESID);
   const bool want_aux = G ? (p.aux_out != nullptr) : (KIND == KIND_FC1);
   const int act = G ? p.act : (KIND == KIND_FC1 ? SC_ACT_GELU : SC_ACT_NONE);
   const bool in_dgelu = G ? (p.aux_in != nullptr) : (KIND == KIND_DGELU);
   const bool in_resid = G ? (p.epi_mode == EPI_IN && p.aux_in == nullptr) : (KIND == KIND_RESID);
-  float x[8];
+  uint64_t x[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(acc[j]);
+  for (int j = 0; j < 8; ++j) x[j] = pk2u(acc[2 * j], acc[2 * j + 1]);
   if (G) {
     if (p.alpha != 1.0f) {
+      const uint64_t al = pk2(p.alpha, p.alpha);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] *= p.alpha;
+      for (int j = 0; j < 8; ++j) x[j] = mul2(x[j], al);
     }
   }
   if (has_bias) {
-    float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      x[2 * q] = add2(x[2 * q], pk2(bv[q].x, bv[q].y));
+      x[2 * q + 1] = add2(x[2 * q + 1], pk2(bv[q].z, bv[q].w));
+    }
   }
   if (G) {
     if (p.rowadd) {
-      const float* ra = p.rowadd + static_cast<int64_t>(row_mod) * p.N + col;
-      float4 b0 = __ldg(reinterpret_cast<const float4*>(ra));
-      float4 b1 = __ldg(reinterpret_cast<const float4*>(ra + 4));
-      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+      const float4* ra = reinterpret_cast<const float4*>(p.rowadd + static_cast<int64_t>(row_mod) * p.N + col);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = __ldg(ra + q);
+        x[2 * q] = add2(x[2 * q], pk2(b.x, b.y));
+        x[2 * q + 1] = add2(x[2 * q + 1], pk2(b.z, b.w));
+      }
     }
     if (p.rowgrp) {
-      const float* rg = p.rowgrp + static_cast<int64_t>(row_grp) * p.N + col;
-      float4 b0 = __ldg(reinterpret_cast<const float4*>(rg));
-      float4 b1 = __ldg(reinterpret_cast<const float4*>(rg + 4));
-      const float s = p.rowgrp_scale;
-      x[0] = fmaf(b0.x, s, x[0]); x[1] = fmaf(b0.y, s, x[1]); x[2] = fmaf(b0.z, s, x[2]);
-      x[3] = fmaf(b0.w, s, x[3]); x[4] = fmaf(b1.x, s, x[4]); x[5] = fmaf(b1.y, s, x[5]);
-      x[6] = fmaf(b1.z, s, x[6]); x[7] = fmaf(b1.w, s, x[7]);
+      const float4* rg = reinterpret_cast<const float4*>(p.rowgrp + static_cast<int64_t>(row_grp) * p.N + col);
+      const uint64_t sc = pk2(p.rowgrp_scale, p.rowgrp_scale);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = __ldg(rg + q);
+        x[2 * q] = fma2(pk2(b.x, b.y), sc, x[2 * q]);
+        x[2 * q + 1] = fma2(pk2(b.z, b.w), sc, x[2 * q + 1]);
+      }
     }
   }
   if (want_aux) {
-    auxp[0] = pack_bf16(x[0], x[1]); auxp[1] = pack_bf16(x[2], x[3]);
-    auxp[2] = pack_bf16(x[4], x[5]); auxp[3] = pack_bf16(x[6], x[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) auxp[j] = pack2_bf16(x[j]);
   }
   if (act == SC_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = gelu_fwd<true>(x[j]);
+    for (int j = 0; j < 8; ++j) x[j] = gelu_fwd2(x[j]);
   } else if (G && act == SC_ACT_TANH) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = tanh_fast(x[j]);
+    for (int j = 0; j < 8; ++j) x[j] = tanh2(x[j]);
   }
   if (in_dgelu || in_resid) {
-    const float2 a0 = unpack_bf16(in.x), a1 = unpack_bf16(in.y), a2 = unpack_bf16(in.z), a3 = unpack_bf16(in.w);
-    if (in_dgelu) {
-      x[0] *= gelu_bwd<true>(a0.x); x[1] *= gelu_bwd<true>(a0.y); x[2] *= gelu_bwd<true>(a1.x);
-      x[3] *= gelu_bwd<true>(a1.y); x[4] *= gelu_bwd<true>(a2.x); x[5] *= gelu_bwd<true>(a2.y);
-      x[6] *= gelu_bwd<true>(a3.x); x[7] *= gelu_bwd<true>(a3.y);
-    } else {
-      x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
-      x[4] += a2.x; x[5] += a2.y; x[6] += a3.x; x[7] += a3.y;
+    const uint32_t iw[8] = {in0.x, in0.y, in0.z, in0.w, in1.x, in1.y, in1.z, in1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint64_t a = unpack2_bf16(iw[j]);
+      x[j] = in_dgelu ? mul2(x[j], gelu_bwd2(a)) : add2(x[j], a);
     }
   }
-  outp[0] = pack_bf16(x[0], x[1]); outp[1] = pack_bf16(x[2], x[3]);
-  outp[2] = pack_bf16(x[4], x[5]); outp[3] = pack_bf16(x[6], x[7]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) outp[j] = pack2_bf16(x[j]);
 }
+
+// Where the NEXT tile of this epilogue warp lives (input-tile prefetch in 4-slot mode).
+struct NextTile {
+  bool valid;
+  int n0, in_row0;
+};
 
 // One 128x256 accumulator tile of the staged epilogue for one warp (32 rows): four 64-column chunks, each
 // drained in 16-column steps (tcgen05.ld.x16 -> math -> st.shared into a SWIZZLE_128B slot) and then written
-// with one (two for EPI_OUT2) TMA store.  Two slots per warp: chunk c uses slot c & 1.  In EPI_IN mode the slot
-// first receives the bf16 input tile by TMA load (chunks 0,1 prefetched before the tile, chunks 2,3 as soon as
-// the store of chunk c-2 has drained the slot) and is overwritten in place with the result.
-template <int KIND>
+// with one (two for EPI_OUT2) TMA store.  The 16 steps are software-pipelined: the tcgen05.ld and the bias
+// reads of step s+1 are in flight while step s is computed.
+//   SLOTS = 2: chunk c uses slot c & 1 (EPI_OUT2: slot 0 = pre-activation copy, slot 1 = output).  In EPI_IN
+//              mode the slot first receives the bf16 input tile by TMA load (chunks 0,1 prefetched before the
+//              tile, chunks 2,3 as soon as the store of chunk c-2 has drained the slot) and is overwritten in place.
+//   SLOTS = 4: chunk c uses slot c (EPI_OUT2: slots 2(c&1), 2(c&1)+1), so the input of all four chunks of the
+//              NEXT tile is requested while this tile is still being drained (slot c-1 is refilled at the end of
+//              chunk c) and a two-output chunk never waits for its own stores.
+template <int KIND, int SLOTS>
 __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmAux,
                                             const CUtensorMap* tmIn, uint32_t t_addr, uint32_t ring, uint32_t in_bar0,
-                                            int lane, int n0, int row0, int in_row0, uint32_t row_mod,
-                                            uint32_t row_grp) {
-  const bool has_in = (p.epi_mode == EPI_IN);
+                                            uint32_t bias_tile, int lane, int n0, int row0, int in_row0,
+                                            uint32_t row_mod, uint32_t row_grp, uint32_t tile_parity,
+                                            const NextTile& next) {
+  constexpr bool G = (KIND == KIND_GEN);
+  const bool no_tma = (p.dbg & 2) != 0;
+  const bool has_in = (p.epi_mode == EPI_IN) && !no_tma;
   const bool two_out = (p.epi_mode == EPI_OUT2);
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const int col0 = n0 + c * 64;
-    if (col0 >= p.N) break;
-    const int s = c & 1;
-    const uint32_t slot_o = ring + (two_out ? 1 : s) * EPI_SLOT_BYTES;
-    const uint32_t slot_a = ring;                                            // pre-activation copy (EPI_OUT2)
+  const bool has_bias = G ? (p.bias != nullptr) : (KIND == KIND_BIAS || KIND == KIND_FC1 || KIND == KIND_RESID);
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+
+  auto out_slot = [&](int c) { return SLOTS == 4 ? (two_out ? 2 * (c & 1) + 1 : c) : (two_out ? 1 : (c & 1)); };
+  auto aux_slot = [&](int c) { return SLOTS == 4 ? 2 * (c & 1) : 0; };
+
+  uint32_t v[2][16];
+  float4 bv[2][4];
+  auto issue = [&](int s, uint32_t (&vv)[16], float4 (&bb)[4]) {
+    tmem_ld_32x32b_x16(t_addr + s * 16, vv);
+    if (has_bias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 w = ld_shared_v4(bias_tile + s * 64 + q * 16);           // same address in every lane: broadcast
+        bb[q] = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+      }
+    }
+  };
+  auto chunk_begin = [&](int c) {
     if (has_in) {
-      mbar_wait(in_bar0 + s * 8, static_cast<uint32_t>(c >> 1) & 1u);        // slot s: use 2t + (c >> 1) of this barrier
+      if (SLOTS == 4) mbar_wait(in_bar0 + c * 8, tile_parity);               // one use of barrier c per tile
+      else mbar_wait(in_bar0 + (c & 1) * 8, static_cast<uint32_t>(c >> 1) & 1u);   // uses 2t + (c >> 1) of barrier c & 1
     } else if (lane == 0) {
       // the TMA store that last read the slot(s) must have drained them
-      if (two_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+      if (SLOTS == 4) { if (two_out) tma_store_wait_read<1>(); else tma_store_wait_read<3>(); }
+      else { if (two_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
     }
     __syncwarp();
-    const uint32_t row_o = slot_o + lane * 128, row_a = slot_a + lane * 128;
-    const uint32_t sw = static_cast<uint32_t>(lane & 7);
-#pragma unroll 1
-    for (int h = 0; h < 4; ++h) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(t_addr + c * 64 + h * 16, v);
-      const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
-      uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
-      if (has_in) {
-        i0 = ld_shared_v4(row_o + pa);
-        i1 = ld_shared_v4(row_o + pb);
-      }
-      tmem_ld_wait();
-      uint32_t o[4], a[4];
-      epilogue_math8<KIND>(p, &v[0], col0 + h * 16, row_mod, row_grp, i0, o, a);
-      st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
-      if (two_out) st_shared_v4(row_a + pa, a[0], a[1], a[2], a[3]);
-      epilogue_math8<KIND>(p, &v[8], col0 + h * 16 + 8, row_mod, row_grp, i1, o, a);
-      st_shared_v4(row_o + pb, o[0], o[1], o[2], o[3]);
-      if (two_out) st_shared_v4(row_a + pb, a[0], a[1], a[2], a[3]);
+  };
+  auto process = [&](int s, const uint32_t (&vv)[16], const float4 (&bb)[4]) {
+    const int c = s >> 2, h = s & 3;
+    const uint32_t row_o = ring + out_slot(c) * EPI_SLOT_BYTES + lane * 128;
+    const uint32_t row_a = ring + aux_slot(c) * EPI_SLOT_BYTES + lane * 128;      // pre-activation copy (EPI_OUT2)
+    const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+    uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
+    if (has_in) {
+      i0 = ld_shared_v4(row_o + pa);
+      i1 = ld_shared_v4(row_o + pb);
     }
+    uint32_t o[8], a[8];
+    epilogue_math16<KIND>(p, vv, bb, n0 + s * 16, row_mod, row_grp, i0, i1, o, a);
+    st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
+    st_shared_v4(row_o + pb, o[4], o[5], o[6], o[7]);
+    if (two_out) {
+      st_shared_v4(row_a + pa, a[0], a[1], a[2], a[3]);
+      st_shared_v4(row_a + pb, a[4], a[5], a[6], a[7]);
+    }
+  };
+  auto chunk_end = [&](int c) {
+    const int col0 = n0 + c * 64;
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
-      if (two_out) tma_store_2d(tmAux, slot_a, col0, row0);
-      tma_store_2d(tmOut, slot_o, col0, row0);
+    if (lane == 0 && !no_tma) {
+      if (two_out) tma_store_2d(tmAux, ring + aux_slot(c) * EPI_SLOT_BYTES, col0, row0);
+      tma_store_2d(tmOut, ring + out_slot(c) * EPI_SLOT_BYTES, col0, row0);
       tma_store_commit();
-      if (has_in && c < 2) {                                                 // refill the slot with chunk c + 2's input
-        tma_store_wait_read<0>();
-        mbar_arrive_expect_tx(in_bar0 + s * 8, EPI_SLOT_BYTES);
-        tma_load_2d(slot_o, tmIn, in_bar0 + s * 8, col0 + 128, in_row0);
+      if (has_in) {
+        if (SLOTS == 4) {
+          if (c >= 1 && next.valid) {                                        // slot c-1 -> the next tile's chunk c-1
+            tma_store_wait_read<1>();
+            mbar_arrive_expect_tx(in_bar0 + (c - 1) * 8, EPI_SLOT_BYTES);
+            tma_load_2d(ring + (c - 1) * EPI_SLOT_BYTES, tmIn, in_bar0 + (c - 1) * 8, next.n0 + (c - 1) * 64, next.in_row0);
+          }
+        } else if (c < 2) {                                                  // refill the slot with chunk c + 2's input
+          tma_store_wait_read<0>();
+          mbar_arrive_expect_tx(in_bar0 + (c & 1) * 8, EPI_SLOT_BYTES);
+          tma_load_2d(ring + (c & 1) * EPI_SLOT_BYTES, tmIn, in_bar0 + (c & 1) * 8, col0 + 128, in_row0);
+        }
       }
     }
+  };
+
+  issue(0, v[0], bv[0]);
+#pragma unroll 1
+  for (int s = 0; s < 16; s += 2) {
+    if ((s & 3) == 0) chunk_begin(s >> 2);
+    tmem_ld_wait();
+    issue(s + 1, v[1], bv[1]);
+    process(s, v[0], bv[0]);
+    tmem_ld_wait();
+    if (s + 2 < 16) issue(s + 2, v[0], bv[0]);
+    process(s + 1, v[1], bv[1]);
+    if ((s & 3) == 2) chunk_end(s >> 2);
   }
 }
 
-template <int A_MN, int B_MN, int CTA2, int NWG>
+template <int A_MN, int B_MN, int CTA2, int NWG, int SLOTS>
 __global__ void __launch_bounds__(128 + NWG * 128, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
                     const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
-  using G = Geo<CTA2, NWG>;
+  using G = Geo<CTA2, NWG, SLOTS>;
   constexpr int STAGES = G::STAGES;
   constexpr int STAGE_BYTES = G::STAGE_BYTES;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ __align__(8) uint64_t epi_in_bar[EPI_WARPS][EPI_SLOTS];
+  __shared__ __align__(8) uint64_t epi_in_bar[MAX_EPI_WARPS][MAX_SLOTS];
   __shared__ uint32_t tmem_base_slot;
 
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms: 1 KB aligned
+  // SWIZZLE_128B atoms need a 1 KB aligned base; the budget in Geo has no slack for re-aligning, so insist on it
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("semcom: dynamic shared memory base 0x%x is not 1 KB aligned\n", smem_base);
+    __trap();
+  }
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;       // 0 = MMA leader of the pair
@@ -364,8 +497,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[s]), 128 * ncta);   // pair: both CTAs' epilogue warpgroups arrive on the leader's
     }
-    for (int w = 0; w < EPI_WARPS; ++w)
-      for (int s = 0; s < EPI_SLOTS; ++s) mbar_init(smem_u32(&epi_in_bar[w][s]), 1);
+    for (int w = 0; w < MAX_EPI_WARPS; ++w)
+      for (int s = 0; s < MAX_SLOTS; ++s) mbar_init(smem_u32(&epi_in_bar[w][s]), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -406,7 +539,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       for (int item = cta_first; item < num_items; item += cta_stride) {
         const Item it = get_item(item);
-        const int m0 = it.m_blk * BM;
+        const int m0 = (p.dbg & 8) ? 0 : it.m_blk * BM;
         const int n0 = it.n_blk * BN + static_cast<int>(rank) * G::B_ROWS;   // pair: this CTA's half of B
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
@@ -433,14 +566,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           } else {
             const uint32_t fb = fb_local;
-            mbar_arrive_expect_tx(fb, STAGE_BYTES);
+            mbar_arrive_expect_tx(fb, (p.dbg & 16) ? A_BYTES : STAGE_BYTES);
             if (A_MN == 0) {
               tma_load_2d(a_dst, &tmA, fb, k0, m0);
             } else {
 #pragma unroll
               for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
             }
-            if (B_MN == 0) {
+            if (p.dbg & 16) {
+            } else if (B_MN == 0) {
               tma_load_2d(b_dst, &tmB, fb, k0, n0);
             } else {
 #pragma unroll
@@ -474,6 +608,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t ad = umma_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
             const uint64_t bd = umma_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
             const uint32_t acc = (kb > it.kb_begin || k > 0) ? 1u : 0u;
+            if (p.dbg & 4) continue;
             if (CTA2) umma_bf16_ss_2sm(d_tmem, ad, bd, idesc, acc);
             else umma_bf16_ss(d_tmem, ad, bd, idesc, acc);
             if (single_acc && it.n_blk == 0) {
@@ -567,21 +702,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
       // ---- staged epilogue: 64-column chunks through per-warp SWIZZLE_128B slots, outputs by TMA store
       //      (box 64 x 32), the optional bf16 input tile (residual / GELU' operand / pos table) by TMA load ----
-      const uint32_t ring = smem_base + G::SMEM + ew * (EPI_SLOTS * EPI_SLOT_BYTES);
-      static_assert(G::RING == NWG * 4 * EPI_SLOTS * EPI_SLOT_BYTES, "ring size");
-      const bool has_in = (p.epi_mode == EPI_IN);
+      const uint32_t ring = smem_base + G::SMEM + ew * (SLOTS * EPI_SLOT_BYTES);
+      const uint32_t bias_tile = smem_base + G::SMEM + G::RING + wg * BIAS_TILE_BYTES;
+      const int wg_tid = static_cast<int>(threadIdx.x) - 128 - wg * 128;      // 0..127 within this warpgroup
+      const bool has_in = (p.epi_mode == EPI_IN) && !(p.dbg & 3);
+      const bool stage_bias = (p.bias != nullptr) && !(p.dbg & 1);
       const uint32_t ib0 = smem_u32(&epi_in_bar[ew][0]);
       auto in_row = [&](int row0) { return p.in_row_period > 0 ? row0 % p.in_row_period : row0; };
+      constexpr int PRE = SLOTS == 4 ? 4 : 2;                                  // input chunks requested ahead of a tile
       if (has_in && lane == 0 && first < num_items) {
         const Item it = get_item(first);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < PRE; ++c) {
           mbar_arrive_expect_tx(ib0 + c * 8, EPI_SLOT_BYTES);
           tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib0 + c * 8, it.n_blk * BN + c * 64, in_row(it.m_blk * BM + q * 32));
         }
       }
       int n = wg;
-      for (int item = first; item < num_items; item += stride2, n += NWG) {
+      uint32_t tile_parity = 0;
+      for (int item = first; item < num_items; item += stride2, n += NWG, tile_parity ^= 1u) {
         const Item it = get_item(item);
         const int as = n & 1;
         const uint32_t t_addr = t_lane + static_cast<uint32_t>(as * BN);
@@ -591,29 +730,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t row_mod = 0, row_grp = 0;
         if (p.rowadd) row_mod = static_cast<uint32_t>(row) % p.rowadd_period;
         if (p.rowgrp) row_grp = static_cast<uint32_t>(row) / p.rowgrp_size;
+        // this tile's 256 bias values: fetched before the accumulator wait, parked in the warpgroup's smem tile
+        float2 bias2 = make_float2(0.f, 0.f);
+        if (stage_bias) bias2 = __ldg(reinterpret_cast<const float2*>(p.bias + n0) + wg_tid);
         mbar_wait(smem_u32(&tmem_full_bar[as]), static_cast<uint32_t>((n >> 1) & 1));
         __syncwarp();
         tc_fence_after();
         const int ir0 = in_row(row0);
+        const int next_item = item + stride2;
+        NextTile next;
+        next.valid = next_item < num_items;
+        next.n0 = 0; next.in_row0 = 0;
+        if (next.valid) {
+          const Item nt = get_item(next_item);
+          next.n0 = nt.n_blk * BN;
+          next.in_row0 = in_row(nt.m_blk * BM + q * 32);
+        }
+        if (p.dbg & 1) {
+          tc_fence_before();
+          release_acc(as);
+          continue;
+        }
+        if (stage_bias) {
+          named_bar_sync(1 + wg, 128);                                         // previous tile's bias reads are done
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_tile + wg_tid * 8), "f"(bias2.x), "f"(bias2.y) : "memory");
+          named_bar_sync(1 + wg, 128);
+        }
         switch (p.epi_kind) {
-          case KIND_PLAIN: staged_tile<KIND_PLAIN>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
-          case KIND_BIAS:  staged_tile<KIND_BIAS>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
-          case KIND_FC1:   staged_tile<KIND_FC1>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
-          case KIND_RESID: staged_tile<KIND_RESID>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
-          case KIND_DGELU: staged_tile<KIND_DGELU>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
-          default:         staged_tile<KIND_GEN>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, lane, n0, row0, ir0, row_mod, row_grp); break;
+#define SC_TILE(KIND) staged_tile<KIND, SLOTS>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, bias_tile, lane, n0, row0, ir0, row_mod, row_grp, tile_parity, next)
+          case KIND_PLAIN: SC_TILE(KIND_PLAIN); break;
+          case KIND_BIAS:  SC_TILE(KIND_BIAS); break;
+          case KIND_FC1:   SC_TILE(KIND_FC1); break;
+          case KIND_RESID: SC_TILE(KIND_RESID); break;
+          case KIND_DGELU: SC_TILE(KIND_DGELU); break;
+          default:         SC_TILE(KIND_GEN); break;
+#undef SC_TILE
         }
         tc_fence_before();
         release_acc(as);
-        // prefetch the first two input chunks of this warpgroup's next tile once the stores have drained the slots
-        const int next = item + stride2;
-        if (has_in && lane == 0 && next < num_items) {
+        // input chunks of this warp's next tile that could not be requested inside the tile: the slots are free once
+        // the stores that read them have drained
+        if (has_in && lane == 0 && next.valid) {
           tma_store_wait_read<0>();
-          const Item nt = get_item(next);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = (SLOTS == 4 ? 3 : 0); c < PRE; ++c) {
             mbar_arrive_expect_tx(ib0 + c * 8, EPI_SLOT_BYTES);
-            tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib0 + c * 8, nt.n_blk * BN + c * 64, in_row(nt.m_blk * BM + q * 32));
+            tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib0 + c * 8, next.n0 + c * 64, next.in_row0);
           }
         }
       }
@@ -631,17 +793,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 struct DebugOverrides {
-  int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0;
+  int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0,
+          gemm_dbg = 0, slots = 0;
 };
 DebugOverrides g_dbg;
 
-template <int A_MN, int B_MN, int CTA2, int NWG>
+template <int A_MN, int B_MN, int CTA2, int NWG, int SLOTS>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAux,
            const CUtensorMap& tmIn, const GemmParams& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, CTA2, NWG>;
-  constexpr int smem = smem_bytes<CTA2, NWG>();
-  constexpr int threads = Geo<CTA2, NWG>::THREADS;
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, CTA2, NWG, SLOTS>;
+  constexpr int smem = Geo<CTA2, NWG, SLOTS>::TOTAL;
+  constexpr int threads = Geo<CTA2, NWG, SLOTS>::THREADS;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -692,6 +855,8 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "generic_epi")) g_dbg.generic_epi = value;
   else if (!strcmp(key, "cta2")) g_dbg.cta2 = value;
   else if (!strcmp(key, "nwg")) g_dbg.nwg = value;
+  else if (!strcmp(key, "gemm_dbg")) g_dbg.gemm_dbg = value;
+  else if (!strcmp(key, "slots")) g_dbg.slots = value;
   else if (!strcmp(key, "reset")) g_dbg = DebugOverrides();
   else {
     sc_set_error("sc_debug_set: unknown key %s", key);
@@ -752,6 +917,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   p.act = epi->act;
   p.atomic = epi->atomic;
   p.colsum = epi->colsum;
+  p.dbg = static_cast<int>(g_dbg.gemm_dbg);
   SC_REQUIRE(!epi->colsum || (a_mn == 1 && epi->out_f32 && !epi->out_bf16), SC_E_SHAPE,
              "sc_gemm_bf16: colsum needs a_mn = 1 and an fp32-only output (the wgrad form)");
   p.vec_ok = (N % 8 == 0) && (epi->ldo % 8 == 0) && sc_aligned16(epi->bias) && sc_aligned16(epi->rowadd) &&
@@ -821,23 +987,35 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   int grid = sc_num_sms();
   if (g_dbg.max_ctas > 0 && grid > g_dbg.max_ctas) grid = (int)g_dbg.max_ctas;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nwg = g_dbg.nwg == 2 ? 2 : 1;          // default: one epilogue warpgroup + the extra pipeline stage
-#define SC_LAUNCH(AM, BMJ, C2)                                                                     \
-  (nwg == 2 ? launch<AM, BMJ, C2, 2>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st)                    \
-            : launch<AM, BMJ, C2, 1>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st))
+  // K <= 256: the tile's MMAs are short and the step is epilogue-bound.  Math-heavy / wide epilogues get two
+  // epilogue warpgroups (two warps per scheduler hide each other's dependency stalls, 3 pipeline stages); the light
+  // residual epilogue does better with one warpgroup and four staging slots per warp (the next tile's input is
+  // prefetched a whole tile ahead, 3 stages).  Longer K: one warpgroup, two slots, 4 stages.
+  // (measured on B200, M = 262144: profiles/r1_gemm_epilogue_configs.json)
+  const bool short_k = K <= 256 && p.epi_mode != EPI_GENERIC;
+  const bool light_in = short_k && p.epi_mode == EPI_IN && p.epi_kind == KIND_RESID;
+  const int nwg = g_dbg.nwg ? (g_dbg.nwg == 2 ? 2 : 1) : ((short_k && !light_in) ? 2 : 1);
+  const int slots = g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2);
+#define SC_LAUNCH1(AM, BMJ, C2, W, S) launch<AM, BMJ, C2, W, S>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st)
+#define SC_LAUNCH(AM, BMJ)                                                                          \
+  (nwg == 2 ? (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 2, 4) : SC_LAUNCH1(AM, BMJ, 0, 2, 2))           \
+            : (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 1, 4) : SC_LAUNCH1(AM, BMJ, 0, 1, 2)))
+#define SC_LAUNCH_PAIR(AM, BMJ) (nwg == 2 ? SC_LAUNCH1(AM, BMJ, 1, 2, 2) : SC_LAUNCH1(AM, BMJ, 1, 1, 2))
   if (cta2) {
     int pairs = grid / 2;
     if (items < pairs) pairs = (int)items;
     grid = 2 * pairs;
-    if (a_mn == 0 && b_mn == 0) return SC_LAUNCH(0, 0, 1);
-    if (a_mn == 0 && b_mn == 1) return SC_LAUNCH(0, 1, 1);
-    if (a_mn == 1 && b_mn == 1) return SC_LAUNCH(1, 1, 1);
-    return SC_LAUNCH(1, 0, 1);
+    if (a_mn == 0 && b_mn == 0) return SC_LAUNCH_PAIR(0, 0);
+    if (a_mn == 0 && b_mn == 1) return SC_LAUNCH_PAIR(0, 1);
+    if (a_mn == 1 && b_mn == 1) return SC_LAUNCH_PAIR(1, 1);
+    return SC_LAUNCH_PAIR(1, 0);
   }
   if (items < grid) grid = (int)items;
-  if (a_mn == 0 && b_mn == 0) return SC_LAUNCH(0, 0, 0);
-  if (a_mn == 0 && b_mn == 1) return SC_LAUNCH(0, 1, 0);
-  if (a_mn == 1 && b_mn == 1) return SC_LAUNCH(1, 1, 0);
-  return SC_LAUNCH(1, 0, 0);
+  if (a_mn == 0 && b_mn == 0) return SC_LAUNCH(0, 0);
+  if (a_mn == 0 && b_mn == 1) return SC_LAUNCH(0, 1);
+  if (a_mn == 1 && b_mn == 1) return SC_LAUNCH(1, 1);
+  return SC_LAUNCH(1, 0);
+#undef SC_LAUNCH_PAIR
+#undef SC_LAUNCH1
 #undef SC_LAUNCH
 }

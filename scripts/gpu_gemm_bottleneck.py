@@ -1,0 +1,114 @@
+"""Bottleneck isolation for sc_gemm_bf16 on the step's dominant shapes (run under gpurun).
+
+For every shape x variant the kernel is timed (CUDA events, inputs larger than L2 by rotating over
+several operand sets) with parts of the pipeline switched off through sc_debug_set("gemm_dbg", bits):
+  1 = epilogue only releases the accumulator     -> loads + MMA alone
+  2 = epilogue math + smem staging, no TMA stores/loads -> cost of the global writes / epilogue inputs
+  4 = no MMAs                                    -> loads + epilogue alone
+  8 = A always block 0 (L2 hits)                 -> cost of the HBM reads
+ 16 = B not loaded                               -> cost of re-streaming the weights
+Results with any bit set are numerically wrong by construction; this is a timing probe only.
+Writes gpurun_out/gemm_bottleneck.json.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+from multimodal_sc_b200 import ops
+
+BF16 = torch.bfloat16
+M = 262144
+SETS = 3          # operand sets rotated between launches (each set >> 126 MB L2 for the big shapes)
+
+
+def make(shape_name):
+    g = lambda *s: (torch.randn(*s, device="cuda") * 0.1).to(BF16)
+    if shape_name == "qkv":      # [M,256] x [768,256]^T + bias
+        return dict(M=M, N=768, K=256, A=lambda: g(M, 256), B=g(768, 256), kw=lambda: dict(bias=torch.zeros(768, device="cuda")))
+    if shape_name == "proj":     # + bias + residual
+        return dict(M=M, N=256, K=256, A=lambda: g(M, 256), B=g(256, 256),
+                    kw=lambda: dict(bias=torch.zeros(256, device="cuda"), resid=g(M, 256)))
+    if shape_name == "fc1":      # + bias, GELU, pre-activation copy
+        return dict(M=M, N=1024, K=256, A=lambda: g(M, 256), B=g(1024, 256),
+                    kw=lambda: dict(bias=torch.zeros(1024, device="cuda"), act="gelu", aux_out=torch.empty(M, 1024, device="cuda", dtype=BF16)))
+    if shape_name == "fc2":      # K = 1024, + bias + residual
+        return dict(M=M, N=256, K=1024, A=lambda: g(M, 1024), B=g(256, 1024),
+                    kw=lambda: dict(bias=torch.zeros(256, device="cuda"), resid=g(M, 256)))
+    if shape_name == "dgrad_fc2":  # dh = dy W2, * GELU'(hpre)
+        return dict(M=M, N=1024, K=256, A=lambda: g(M, 256), B=g(256, 1024), b_mn=True,
+                    kw=lambda: dict(aux_in=g(M, 1024)))
+    if shape_name == "dgrad_fc1":  # dx = dhpre W1
+        return dict(M=M, N=256, K=1024, A=lambda: g(M, 1024), B=g(1024, 256), b_mn=True, kw=lambda: dict())
+    if shape_name == "plain256":
+        return dict(M=M, N=256, K=256, A=lambda: g(M, 256), B=g(256, 256), kw=lambda: dict())
+    raise KeyError(shape_name)
+
+
+def time_case(spec, dbg, nwg, iters=12, slots=0):
+    ops.debug_set("reset", 0)
+    ops.debug_set("gemm_dbg", dbg)
+    ops.debug_set("nwg", nwg)
+    ops.debug_set("slots", slots)
+    sets = []
+    for _ in range(SETS):
+        kw = spec["kw"]()
+        sets.append((spec["A"](), kw, torch.empty(spec["M"], spec["N"], device="cuda", dtype=BF16)))
+    def run(i):
+        A, kw, out = sets[i % SETS]
+        ops.gemm(A, spec["B"], b_mn=spec.get("b_mn", False), out=out, **kw)
+    for i in range(3):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ops.debug_set("reset", 0)
+    return e0.elapsed_time(e1) / iters * 1e3   # us
+
+
+def main():
+    out = {}
+    variants = [("full", 0), ("epi_skip", 1), ("epi_no_tma", 2), ("no_mma", 4), ("a_l2", 8), ("no_b", 16),
+                ("epi_skip+a_l2", 9), ("epi_skip+no_b", 17), ("epi_skip+no_mma", 5), ("no_mma+no_tma", 6)]
+    if os.environ.get("SC_BOTTLENECK_QUICK"):
+        variants = [("full", 0), ("epi_skip", 1), ("epi_no_tma", 2), ("no_mma+no_tma", 6)]
+    for name in ("qkv", "proj", "fc1", "fc2", "dgrad_fc2", "dgrad_fc1", "plain256"):
+        spec = make(name)
+        rec = {}
+        if os.environ.get("SC_BOTTLENECK_CFG"):
+            # epilogue configuration sweep: (warpgroups, slots per warp); 0/0 = the library's own choice
+            for nwg, slots in ((0, 0), (1, 2), (2, 2), (1, 4), (2, 4)):
+                for vn, bits in (("full", 0), ("epi_skip", 1), ("no_mma+no_tma", 6)):
+                    try:
+                        rec[f"w{nwg}s{slots}.{vn}"] = round(time_case(spec, bits, nwg, slots=slots), 1)
+                    except Exception as e:   # noqa: BLE001
+                        rec[f"w{nwg}s{slots}.{vn}"] = f"ERR {e}"
+            out[name] = rec
+            print(name, json.dumps(rec), flush=True)
+            continue
+        for nwg in (1, 2):
+            for vn, bits in variants:
+                try:
+                    rec[f"nwg{nwg}.{vn}"] = round(time_case(spec, bits, nwg), 1)
+                except Exception as e:   # noqa: BLE001
+                    rec[f"nwg{nwg}.{vn}"] = f"ERR {e}"
+        out[name] = rec
+        print(name, json.dumps(rec), flush=True)
+        del spec
+        torch.cuda.empty_cache()
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/gemm_bottleneck.json", "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
