@@ -144,6 +144,9 @@ def run_native(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
+    for kv in a.debug_set:
+        k, v = kv.split("=")
+        ops.debug_set(k, int(v))
     sp = SpecV0()
     B = a.minibatch
     pol = SemComPolicy(sp, device=dev)
@@ -272,6 +275,8 @@ def run_native(a):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
     if cpu:
         line["cpu_baseline"] = cpu
+    if a.debug_set:
+        line["config"]["debug"] = list(a.debug_set)      # an A/B run, not a headline number
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -285,6 +290,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--minibatch", type=int, default=MB_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--debug-set", action="append", default=[], metavar="KEY=INT",
+                    help="A/B switch forwarded to sc_debug_set (e.g. nwg=1 slots=2); recorded in config.debug")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

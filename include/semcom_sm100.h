@@ -101,6 +101,21 @@ typedef struct sc_gemm_epilogue {
 int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn,
                  int64_t lda, int64_t ldb, const sc_gemm_epilogue* epi, int ksplit, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Transformer MLP as one kernel per direction (SPEC v0 a1/a2/a5: the block's fc1 -> GELU -> fc2).
+ * The 128 x R hidden tile is produced chunk by chunk in TMEM, transformed by the epilogue warps and consumed
+ * by the second GEMM from shared memory; it never makes an HBM round trip between the two GEMMs.
+ *   sc_mlp_fwd:        out = resid + gelu(x W1^T + b1) W2^T + b2;   hpre (pre-activation) and h (activation)
+ *                      are saved for backward when the pointers are non-null (both bf16 [M, R]).
+ *   sc_mlp_bwd_dgrad:  dhpre = (dy W2) o gelu'(hpre)  (saved, bf16 [M, R]: the fc1 wgrad operand),
+ *                      dx = dhpre W1.   The two weight gradients stay sc_gemm_bf16 calls.
+ * x/dy/out/dx/resid: bf16 [M, D] row-major, D must be 256; W1: bf16 [R, D]; W2: bf16 [D, R]; R % 128 == 0.
+ * ------------------------------------------------------------------------------------- */
+int sc_mlp_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+               const void* resid, void* hpre, void* h, void* out, int64_t M, int D, int R, void* stream);
+int sc_mlp_bwd_dgrad(const void* dy, const void* w1, const void* w2, const void* hpre, void* dhpre, void* dx,
+                     int64_t M, int D, int R, void* stream);
+
 /* test hook: override UMMA descriptor fields (0 = library default). Not for product use. */
 int sc_debug_set(const char* key, int64_t value);
 

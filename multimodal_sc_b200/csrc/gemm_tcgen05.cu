@@ -97,7 +97,8 @@ struct GemmParams {
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
   // bottleneck-isolation switches (sc_debug_set("gemm_dbg", bits); results are WRONG when any bit is set):
   //   1 = epilogue only releases the accumulator, 2 = epilogue without its TMA stores/loads,
-  //   4 = no MMAs issued, 8 = every tile loads A block 0 (no HBM reads), 16 = B tiles are not loaded
+  //   4 = no MMAs issued, 8 = every tile loads A block 0 (no HBM reads), 16 = B tiles are not loaded,
+  //   32 = no operand loads at all (MMAs run on stale shared memory)
   int dbg;
 };
 
@@ -544,6 +545,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          if (p.dbg & 32) {                                   // no loads at all: raw MMA issue rate on stale smem
+            if (!CTA2 || rank == 0) mbar_arrive(fb_local);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
           const int k0 = kb * BK;

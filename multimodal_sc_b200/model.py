@@ -18,6 +18,7 @@ so that `loss.backward()` works exactly as with the oracle.
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 
 import torch
@@ -142,6 +143,8 @@ class Engine:
         self.spec, self.flat, self.device = spec, flat, device
         self.arenas = {}
         self.sms = torch.cuda.get_device_properties(device).multi_processor_count
+        # SC_FUSED_MLP=0 selects the two-GEMM MLP schedule everywhere (A/B runs)
+        self.fused_mlp = os.environ.get("SC_FUSED_MLP", "1") != "0"
 
     def arena(self, B: int) -> _Arena:
         a = self.arenas.get(B)
@@ -178,6 +181,13 @@ class Engine:
         xn2 = k("xn2", (M, D))
         ops.layernorm_fwd(x1, f.w32(f"{pfx}.ln2.weight"), f.w32(f"{pfx}.ln2.bias"), sp.ln_eps, y=xn2,
                           mean=k("mean2", (M,), F32), rstd=k("rstd2", (M,), F32))
+        if not train and self.fused_mlp and D == 256:
+            # inference: fc1 -> GELU -> fc2 in one kernel, the hidden activation never leaves the SM
+            ops.mlp_fwd(xn2, f.w16(f"{pfx}.fc1.weight"), f.w32(f"{pfx}.fc1.bias"), f.w16(f"{pfx}.fc2.weight"),
+                        f.w32(f"{pfx}.fc2.bias"), resid=x1, out=x_out)
+            return
+        # training saves both hpre and h: two wide outputs make the fused kernel store-bound, so the forward
+        # keeps the two-GEMM form (profiles/README.md, r1 fused-MLP table)
         h = k("h", (M, sp.d_mlp))
         hpre = k("hpre", (M, sp.d_mlp)) if train else None
         ops.gemm(xn2, f.w16(f"{pfx}.fc1.weight"), bias=f.w32(f"{pfx}.fc1.bias"), act="gelu", aux_out=hpre, out=h)
@@ -192,9 +202,16 @@ class Engine:
         s = lambda n, shape, dt=BF16: A.buf(f"scratch.{n}.{shape[0]}", shape, dt)   # shared across blocks
         # ---- MLP ----
         dhpre = s("dh", (M, sp.d_mlp))
-        self._linear_bwd(dx_out, k("h"), f"{pfx}.fc2", dx=dhpre, bias_colsum=False, aux_in=k("hpre"))
         dxn2 = s("dxn", (M, D))
-        self._linear_bwd(dhpre, k("xn2"), f"{pfx}.fc1", dx=dxn2)
+        if self.fused_mlp and D == 256:
+            # both dgrad GEMMs in one kernel (dhpre stays on chip between them); the wgrads follow as split-K GEMMs
+            ops.mlp_bwd_dgrad(dx_out, f.w16(f"{pfx}.fc1.weight"), f.w16(f"{pfx}.fc2.weight"), k("hpre"),
+                              dhpre=dhpre, dx=dxn2)
+            self._linear_bwd(dx_out, k("h"), f"{pfx}.fc2", bias_colsum=False)
+            self._linear_bwd(dhpre, k("xn2"), f"{pfx}.fc1")
+        else:
+            self._linear_bwd(dx_out, k("h"), f"{pfx}.fc2", dx=dhpre, bias_colsum=False, aux_in=k("hpre"))
+            self._linear_bwd(dhpre, k("xn2"), f"{pfx}.fc1", dx=dxn2)
         dx1 = s("dx1", (M, D))
         ops.layernorm_bwd(dxn2, k("x1"), k("mean2"), k("rstd2"), f.w32(f"{pfx}.ln2.weight"),
                           f.g(f"{pfx}.ln2.weight"), f.g(f"{pfx}.ln2.bias"), dres=dx_out, dx=dx1,

@@ -71,6 +71,14 @@ def _profiled(name):
                 for extra in ("resid", "aux_in", "aux_out"):
                     if k.get(extra) is not None:
                         by += 2.0 * M * N
+            elif name in ("mlp_fwd", "mlp_bwd_dgrad"):
+                M, D = a[0].shape
+                R = a[1].shape[0]
+                fl = 2.0 * 2.0 * M * D * R
+                if name == "mlp_fwd":       # x + resid + out, hpre + h written, weights once
+                    by = 2.0 * M * D * (2 + (k.get("resid") is not None)) + 2.0 * M * R * ((k.get("hpre") is not None) + (k.get("h") is not None)) + 4.0 * D * R
+                else:                       # dy + dx, hpre read, dhpre written
+                    by = 2.0 * M * D * 2 + 2.0 * M * R * 2 + 4.0 * D * R
             elif name in ("attn_fwd", "attn_bwd"):
                 qkv, Bn, S, H = a[0], a[-3] if name == "attn_bwd" else a[1], a[-2] if name == "attn_bwd" else a[2], a[-1] if name == "attn_bwd" else a[3]
                 Sk = 128            # every item is a 128-row tile (two sequences share one when S = 64)
@@ -134,6 +142,39 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, r
                                   B.stride(0), C.byref(epi), ksplit, stream_ptr())
     check(rc, "sc_gemm_bf16")
     return o
+
+
+@_profiled("mlp_fwd")
+def mlp_fwd(x, w1, b1, w2, b2, *, resid=None, hpre=None, h=None, out=None):
+    """out = resid + gelu(x w1^T + b1) w2^T + b2 in one kernel (sc_mlp_fwd).  x [M,256], w1 [R,256], w2 [256,R] bf16;
+    hpre / h (bf16 [M,R]) are written when given (training)."""
+    _cuda(x, w1, w2)
+    M, D = x.shape
+    R = w1.shape[0]
+    assert x.dtype == BF16 and w1.dtype == BF16 and w2.dtype == BF16 and x.is_contiguous()
+    assert w1.shape == (R, D) and w2.shape == (D, R) and w1.is_contiguous() and w2.is_contiguous()
+    if out is None:
+        out = torch.empty(M, D, device=x.device, dtype=BF16)
+    for t, shp in ((resid, (M, D)), (out, (M, D)), (hpre, (M, R)), (h, (M, R))):
+        if t is not None:
+            assert t.dtype == BF16 and t.shape == shp and t.is_contiguous()
+    rc = _lib.load().sc_mlp_fwd(ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(resid), ptr(hpre), ptr(h), ptr(out),
+                                M, D, R, stream_ptr())
+    check(rc, "sc_mlp_fwd")
+    return out
+
+
+@_profiled("mlp_bwd_dgrad")
+def mlp_bwd_dgrad(dy, w1, w2, hpre, *, dhpre, dx):
+    """dhpre = (dy w2) * gelu'(hpre), dx = dhpre w1 in one kernel (sc_mlp_bwd_dgrad)."""
+    _cuda(dy, w1, w2, hpre, dhpre, dx)
+    M, D = dy.shape
+    R = w1.shape[0]
+    for t, shp in ((dy, (M, D)), (dx, (M, D)), (hpre, (M, R)), (dhpre, (M, R)), (w1, (R, D)), (w2, (D, R))):
+        assert t.dtype == BF16 and t.shape == shp and t.is_contiguous()
+    rc = _lib.load().sc_mlp_bwd_dgrad(ptr(dy), ptr(w1), ptr(w2), ptr(hpre), ptr(dhpre), ptr(dx), M, D, R, stream_ptr())
+    check(rc, "sc_mlp_bwd_dgrad")
+    return dx
 
 
 def debug_set(key: str, value: int):

@@ -45,13 +45,16 @@ def make(shape_name):
                     kw=lambda: dict(aux_in=g(M, 1024)))
     if shape_name == "dgrad_fc1":  # dx = dhpre W1
         return dict(M=M, N=256, K=1024, A=lambda: g(M, 1024), B=g(1024, 256), b_mn=True, kw=lambda: dict())
+    if shape_name == "big":
+        return dict(M=8192, N=8192, K=8192, A=lambda: g(8192, 8192), B=g(8192, 8192), kw=lambda: dict())
     if shape_name == "plain256":
         return dict(M=M, N=256, K=256, A=lambda: g(M, 256), B=g(256, 256), kw=lambda: dict())
     raise KeyError(shape_name)
 
 
-def time_case(spec, dbg, nwg, iters=12, slots=0):
+def time_case(spec, dbg, nwg, iters=12, slots=0, cta2=0):
     ops.debug_set("reset", 0)
+    ops.debug_set("cta2", cta2)
     ops.debug_set("gemm_dbg", dbg)
     ops.debug_set("nwg", nwg)
     ops.debug_set("slots", slots)
@@ -81,9 +84,26 @@ def main():
                 ("epi_skip+a_l2", 9), ("epi_skip+no_b", 17), ("epi_skip+no_mma", 5), ("no_mma+no_tma", 6)]
     if os.environ.get("SC_BOTTLENECK_QUICK"):
         variants = [("full", 0), ("epi_skip", 1), ("epi_no_tma", 2), ("no_mma+no_tma", 6)]
-    for name in ("qkv", "proj", "fc1", "fc2", "dgrad_fc2", "dgrad_fc1", "plain256"):
+    names = ("qkv", "proj", "fc1", "fc2", "dgrad_fc2", "dgrad_fc1", "plain256")
+    if os.environ.get("SC_BOTTLENECK_MMA"):
+        names = ("fc2", "qkv", "fc1", "big")
+    for name in names:
         spec = make(name)
         rec = {}
+        if os.environ.get("SC_BOTTLENECK_MMA"):
+            # raw tensor-pipe rate: no loads, no epilogue work (bits 32 | 1), single CTA per tile and CTA pairs
+            for cta2 in (0, 1):
+                for vn, bits in (("mma_only", 33), ("loads+mma", 1), ("full", 0)):
+                    ops.debug_set("reset", 0)
+                    try:
+                        rec[f"cta2={cta2}.{vn}"] = round(time_case(spec, bits, 1, slots=2, cta2=cta2), 1)
+                    except Exception as e:   # noqa: BLE001
+                        rec[f"cta2={cta2}.{vn}"] = f"ERR {e}"
+            fl = 2.0 * spec["M"] * spec["N"] * spec["K"]
+            rec["tflops_mma_only"] = round(fl / rec["cta2=0.mma_only"] / 1e6, 1) if isinstance(rec["cta2=0.mma_only"], float) else None
+            out[name] = rec
+            print(name, json.dumps(rec), flush=True)
+            continue
         if os.environ.get("SC_BOTTLENECK_CFG"):
             # epilogue configuration sweep: (warpgroups, slots per warp); 0/0 = the library's own choice
             for nwg, slots in ((0, 0), (1, 2), (2, 2), (1, 4), (2, 4)):

@@ -1,0 +1,105 @@
+"""GPU parity: the fused MLP kernels (sc_mlp_fwd / sc_mlp_bwd_dgrad) vs the oracle's block MLP.
+
+The oracle's MLP (oracle/model.py: Block.forward, `x + fc2(gelu(fc1(ln2(x))))`, tanh-form GELU) is restated
+here on the same bf16-rounded operands in fp32; tolerance is the bf16 bar of BASELINE.json (rtol 2e-2 relative
+to the tensor's scale).  Edge cases: one tile, a ragged tail (M % 128 != 0), several tiles per CTA, no residual,
+inference mode (nothing saved), narrower hidden width.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _mk(M, R, seed, D=256):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *s, sc=1.0: torch.randn(*s, generator=g, device="cuda") * sc
+    x = rn(M, D).to(BF16)
+    w1 = rn(R, D, sc=D ** -0.5).to(BF16)
+    w2 = rn(D, R, sc=R ** -0.5).to(BF16)
+    b1 = rn(R, sc=0.2)
+    b2 = rn(D, sc=0.2)
+    resid = rn(M, D).to(BF16)
+    return x, w1, b1, w2, b2, resid
+
+
+def _rel(got, ref):
+    return float((got.float() - ref.float()).abs().max() / (ref.float().abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("M,R", [(128, 1024), (200, 1024), (4096 + 37, 1024), (148 * 128 * 2 + 5, 1024), (333, 256)])
+def test_mlp_fwd_matches_oracle(cuda_lib, M, R):
+    from multimodal_sc_b200 import ops
+    x, w1, b1, w2, b2, resid = _mk(M, R, seed=M)
+    hpre = torch.full((M, R), float("nan"), device="cuda", dtype=BF16)
+    h = torch.full((M, R), float("nan"), device="cuda", dtype=BF16)
+    out = torch.full((M, 256), float("nan"), device="cuda", dtype=BF16)
+    ops.mlp_fwd(x, w1, b1, w2, b2, resid=resid, hpre=hpre, h=h, out=out)
+    torch.cuda.synchronize()
+    hpre_ref = x.float() @ w1.float().t() + b1
+    h_ref = F.gelu(hpre_ref, approximate="tanh")
+    # the kernel feeds the bf16-rounded activation to the second GEMM, like the unfused path
+    out_ref = h_ref.to(BF16).float() @ w2.float().t() + b2 + resid.float()
+    assert not torch.isnan(out.float()).any() and not torch.isnan(h.float()).any() and not torch.isnan(hpre.float()).any()
+    assert _rel(hpre, hpre_ref) < 1e-2, ("hpre", _rel(hpre, hpre_ref))
+    assert _rel(h, h_ref) < 1e-2, ("h", _rel(h, h_ref))
+    assert _rel(out, out_ref) < 1e-2, ("out", _rel(out, out_ref))
+
+
+def test_mlp_fwd_inference_no_saves_no_resid(cuda_lib):
+    from multimodal_sc_b200 import ops
+    M, R = 1000, 1024
+    x, w1, b1, w2, b2, _ = _mk(M, R, seed=5)
+    out = ops.mlp_fwd(x, w1, b1, w2, b2)
+    torch.cuda.synchronize()
+    ref = F.gelu(x.float() @ w1.float().t() + b1, approximate="tanh").to(BF16).float() @ w2.float().t() + b2
+    assert _rel(out, ref) < 1e-2
+
+
+def test_mlp_fwd_equals_unfused_gemms(cuda_lib):
+    """same operands through the two-GEMM path (sc_gemm_bf16 x 2): results agree to bf16 rounding."""
+    from multimodal_sc_b200 import ops
+    M, R = 2048 + 64, 1024
+    x, w1, b1, w2, b2, resid = _mk(M, R, seed=9)
+    h1 = torch.empty(M, R, device="cuda", dtype=BF16)
+    hp1 = torch.empty(M, R, device="cuda", dtype=BF16)
+    o1 = torch.empty(M, 256, device="cuda", dtype=BF16)
+    ops.gemm(x, w1, bias=b1, act="gelu", aux_out=hp1, out=h1)
+    ops.gemm(h1, w2, bias=b2, resid=resid, out=o1)
+    h2, hp2, o2 = torch.empty_like(h1), torch.empty_like(hp1), torch.empty_like(o1)
+    ops.mlp_fwd(x, w1, b1, w2, b2, resid=resid, hpre=hp2, h=h2, out=o2)
+    torch.cuda.synchronize()
+    assert _rel(hp2, hp1) < 4e-3 and _rel(h2, h1) < 4e-3 and _rel(o2, o1) < 8e-3
+
+
+@pytest.mark.parametrize("M,R", [(128, 1024), (777, 1024), (148 * 128 + 129, 1024), (260, 384)])
+def test_mlp_bwd_dgrad_matches_autograd(cuda_lib, M, R):
+    from multimodal_sc_b200 import ops
+    x, w1, b1, w2, b2, _ = _mk(M, R, seed=100 + M)
+    g = torch.Generator(device="cuda").manual_seed(M)
+    dy = torch.randn(M, 256, generator=g, device="cuda").to(BF16)
+    hpre = (x.float() @ w1.float().t() + b1).to(BF16)
+    dhpre = torch.full((M, R), float("nan"), device="cuda", dtype=BF16)
+    dx = torch.full((M, 256), float("nan"), device="cuda", dtype=BF16)
+    ops.mlp_bwd_dgrad(dy, w1, w2, hpre, dhpre=dhpre, dx=dx)
+    torch.cuda.synchronize()
+    hp = hpre.float().requires_grad_(True)
+    hact = F.gelu(hp, approximate="tanh")
+    (hact * (dy.float() @ w2.float())).sum().backward()
+    dhpre_ref = hp.grad
+    dx_ref = dhpre_ref.to(BF16).float() @ w1.float()
+    assert not torch.isnan(dx.float()).any() and not torch.isnan(dhpre.float()).any()
+    assert _rel(dhpre, dhpre_ref) < 1e-2, ("dhpre", _rel(dhpre, dhpre_ref))
+    assert _rel(dx, dx_ref) < 1e-2, ("dx", _rel(dx, dx_ref))
+
+
+def test_mlp_rejects_bad_shapes(cuda_lib):
+    from multimodal_sc_b200 import _lib, ops
+    x = torch.zeros(128, 128, device="cuda", dtype=BF16)
+    w1 = torch.zeros(1024, 128, device="cuda", dtype=BF16)
+    w2 = torch.zeros(128, 1024, device="cuda", dtype=BF16)
+    with pytest.raises(_lib.SemcomError):
+        ops.mlp_fwd(x, w1, None, w2, None)
