@@ -95,6 +95,12 @@ struct GemmParams {
   int in_row_period;            // > 0: the TMA input tile is a [period, N] table indexed by row % period
   // UMMA descriptor fields (bytes); defaults set by the host, overridable for bring-up
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+  // skinny problems (one N tile with N < 256, one M tile with M <= 64): only the live part of the operand tiles is
+  // loaded and the MMA is issued with the narrow N — TMA boxes that are mostly out of bounds are slow to zero-fill
+  int n_mma;                    // MMA N = rows of the K-major B box (multiple of 16, <= 256)
+  int n_chunks;                 // 64-column chunks of an MN-major B tile that are loaded
+  int m_chunks;                 // 64-column chunks of an MN-major A tile that are loaded
+  uint32_t a_tx, b_tx;          // bytes per stage that the loads above deliver
   // bottleneck-isolation switches (sc_debug_set("gemm_dbg", bits); results are WRONG when any bit is set):
   //   1 = epilogue only releases the accumulator, 2 = epilogue without its TMA stores/loads,
   //   4 = no MMAs issued, 8 = every tile loads A block 0 (no HBM reads), 16 = B tiles are not loaded,
@@ -572,19 +578,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           } else {
             const uint32_t fb = fb_local;
-            mbar_arrive_expect_tx(fb, (p.dbg & 16) ? A_BYTES : STAGE_BYTES);
+            mbar_arrive_expect_tx(fb, (p.dbg & 16) ? p.a_tx : p.a_tx + p.b_tx);
             if (A_MN == 0) {
               tma_load_2d(a_dst, &tmA, fb, k0, m0);
             } else {
-#pragma unroll
-              for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
+              for (int c = 0; c < p.m_chunks; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
             }
             if (p.dbg & 16) {
             } else if (B_MN == 0) {
-              tma_load_2d(b_dst, &tmB, fb, k0, n0);
+              tma_load_2d(b_dst, &tmB, fb, k0, n0);                      // box = 64 k x n_mma rows
             } else {
-#pragma unroll
-              for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
+              for (int c = 0; c < p.n_chunks; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -594,7 +598,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && rank == 0) {                              // pair: only the leader CTA issues MMAs
-      constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
+      const uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, CTA2 ? BN : static_cast<uint32_t>(p.n_mma), A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -940,11 +944,21 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   if (g_dbg.b_sbo) p.b_sbo = (uint32_t)g_dbg.b_sbo;
   if (g_dbg.b_kstep) p.b_kstep = (uint32_t)g_dbg.b_kstep;
 
+  // skinny operands: load and multiply only the live part of the tile
+  p.n_mma = BN; p.n_chunks = BN / 64; p.m_chunks = BM / 64;
+  if (!cta2 && p.tiles_n == 1 && N < BN) {
+    p.n_mma = static_cast<int>((N + 15) / 16 * 16);
+    p.n_chunks = (p.n_mma + 63) / 64;
+  }
+  if (!cta2 && p.tiles_m == 1 && M <= 64) p.m_chunks = 1;
+  p.a_tx = a_mn ? static_cast<uint32_t>(p.m_chunks) * CHUNK_BYTES : A_BYTES;
+  p.b_tx = b_mn ? static_cast<uint32_t>(p.n_chunks) * CHUNK_BYTES : static_cast<uint32_t>(p.n_mma) * BK * 2;
+
   CUtensorMap tmA, tmB;
   if (a_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
   else           rc = sc_encode_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK);
   if (rc != SC_OK) return rc;
-  if (b_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, cta2 ? BN / 2 : BN);
+  if (b_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, cta2 ? BN / 2 : p.n_mma);
   else           rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK);
   if (rc != SC_OK) return rc;
 

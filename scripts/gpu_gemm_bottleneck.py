@@ -45,6 +45,14 @@ def make(shape_name):
                     kw=lambda: dict(aux_in=g(M, 1024)))
     if shape_name == "dgrad_fc1":  # dx = dhpre W1
         return dict(M=M, N=256, K=1024, A=lambda: g(M, 1024), B=g(1024, 256), b_mn=True, kw=lambda: dict())
+    if shape_name == "sym":        # symbol projection: [M,256] x [16,256]^T + bias -> fp32 [M,16]
+        return dict(M=M, N=16, K=256, A=lambda: g(M, 256), B=g(16, 256), f32=True,
+                    kw=lambda: dict(bias=torch.zeros(16, device="cuda")))
+    if shape_name == "dsym":       # its dgrad twin in the decoder: [2M,256] x [256,16] -> fp32 [2M,16]
+        return dict(M=2 * M, N=16, K=256, A=lambda: g(2 * M, 256), B=g(256, 16), b_mn=True, f32=True, kw=lambda: dict())
+    if shape_name == "inproj":     # decoder input projection: K = 16
+        return dict(M=2 * M, N=256, K=16, A=lambda: g(2 * M, 16), B=g(256, 16),
+                    kw=lambda: dict(bias=torch.zeros(256, device="cuda")))
     if shape_name == "big":
         return dict(M=8192, N=8192, K=8192, A=lambda: g(8192, 8192), B=g(8192, 8192), kw=lambda: dict())
     if shape_name == "plain256":
@@ -61,10 +69,14 @@ def time_case(spec, dbg, nwg, iters=12, slots=0, cta2=0):
     sets = []
     for _ in range(SETS):
         kw = spec["kw"]()
-        sets.append((spec["A"](), kw, torch.empty(spec["M"], spec["N"], device="cuda", dtype=BF16)))
+        sets.append((spec["A"](), kw, torch.empty(spec["M"], spec["N"], device="cuda",
+                                                     dtype=torch.float32 if spec.get("f32") else BF16)))
     def run(i):
         A, kw, out = sets[i % SETS]
-        ops.gemm(A, spec["B"], b_mn=spec.get("b_mn", False), out=out, **kw)
+        if spec.get("f32"):
+            ops.gemm(A, spec["B"], b_mn=spec.get("b_mn", False), out_f32=out, **kw)
+        else:
+            ops.gemm(A, spec["B"], b_mn=spec.get("b_mn", False), out=out, **kw)
     for i in range(3):
         run(i)
     torch.cuda.synchronize()
@@ -87,6 +99,8 @@ def main():
     names = ("qkv", "proj", "fc1", "fc2", "dgrad_fc2", "dgrad_fc1", "plain256")
     if os.environ.get("SC_BOTTLENECK_MMA"):
         names = ("fc2", "qkv", "fc1", "big")
+    if os.environ.get("SC_BOTTLENECK_SKINNY"):
+        names = ("sym", "dsym", "inproj", "plain256")
     for name in names:
         spec = make(name)
         rec = {}
@@ -101,6 +115,16 @@ def main():
                         rec[f"cta2={cta2}.{vn}"] = f"ERR {e}"
             fl = 2.0 * spec["M"] * spec["N"] * spec["K"]
             rec["tflops_mma_only"] = round(fl / rec["cta2=0.mma_only"] / 1e6, 1) if isinstance(rec["cta2=0.mma_only"], float) else None
+            out[name] = rec
+            print(name, json.dumps(rec), flush=True)
+            continue
+        if os.environ.get("SC_BOTTLENECK_SKINNY"):
+            for vn, bits in (("full", 0), ("epi_skip", 1), ("no_mma", 4), ("no_b", 16), ("epi_skip+no_b", 17), ("epi_skip+no_mma", 5),
+                             ("loads_off", 32), ("loads_off+epi_skip", 33)):
+                try:
+                    rec[vn] = round(time_case(spec, bits, 0), 1)
+                except Exception as e:   # noqa: BLE001
+                    rec[vn] = f"ERR {e}"
             out[name] = rec
             print(name, json.dumps(rec), flush=True)
             continue
