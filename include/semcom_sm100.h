@@ -96,6 +96,15 @@ typedef struct sc_gemm_epilogue {
   float* colsum;           /* a_mn = 1 (wgrad form) only: colsum[m] += sum_k A(m,k), i.e. the bias gradient
                               sum_tokens dy[token, m], computed by one extra tcgen05.mma per K-slice against
                               an all-ones shared-memory tile (no extra memory traffic) */
+  /* fused LayerNorm of the output row (N == 256, bf16 output with bias and one bf16 input tile): besides
+   * out_bf16 = acc + bias + resid the kernel writes ln_out = LayerNorm(out_bf16) * ln_gamma + ln_beta (bf16,
+   * same leading dimension) and the row statistics (fp32 [M], optional) that sc_layernorm_bwd consumes. */
+  void* ln_out;
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
 } sc_gemm_epilogue;
 
 int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn,

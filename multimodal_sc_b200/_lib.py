@@ -39,6 +39,12 @@ class GemmEpilogue(C.Structure):
         ("atomic", C.c_int32),
         ("rowadd_bf16", C.c_void_p),
         ("colsum", C.c_void_p),
+        ("ln_out", C.c_void_p),
+        ("ln_gamma", C.c_void_p),
+        ("ln_beta", C.c_void_p),
+        ("ln_mean", C.c_void_p),
+        ("ln_rstd", C.c_void_p),
+        ("ln_eps", C.c_float),
     ]
 
 

@@ -44,7 +44,9 @@ template <int CTA2, int NWG, int SLOTS> struct Geo {
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING = NWG * 4 * SLOTS * EPI_SLOT_BYTES;
-  static constexpr int BIAS = NWG * BIAS_TILE_BYTES;
+  // one bias tile per warpgroup; the 1-warpgroup / 4-slot geometry also parks LayerNorm gamma and beta (fused LN)
+  static constexpr int LN_TILES = (NWG == 1 && SLOTS == 4 && !CTA2) ? 2 : 0;
+  static constexpr int BIAS = (NWG + LN_TILES) * BIAS_TILE_BYTES;
   static constexpr int STAGES_FIT = (SMEM_LIMIT - STATIC_SMEM_RESERVE - RING - BIAS) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int SMEM = STAGES * STAGE_BYTES;
@@ -67,6 +69,7 @@ constexpr int KIND_BIAS = 2;                         // + bias
 constexpr int KIND_FC1 = 3;                          // + bias, pre-activation copy, tanh-GELU
 constexpr int KIND_RESID = 4;                        // + bias + residual tile
 constexpr int KIND_DGELU = 5;                        // * GELU'(pre-activation tile)
+constexpr int KIND_RESID_LN = 6;                     // + bias + residual tile, then LayerNorm of the row as a second output
 constexpr uint32_t TMEM_COLS = 512;
 
 struct GemmParams {
@@ -93,6 +96,12 @@ struct GemmParams {
   int epi_kind;
   float* colsum;                // a_mn = 1 only: colsum[m] += sum_k A(m,k) via an extra MMA against an all-ones tile
   int in_row_period;            // > 0: the TMA input tile is a [period, N] table indexed by row % period
+  // fused LayerNorm of the output row (N == 256 only): second bf16 output through tmAux, statistics to ln_mean/ln_rstd
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
   // UMMA descriptor fields (bytes); defaults set by the host, overridable for bring-up
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
   // skinny problems (one N tile with N < 256, one M tile with M <= 64): only the live part of the operand tiles is
@@ -468,6 +477,123 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
   }
 }
 
+// Residual GEMM epilogue with the following LayerNorm fused in (N == 256, 4 slots per warp, 1 warpgroup):
+//   pass 1: x = acc + bias + residual tile -> bf16 into the four slots (TMA store, tmOut) while the row statistics
+//           accumulate in registers (from the rounded values, like the stand-alone LayerNorm kernel reads them);
+//   pass 2: the slots still hold the whole 32 x 256 row block: y = (x - mean) rstd gamma + beta is written over it
+//           chunk by chunk once the first store has read the slot, and leaves through tmLn.
+// The next tile's residual chunks are requested as the second stores drain.
+__device__ __forceinline__ void staged_tile_ln(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmLn,
+                                               const CUtensorMap* tmIn, uint32_t t_addr, uint32_t ring, uint32_t in_bar0,
+                                               uint32_t bias_tile, uint32_t gamma_tile, uint32_t beta_tile, int lane,
+                                               int row0, int64_t row, bool row_ok, uint32_t tile_parity,
+                                               const NextTile& next) {
+  const bool no_tma = (p.dbg & 2) != 0;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  auto lds4 = [&](uint32_t addr) {
+    const uint4 w = ld_shared_v4(addr);
+    return make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+  };
+  uint32_t v[2][16];
+  float4 bv[2][4];
+  uint64_t s1 = pk2(0.f, 0.f), s2 = s1;
+  auto issue = [&](int s, uint32_t (&vv)[16], float4 (&bb)[4]) {
+    tmem_ld_32x32b_x16(t_addr + s * 16, vv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bb[q] = lds4(bias_tile + s * 64 + q * 16);
+  };
+  auto pass1 = [&](int s, const uint32_t (&vv)[16], const float4 (&bb)[4]) {
+    const int c = s >> 2, h = s & 3;
+    const uint32_t row_o = ring + c * EPI_SLOT_BYTES + lane * 128;
+    const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+    uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
+    if (!no_tma) {
+      i0 = ld_shared_v4(row_o + pa);
+      i1 = ld_shared_v4(row_o + pb);
+    }
+    const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = bb[j >> 1];
+      uint64_t x = add2(pk2u(vv[2 * j], vv[2 * j + 1]), (j & 1) ? pk2(b.z, b.w) : pk2(b.x, b.y));
+      x = add2(x, unpack2_bf16(iw[j]));
+      o[j] = pack2_bf16(x);
+      const uint64_t xr = unpack2_bf16(o[j]);
+      s1 = add2(s1, xr);
+      s2 = fma2(xr, xr, s2);
+    }
+    st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
+    st_shared_v4(row_o + pb, o[4], o[5], o[6], o[7]);
+  };
+  issue(0, v[0], bv[0]);
+#pragma unroll 1
+  for (int s = 0; s < 16; s += 2) {
+    if ((s & 3) == 0) {
+      if (!no_tma) mbar_wait(in_bar0 + (s >> 2) * 8, tile_parity);
+      __syncwarp();
+    }
+    tmem_ld_wait();
+    issue(s + 1, v[1], bv[1]);
+    pass1(s, v[0], bv[0]);
+    tmem_ld_wait();
+    if (s + 2 < 16) issue(s + 2, v[0], bv[0]);
+    pass1(s + 1, v[1], bv[1]);
+    if ((s & 3) == 2) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && !no_tma) {
+        tma_store_2d(tmOut, ring + (s >> 2) * EPI_SLOT_BYTES, (s >> 2) * 64, row0);
+        tma_store_commit();
+      }
+    }
+  }
+  float a0, a1, q0, q1;
+  upk2(s1, a0, a1);
+  upk2(s2, q0, q1);
+  const float mean = (a0 + a1) * (1.0f / BN);
+  const float var = fmaxf((q0 + q1) * (1.0f / BN) - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + p.ln_eps);
+  if (row_ok) {
+    if (p.ln_mean) p.ln_mean[row] = mean;
+    if (p.ln_rstd) p.ln_rstd[row] = rstd;
+  }
+  const uint64_t rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    if (lane == 0) tma_store_wait_read<3>();                   // the x store of chunk c has read the slot
+    __syncwarp();
+    const uint32_t row_o = ring + c * EPI_SLOT_BYTES + lane * 128;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int s = c * 4 + h;
+      const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+      const uint4 i0 = ld_shared_v4(row_o + pa), i1 = ld_shared_v4(row_o + pb);
+      const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+      uint32_t o[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 g = lds4(gamma_tile + s * 64 + q * 16), b = lds4(beta_tile + s * 64 + q * 16);
+        o[2 * q] = pack2_bf16(fma2(fma2(unpack2_bf16(iw[2 * q]), rs2, nm2), pk2(g.x, g.y), pk2(b.x, b.y)));
+        o[2 * q + 1] = pack2_bf16(fma2(fma2(unpack2_bf16(iw[2 * q + 1]), rs2, nm2), pk2(g.z, g.w), pk2(b.z, b.w)));
+      }
+      st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
+      st_shared_v4(row_o + pb, o[4], o[5], o[6], o[7]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && !no_tma) {
+      tma_store_2d(tmLn, ring + c * EPI_SLOT_BYTES, c * 64, row0);
+      tma_store_commit();
+      if (c >= 1 && next.valid) {                              // slot c-1 is free: the next tile's residual chunk c-1
+        tma_store_wait_read<1>();
+        mbar_arrive_expect_tx(in_bar0 + (c - 1) * 8, EPI_SLOT_BYTES);
+        tma_load_2d(ring + (c - 1) * EPI_SLOT_BYTES, tmIn, in_bar0 + (c - 1) * 8, next.n0 + (c - 1) * 64, next.in_row0);
+      }
+    }
+  }
+}
+
 template <int A_MN, int B_MN, int CTA2, int NWG, int SLOTS>
 __global__ void __launch_bounds__(128 + NWG * 128, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -521,6 +647,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
       st_shared_v4(ones_tile + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
+  }
+  if (G::LN_TILES && p.ln_gamma) {                           // fused LayerNorm: gamma / beta of the 256 columns
+    const uint32_t ln_base = smem_base + G::SMEM + G::RING + NWG * BIAS_TILE_BYTES;
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+      const float w = i < BN ? __ldg(p.ln_gamma + i) : __ldg(p.ln_beta + i - BN);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(ln_base + i * 4), "f"(w) : "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -773,6 +906,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           case KIND_FC1:   SC_TILE(KIND_FC1); break;
           case KIND_RESID: SC_TILE(KIND_RESID); break;
           case KIND_DGELU: SC_TILE(KIND_DGELU); break;
+          case KIND_RESID_LN:
+            if constexpr (G::LN_TILES != 0) {
+              const uint32_t ln_base = smem_base + G::SMEM + G::RING + NWG * BIAS_TILE_BYTES;
+              staged_tile_ln(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, bias_tile, ln_base, ln_base + BIAS_TILE_BYTES, lane,
+                             row0, static_cast<int64_t>(row0) + lane, static_cast<int64_t>(row0) + lane < p.M, tile_parity, next);
+            }
+            break;
           default:         SC_TILE(KIND_GEN); break;
 #undef SC_TILE
         }
@@ -983,13 +1123,15 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
       if (!b && epi->act == SC_ACT_NONE && !epi->aux_out && no_in) p.epi_kind = KIND_PLAIN;
       else if (b && epi->act == SC_ACT_NONE && !epi->aux_out && no_in) p.epi_kind = KIND_BIAS;
       else if (b && epi->act == SC_ACT_GELU && epi->aux_out && no_in) p.epi_kind = KIND_FC1;
-      else if (b && epi->act == SC_ACT_NONE && (epi->resid || pos16)) p.epi_kind = KIND_RESID;
+      else if (b && epi->act == SC_ACT_NONE && (epi->resid || pos16)) p.epi_kind = epi->ln_out ? KIND_RESID_LN : KIND_RESID;
       else if (!b && epi->act == SC_ACT_NONE && epi->aux_in) p.epi_kind = KIND_DGELU;
     }
     const uint64_t ldb_bytes = (uint64_t)epi->ldo * 2;
     if ((rc = sc_encode_tmap_2d_bf16(&tmOut, epi->out_bf16, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
     if (epi->aux_out &&
         (rc = sc_encode_tmap_2d_bf16(&tmAux, epi->aux_out, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
+    if (epi->ln_out &&
+        (rc = sc_encode_tmap_2d_bf16(&tmAux, epi->ln_out, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
     if (one_in && pos16) {
       p.in_row_period = (int)epi->rowadd_period;
       if ((rc = sc_encode_tmap_2d_bf16(&tmIn, epi->rowadd_bf16, (uint64_t)N, (uint64_t)epi->rowadd_period,
@@ -998,6 +1140,15 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
       const void* in = epi->resid ? epi->resid : epi->aux_in;
       if ((rc = sc_encode_tmap_2d_bf16(&tmIn, in, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;
     }
+  }
+  if (epi->ln_out) {
+    SC_REQUIRE(staged_ok && p.epi_kind == KIND_RESID_LN && N == BN && !cta2 && epi->ln_gamma && epi->ln_beta &&
+                   sc_aligned16(epi->ln_out),
+               SC_E_SHAPE,
+               "sc_gemm_bf16: the fused LayerNorm needs N == 256, a bf16 output with bias and one bf16 input tile "
+               "(resid or rowadd_bf16), alpha == 1, no activation, ln_gamma and ln_beta");
+    p.ln_gamma = epi->ln_gamma; p.ln_beta = epi->ln_beta; p.ln_mean = epi->ln_mean; p.ln_rstd = epi->ln_rstd;
+    p.ln_eps = epi->ln_eps;
   }
   SC_REQUIRE(staged_ok || !epi->rowadd_bf16, SC_E_SHAPE,
              "sc_gemm_bf16: rowadd_bf16 needs the staged epilogue (bf16 output, N %% 256 == 0, period %% 32 == 0, "
@@ -1014,8 +1165,9 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   // (measured on B200, M = 262144: profiles/r1_gemm_epilogue_configs.json)
   const bool short_k = K <= 256 && p.epi_mode != EPI_GENERIC;
   const bool light_in = short_k && p.epi_mode == EPI_IN && p.epi_kind == KIND_RESID;
-  const int nwg = g_dbg.nwg ? (g_dbg.nwg == 2 ? 2 : 1) : ((short_k && !light_in) ? 2 : 1);
-  const int slots = g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2);
+  const bool fused_ln = p.epi_kind == KIND_RESID_LN && p.epi_mode == EPI_IN;       // needs 1 warpgroup x 4 slots
+  const int nwg = fused_ln ? 1 : (g_dbg.nwg ? (g_dbg.nwg == 2 ? 2 : 1) : ((short_k && !light_in) ? 2 : 1));
+  const int slots = fused_ln ? 4 : (g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2));
 #define SC_LAUNCH1(AM, BMJ, C2, W, S) launch<AM, BMJ, C2, W, S>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st)
 #define SC_LAUNCH(AM, BMJ)                                                                          \
   (nwg == 2 ? (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 2, 4) : SC_LAUNCH1(AM, BMJ, 0, 2, 2))           \

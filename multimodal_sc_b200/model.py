@@ -145,6 +145,8 @@ class Engine:
         self.sms = torch.cuda.get_device_properties(device).multi_processor_count
         # SC_FUSED_MLP=0 selects the two-GEMM MLP schedule everywhere (A/B runs)
         self.fused_mlp = os.environ.get("SC_FUSED_MLP", "1") != "0"
+        # SC_FUSED_LN=0: every LayerNorm forward is its own kernel instead of a GEMM epilogue
+        self.fused_ln = os.environ.get("SC_FUSED_LN", "1") != "0"
 
     def arena(self, B: int) -> _Arena:
         a = self.arenas.get(B)
@@ -165,33 +167,59 @@ class Engine:
                  ksplit=_wgrad_ksplit(N, K, dy.shape[0], self.sms),
                  colsum=f.g(f"{wname}.bias") if bias_colsum else None)
 
-    def _block_fwd(self, A, pfx, x_in, x_out, B, S, train):
+    def _ln_spec(self, A, wname, M, y_name, mean_name, rstd_name):
+        """arguments of a LayerNorm whose parameters are `wname`.{weight,bias}: either run it (ops.layernorm_fwd)
+        or hand it to the producing GEMM as its fused second output (ops.gemm(..., ln=spec))."""
+        sp, f = self.spec, self.flat
+        return dict(gamma=f.w32(f"{wname}.weight"), beta=f.w32(f"{wname}.bias"), eps=sp.ln_eps,
+                    y=A.buf(y_name, (M, sp.d_model)), mean=A.buf(mean_name, (M,), F32), rstd=A.buf(rstd_name, (M,), F32))
+
+    def _block_ln1(self, A, pfx, M):
+        return self._ln_spec(A, f"{pfx}.ln1", M, f"{pfx}.xn1", f"{pfx}.mean1", f"{pfx}.rstd1")
+
+    @staticmethod
+    def _run_ln(x, ln):
+        ops.layernorm_fwd(x, ln["gamma"], ln["beta"], ln["eps"], y=ln["y"], mean=ln["mean"], rstd=ln["rstd"])
+
+    def _block_fwd(self, A, pfx, x_in, x_out, B, S, train, xn1_ready=False, next_ln=None):
+        """one pre-LN block.  `xn1_ready`: the producer of x_in already wrote LN1(x_in) (fused epilogue).
+        `next_ln`: the LayerNorm that consumes x_out (next block's LN1 or the stack's final norm); it is applied
+        here, fused into the fc2 GEMM's epilogue when possible."""
         sp, f = self.spec, self.flat
         M, D, H = x_in.shape[0], sp.d_model, sp.n_heads
         k = lambda n, shape, dt=BF16: A.buf(f"{pfx}.{n}", shape, dt)
-        xn1 = k("xn1", (M, D))
-        ops.layernorm_fwd(x_in, f.w32(f"{pfx}.ln1.weight"), f.w32(f"{pfx}.ln1.bias"), sp.ln_eps, y=xn1,
-                          mean=k("mean1", (M,), F32), rstd=k("rstd1", (M,), F32))
+        fuse_ln = self.fused_ln and D == 256
+        ln1 = self._block_ln1(A, pfx, M)
+        if not xn1_ready:
+            self._run_ln(x_in, ln1)
+        xn1 = ln1["y"]
         qkv = k("qkv", (M, 3 * D))
         ops.gemm(xn1, f.w16(f"{pfx}.qkv.weight"), bias=f.w32(f"{pfx}.qkv.bias"), out=qkv)
         ao = k("ao", (M, D))
         ops.attn_fwd(qkv, B, S, H, out=ao, lse=k("lse", (M, H), F32))
         x1 = k("x1", (M, D))
-        ops.gemm(ao, f.w16(f"{pfx}.proj.weight"), bias=f.w32(f"{pfx}.proj.bias"), resid=x_in, out=x1)
-        xn2 = k("xn2", (M, D))
-        ops.layernorm_fwd(x1, f.w32(f"{pfx}.ln2.weight"), f.w32(f"{pfx}.ln2.bias"), sp.ln_eps, y=xn2,
-                          mean=k("mean2", (M,), F32), rstd=k("rstd2", (M,), F32))
+        ln2 = self._ln_spec(A, f"{pfx}.ln2", M, f"{pfx}.xn2", f"{pfx}.mean2", f"{pfx}.rstd2")
+        ops.gemm(ao, f.w16(f"{pfx}.proj.weight"), bias=f.w32(f"{pfx}.proj.bias"), resid=x_in, out=x1,
+                 ln=ln2 if fuse_ln else None)
+        if not fuse_ln:
+            self._run_ln(x1, ln2)
+        xn2 = ln2["y"]
         if not train and self.fused_mlp and D == 256:
             # inference: fc1 -> GELU -> fc2 in one kernel, the hidden activation never leaves the SM
             ops.mlp_fwd(xn2, f.w16(f"{pfx}.fc1.weight"), f.w32(f"{pfx}.fc1.bias"), f.w16(f"{pfx}.fc2.weight"),
                         f.w32(f"{pfx}.fc2.bias"), resid=x1, out=x_out)
+            if next_ln is not None:
+                self._run_ln(x_out, next_ln)
             return
         # training saves both hpre and h: two wide outputs make the fused kernel store-bound, so the forward
         # keeps the two-GEMM form (profiles/README.md, r1 fused-MLP table)
         h = k("h", (M, sp.d_mlp))
         hpre = k("hpre", (M, sp.d_mlp)) if train else None
         ops.gemm(xn2, f.w16(f"{pfx}.fc1.weight"), bias=f.w32(f"{pfx}.fc1.bias"), act="gelu", aux_out=hpre, out=h)
-        ops.gemm(h, f.w16(f"{pfx}.fc2.weight"), bias=f.w32(f"{pfx}.fc2.bias"), resid=x1, out=x_out)
+        ops.gemm(h, f.w16(f"{pfx}.fc2.weight"), bias=f.w32(f"{pfx}.fc2.bias"), resid=x1, out=x_out,
+                 ln=next_ln if fuse_ln else None)
+        if next_ln is not None and not fuse_ln:
+            self._run_ln(x_out, next_ln)
 
     def _block_bwd(self, A, pfx, x_in, dx_out, dx_in, prev_bias_grad, B, S):
         """dx_out: grad wrt block output [M,D] (its column sums were already added to fc2.bias grad by the
@@ -239,13 +267,17 @@ class Engine:
             M = B * S
             tok = ops.patchify(img, patch, out=A.buf(f"{enc}.tok", (M, img.shape[1] * patch * patch)))
             xs = [A.buf(f"{enc}.x{l}", (M, D)) for l in range(sp.enc_layers + 1)]
+            fuse_ln = self.fused_ln and D == 256
+            # every LayerNorm rides on the epilogue of the GEMM that produces its input: the patch embedding feeds
+            # block 0's LN1, each block's fc2 feeds the next block's LN1 / the final norm
             ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
-                     rowadd=f.w16(f"{enc}.pos"), out=xs[0])
+                     rowadd=f.w16(f"{enc}.pos"), out=xs[0],
+                     ln=self._block_ln1(A, f"{enc}.blocks.0", M) if fuse_ln else None)
+            final_ln = self._ln_spec(A, f"{enc}.norm", M, f"{enc}.t", f"{enc}.mean", f"{enc}.rstd")
             for l in range(sp.enc_layers):
-                self._block_fwd(A, f"{enc}.blocks.{l}", xs[l], xs[l + 1], B, S, train)
-            t = A.buf(f"{enc}.t", (M, D))
-            ops.layernorm_fwd(xs[-1], f.w32(f"{enc}.norm.weight"), f.w32(f"{enc}.norm.bias"), sp.ln_eps, y=t,
-                              mean=A.buf(f"{enc}.mean", (M,), F32), rstd=A.buf(f"{enc}.rstd", (M,), F32))
+                nxt = self._block_ln1(A, f"{enc}.blocks.{l + 1}", M) if l + 1 < sp.enc_layers else final_ln
+                self._block_fwd(A, f"{enc}.blocks.{l}", xs[l], xs[l + 1], B, S, train, xn1_ready=fuse_ln, next_ln=nxt)
+            t = final_ln["y"]
             ops.gemm(t, f.w16(f"{enc}.sym.weight"), bias=f.w32(f"{enc}.sym.bias"), out_f32=z_mm[mi].view(M, C))
         # ---- channel ----
         y16 = A.buf("y16", (B, 2, k_sym))
@@ -258,13 +290,14 @@ class Engine:
         Sd = sp.dec_tokens
         Md = B * Sd
         xd = [A.buf(f"dec.x{l}", (Md, D)) for l in range(sp.dec_layers + 1)]
+        fuse_ln = self.fused_ln and D == 256
         ops.gemm(y16.view(Md, C), f.w16("dec.in_proj.weight"), bias=f.w32("dec.in_proj.bias"),
-                 rowadd=f.w16("dec.pos"), out=xd[0])
+                 rowadd=f.w16("dec.pos"), out=xd[0], ln=self._block_ln1(A, "dec.blocks.0", Md) if fuse_ln else None)
+        final_ln = self._ln_spec(A, "dec.norm", Md, "dec.tn", "dec.mean", "dec.rstd")
         for l in range(sp.dec_layers):
-            self._block_fwd(A, f"dec.blocks.{l}", xd[l], xd[l + 1], B, Sd, train)
-        tn = A.buf("dec.tn", (Md, D))
-        ops.layernorm_fwd(xd[-1], f.w32("dec.norm.weight"), f.w32("dec.norm.bias"), sp.ln_eps, y=tn,
-                          mean=A.buf("dec.mean", (Md,), F32), rstd=A.buf("dec.rstd", (Md,), F32))
+            nxt = self._block_ln1(A, f"dec.blocks.{l + 1}", Md) if l + 1 < sp.dec_layers else final_ln
+            self._block_fwd(A, f"dec.blocks.{l}", xd[l], xd[l + 1], B, Sd, train, xn1_ready=fuse_ln, next_ln=nxt)
+        tn = final_ln["y"]
         feat = ops.meanpool_fwd(tn.view(B, Sd, D), out_bf16=A.buf("dec.f", (B, D)))
         recon = A.buf("dec.recon", (Md, D))
         ops.gemm(tn, f.w16("dec.recon.weight"), bias=f.w32("dec.recon.bias"), out=recon)

@@ -68,7 +68,7 @@ def _profiled(name):
                     nm += f"[{M}x{N}x{K}]"
                 fl = 2.0 * M * N * K
                 by = 2.0 * (M * K + N * K) + (4.0 if k.get("out_f32") is not None and k.get("out") is None else 2.0) * M * N
-                for extra in ("resid", "aux_in", "aux_out"):
+                for extra in ("resid", "aux_in", "aux_out", "ln"):
                     if k.get(extra) is not None:
                         by += 2.0 * M * N
             elif name in ("mlp_fwd", "mlp_bwd_dgrad"):
@@ -102,12 +102,13 @@ def _cuda(*ts):
 @_profiled("gemm")
 def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, rowgrp_size=0,
          rowgrp_scale=1.0, alpha=1.0, resid=None, aux_in=None, aux_out=None, out=None,
-         out_f32=None, act=None, atomic=False, ksplit=1, colsum=None):
+         out_f32=None, act=None, atomic=False, ksplit=1, colsum=None, ln=None):
     """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of sc_gemm_bf16.
 
     a_mn=False: A is [M,K]; a_mn=True: A is [K,M].  b_mn=False: B is [N,K]; b_mn=True: B is [K,N].
     `out` (bf16 [M,N]) and/or `out_f32` (fp32 [M,N]) receive the result; both may be strided
-    views with the same leading dimension."""
+    views with the same leading dimension.
+    `ln` = dict(gamma, beta, eps, y[, mean, rstd]) fuses LayerNorm(out) as a second bf16 output (N == 256 only)."""
     _cuda(A, B)
     assert A.dtype == BF16 and B.dtype == BF16 and A.dim() == 2 and B.dim() == 2
     assert A.stride(1) == 1 and B.stride(1) == 1
@@ -138,6 +139,11 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, r
         rowgrp=ptr(rowgrp), rowgrp_size=rowgrp_size, rowgrp_scale=rowgrp_scale, alpha=alpha,
         resid=ptr(resid), aux_in=ptr(aux_in), aux_out=ptr(aux_out), out_bf16=ptr(out),
         out_f32=ptr(out_f32), ldo=ldo, act=SC_ACT[act], atomic=int(atomic), colsum=ptr(colsum))
+    if ln is not None:
+        y = ln["y"]
+        assert y.dtype == BF16 and y.shape == (M, N) and y.stride(1) == 1 and y.stride(0) == ldo
+        epi.ln_out, epi.ln_gamma, epi.ln_beta = ptr(y), ptr(ln["gamma"]), ptr(ln["beta"])
+        epi.ln_mean, epi.ln_rstd, epi.ln_eps = ptr(ln.get("mean")), ptr(ln.get("rstd")), float(ln["eps"])
     rc = _lib.load().sc_gemm_bf16(ptr(A), ptr(B), M, N, K, int(a_mn), int(b_mn), A.stride(0),
                                   B.stride(0), C.byref(epi), ksplit, stream_ptr())
     check(rc, "sc_gemm_bf16")

@@ -103,3 +103,36 @@ def test_mlp_rejects_bad_shapes(cuda_lib):
     w2 = torch.zeros(128, 1024, device="cuda", dtype=BF16)
     with pytest.raises(_lib.SemcomError):
         ops.mlp_fwd(x, w1, None, w2, None)
+
+
+@pytest.mark.parametrize("M,K,mode", [(128, 256, "resid"), (333, 256, "resid"), (148 * 128 * 2 + 77, 1024, "resid"),
+                                      (4096 + 5, 768, "pos"), (640, 16, "pos")])
+def test_gemm_fused_layernorm_epilogue(cuda_lib, M, K, mode):
+    """out = x W^T + b + (resid | pos[row % 64]) with LayerNorm(out) as a fused second output == the two-kernel path."""
+    from multimodal_sc_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    rn = lambda *s, sc=1.0: torch.randn(*s, generator=g, device="cuda") * sc
+    x = rn(M, K).to(BF16)
+    w = rn(256, K, sc=K ** -0.5).to(BF16)
+    b = rn(256, sc=0.3)
+    gamma, beta = 1.0 + rn(256, sc=0.2), rn(256, sc=0.2)
+    resid = rn(M, 256, sc=2.0).to(BF16)
+    pos = rn(64, 256).to(BF16)
+    kw = dict(resid=resid) if mode == "resid" else dict(rowadd=pos)
+    o_ref = torch.empty(M, 256, device="cuda", dtype=BF16)
+    ops.gemm(x, w, bias=b, out=o_ref, **kw)
+    y_ref, m_ref, r_ref = torch.empty_like(o_ref), torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    ops.layernorm_fwd(o_ref, gamma, beta, 1e-5, y=y_ref, mean=m_ref, rstd=r_ref)
+    o = torch.full((M, 256), float("nan"), device="cuda", dtype=BF16)
+    y = torch.full((M, 256), float("nan"), device="cuda", dtype=BF16)
+    mean, rstd = torch.full((M,), float("nan"), device="cuda"), torch.full((M,), float("nan"), device="cuda")
+    ops.gemm(x, w, bias=b, out=o, ln=dict(gamma=gamma, beta=beta, eps=1e-5, y=y, mean=mean, rstd=rstd), **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(o, o_ref), "the primary output must not change"
+    assert not torch.isnan(y.float()).any() and not torch.isnan(mean).any() and not torch.isnan(rstd).any()
+    assert float((mean - m_ref).abs().max()) < 1e-4 * (1 + float(m_ref.abs().max()))
+    assert float(((rstd - r_ref) / r_ref).abs().max()) < 1e-3
+    assert _rel(y, y_ref) < 1e-2
+    # and against the fp32 definition
+    y32 = F.layer_norm(o_ref.float(), (256,), gamma, beta, 1e-5)
+    assert _rel(y, y32) < 1e-2
