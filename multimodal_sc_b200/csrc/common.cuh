@@ -103,6 +103,55 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Non-blocking phase test.  Issued one stage AHEAD by the single-thread roles: the SYNCS round trip (~150 cycles even
+// for a completed phase) then overlaps the MMA / TMA issue of the current stage instead of preceding it.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+
+// Hot-spinning wait (mbarrier.test_wait never suspends the thread).  Only for roles that are ONE thread per CTA
+// (TMA producer, MMA issuer): the spin costs a few issue slots on one scheduler but reacts within tens of cycles.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (it > (1u << 28)) {
+      printf("semcom: mbarrier timeout (spin wait, block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+// One lane of a CONVERGED warp (PTX elect.sync).  The single-thread roles (TMA producer, MMA issuer) run their loops
+// with all 32 lanes converged and guard only the issuing instruction with this predicate: ptxas then keeps the
+// warp-uniform descriptors / coordinates in uniform registers.  A loop inside `if (lane == 0)` is divergent code to
+// ptxas, which wraps every UTCHMMA / UTMALDG in an R2UR + ELECT waterfall (~48 instructions per MMA: the issuing
+// thread, not the tensor pipe, then sets the pace).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0u;
+}
+
 // ---- proxies / fences ---------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

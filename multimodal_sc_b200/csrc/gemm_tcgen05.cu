@@ -113,7 +113,9 @@ struct GemmParams {
   // bottleneck-isolation switches (sc_debug_set("gemm_dbg", bits); results are WRONG when any bit is set):
   //   1 = epilogue only releases the accumulator, 2 = epilogue without its TMA stores/loads,
   //   4 = no MMAs issued, 8 = every tile loads A block 0 (no HBM reads), 16 = B tiles are not loaded,
-  //   32 = no operand loads at all (MMAs run on stale shared memory)
+  //   32 = no operand loads at all (MMAs run on stale shared memory),
+  //   64 = producer / MMA threads hot-spin on their mbarriers (mbarrier.test_wait),
+  //   128 = CTA 0 prints the MMA warp's cycles per k-block
   int dbg;
 };
 
@@ -674,99 +676,131 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // All 32 lanes run the loop converged, one elected lane issues (see elect_one_sync); the test of the NEXT
+    // stage's empty barrier is issued before this stage's loads so its latency hides behind them.
+    {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t ready = mbar_test(smem_u32(&empty_bar[0]), 1u);
       for (int item = cta_first; item < num_items; item += cta_stride) {
         const Item it = get_item(item);
         const int m0 = (p.dbg & 8) ? 0 : it.m_blk * BM;
         const int n0 = it.n_blk * BN + static_cast<int>(rank) * G::B_ROWS;   // pair: this CTA's half of B
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          if (p.dbg & 32) {                                   // no loads at all: raw MMA issue rate on stale smem
-            if (!CTA2 || rank == 0) mbar_arrive(fb_local);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            continue;
-          }
+          if (!ready) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+          const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
+          ready = mbar_test(smem_u32(&empty_bar[nstage]), nphase ^ 1u);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
           const int k0 = kb * BK;
-          if (CTA2) {
-            // all bytes of both CTAs are accounted on the LEADER's full barrier
-            const uint32_t fb = mapa_shared(fb_local, 0);
-            if (rank == 0) mbar_arrive_expect_tx(fb_local, 2 * STAGE_BYTES);
-            if (A_MN == 0) {
-              tma_load_2d_2sm(a_dst, &tmA, fb, k0, m0);
-            } else {
+          if (elect_one_sync()) {
+            if (p.dbg & 32) {                                   // no loads at all: raw MMA issue rate on stale smem
+              if (!CTA2 || rank == 0) mbar_arrive(fb_local);
+            } else if (CTA2) {
+              // all bytes of both CTAs are accounted on the LEADER's full barrier
+              const uint32_t fb = mapa_shared(fb_local, 0);
+              if (rank == 0) mbar_arrive_expect_tx(fb_local, 2 * STAGE_BYTES);
+              if (A_MN == 0) {
+                tma_load_2d_2sm(a_dst, &tmA, fb, k0, m0);
+              } else {
 #pragma unroll
-              for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
-            }
-            if (B_MN == 0) {
-              tma_load_2d_2sm(b_dst, &tmB, fb, k0, n0);
-            } else {
+                for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
+              }
+              if (B_MN == 0) {
+                tma_load_2d_2sm(b_dst, &tmB, fb, k0, n0);
+              } else {
 #pragma unroll
-              for (int c = 0; c < G::B_ROWS / 64; ++c)
-                tma_load_2d_2sm(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
-            }
-          } else {
-            const uint32_t fb = fb_local;
-            mbar_arrive_expect_tx(fb, (p.dbg & 16) ? p.a_tx : p.a_tx + p.b_tx);
-            if (A_MN == 0) {
-              tma_load_2d(a_dst, &tmA, fb, k0, m0);
+                for (int c = 0; c < G::B_ROWS / 64; ++c)
+                  tma_load_2d_2sm(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
+              }
             } else {
-              for (int c = 0; c < p.m_chunks; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
-            }
-            if (p.dbg & 16) {
-            } else if (B_MN == 0) {
-              tma_load_2d(b_dst, &tmB, fb, k0, n0);                      // box = 64 k x n_mma rows
-            } else {
-              for (int c = 0; c < p.n_chunks; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
+              const uint32_t fb = fb_local;
+              mbar_arrive_expect_tx(fb, (p.dbg & 16) ? p.a_tx : p.a_tx + p.b_tx);
+              if (A_MN == 0) {
+                tma_load_2d(a_dst, &tmA, fb, k0, m0);
+              } else {
+                for (int c = 0; c < p.m_chunks; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
+              }
+              if (p.dbg & 16) {
+              } else if (B_MN == 0) {
+                tma_load_2d(b_dst, &tmB, fb, k0, n0);                      // box = 64 k x n_mma rows
+              } else {
+                for (int c = 0; c < p.n_chunks; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + 64 * c, k0);
+              }
             }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          __syncwarp();
+          stage = nstage;
+          phase = nphase;
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {                              // pair: only the leader CTA issues MMAs
+    // All 32 lanes run this loop converged (warp-uniform control flow and operands); one elected lane issues the
+    // tcgen05 instructions.  Descriptors are a per-stage constant plus k * step in the 14-bit start-address field.
+    // Per k-block the issuing lane needs ~4 x 60 cycles for the MMAs + ~65 for the commit; a blocking wait in front
+    // (~170 cycles even when the phase is complete) would push that past the 512 cycles the tensor pipe needs, so
+    // the NEXT stage's full barrier is tested before this stage's MMAs are issued and only waited on if not ready.
+    if (rank == 0) {                                           // pair: only the leader CTA issues MMAs
       const uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, CTA2 ? BN : static_cast<uint32_t>(p.n_mma), A_MN, B_MN);
+      const uint64_t a_desc0 = umma_smem_desc(0, p.a_lbo, p.a_sbo);
+      const uint64_t b_desc0 = umma_smem_desc(0, p.b_lbo, p.b_sbo);
+      const uint32_t a_step = p.a_kstep >> 4, b_step = p.b_kstep >> 4;
+      const bool mma_off = (p.dbg & 4) != 0;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const long long t_begin = clock64();
+      long long n_kb = 0;
+      uint32_t ready = mbar_test(smem_u32(&full_bar[0]), 0u);
       for (int item = cta_first; item < num_items; item += cta_stride) {
         const Item it = get_item(item);
         mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        const bool rowsum = single_acc && it.n_blk == 0;
+        n_kb += it.kb_end - it.kb_begin;
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (!ready) mbar_wait(smem_u32(&full_bar[stage]), phase);
+          const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+          const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
+          ready = mbar_test(smem_u32(&full_bar[nstage]), nphase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint64_t ad = a_desc0 + (a_addr >> 4);
+          const uint64_t bd = b_desc0 + ((a_addr + A_BYTES) >> 4);
+          const uint32_t first = (kb > it.kb_begin) ? 1u : 0u;
+          if (elect_one_sync()) {
+            if (!mma_off) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = umma_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
-            const uint64_t bd = umma_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
-            const uint32_t acc = (kb > it.kb_begin || k > 0) ? 1u : 0u;
-            if (p.dbg & 4) continue;
-            if (CTA2) umma_bf16_ss_2sm(d_tmem, ad, bd, idesc, acc);
-            else umma_bf16_ss(d_tmem, ad, bd, idesc, acc);
-            if (single_acc && it.n_blk == 0) {
-              constexpr uint32_t idesc_ones = umma_idesc_bf16(CTA2 ? 2 * BM : BM, 16, A_MN, 1);
-              const uint64_t od = umma_smem_desc(ones_tile, CHUNK_BYTES, 1024);
-              if (CTA2) umma_bf16_ss_2sm(tmem_base + BN, ad, od, idesc_ones, acc);
-              else umma_bf16_ss(tmem_base + BN, ad, od, idesc_ones, acc);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t acc = (k > 0) ? 1u : first;
+                if (CTA2) umma_bf16_ss_2sm(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
+                else umma_bf16_ss(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
+                if (rowsum) {
+                  constexpr uint32_t idesc_ones = umma_idesc_bf16(CTA2 ? 2 * BM : BM, 16, A_MN, 1);
+                  const uint64_t od = umma_smem_desc(ones_tile, CHUNK_BYTES, 1024);
+                  if (CTA2) umma_bf16_ss_2sm(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
+                  else umma_bf16_ss(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
+                }
+              }
             }
+            // smem slot reusable (in both CTAs of a pair) when the MMAs retire
+            if (CTA2) umma_commit_2sm(smem_u32(&empty_bar[stage])); else umma_commit(smem_u32(&empty_bar[stage]));
           }
-          // smem slot reusable (in both CTAs of a pair) when the MMAs retire
-          if (CTA2) umma_commit_2sm(smem_u32(&empty_bar[stage])); else umma_commit(smem_u32(&empty_bar[stage]));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          __syncwarp();
+          stage = nstage;
+          phase = nphase;
         }
         // accumulator complete (published to both CTAs of a pair)
-        if (CTA2) umma_commit_2sm(smem_u32(&tmem_full_bar[as])); else umma_commit(smem_u32(&tmem_full_bar[as]));
+        if (elect_one_sync()) {
+          if (CTA2) umma_commit_2sm(smem_u32(&tmem_full_bar[as])); else umma_commit(smem_u32(&tmem_full_bar[as]));
+        }
+        __syncwarp();
         if (single_acc) {
           aphase ^= 1u;
         } else {
@@ -774,6 +808,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (as == 0) aphase ^= 1u;
         }
       }
+      if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0)       // issue-loop pace: 512 clk per k-block is the tensor pipe's floor
+        printf("semcom gemm: MMA warp issued %lld k-blocks in %lld clk (%.0f clk per k-block)\n", n_kb,
+               clock64() - t_begin, double(clock64() - t_begin) / double(n_kb > 0 ? n_kb : 1));
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================

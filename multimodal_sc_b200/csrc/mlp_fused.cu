@@ -197,12 +197,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   if (warp == 0) {
     // ===================== weight producer =====================
-    if (lane == 0) {
+    // converged warp, one elected lane issues the TMA loads; the next stage's empty barrier is tested ahead
+    {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t ready = mbar_test(smem_u32(&w_empty[0]), 1u);
       auto next_stage = [&]() -> uint32_t {
-        mbar_wait(smem_u32(&w_empty[stage]), phase ^ 1u);
-        mbar_arrive_expect_tx(smem_u32(&w_full[stage]), STAGE_BYTES);
+        if (!ready) mbar_wait(smem_u32(&w_empty[stage]), phase ^ 1u);
+        const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+        const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
+        ready = mbar_test(smem_u32(&w_empty[nstage]), nphase ^ 1u);
         return ring + stage * STAGE_BYTES;
       };
       auto advance = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1u; } };
@@ -210,16 +214,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int t = 0; t < 2; ++t) {
           const uint32_t dst = next_stage();
           const uint32_t fb = smem_u32(&w_full[stage]);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(fb, STAGE_BYTES);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int kb = 2 * t + u;
-            if (!BWD) {                                     // W1 [R, 256] K-major: 128 hidden rows x 64 k
-              tma_load_2d(dst + u * KB_BYTES, &tmWa, fb, kb * 64, j * HC);
-            } else {                                        // W2 [256, R] read MN-major: 64 k-rows x (2 x 64) hidden columns
-              tma_load_2d(dst + u * KB_BYTES, &tmWa, fb, j * HC, kb * 64);
-              tma_load_2d(dst + u * KB_BYTES + CHUNK8K, &tmWa, fb, j * HC + 64, kb * 64);
+            for (int u = 0; u < 2; ++u) {
+              const int kb = 2 * t + u;
+              if (!BWD) {                                   // W1 [R, 256] K-major: 128 hidden rows x 64 k
+                tma_load_2d(dst + u * KB_BYTES, &tmWa, fb, kb * 64, j * HC);
+              } else {                                      // W2 [256, R] read MN-major: 64 k-rows x (2 x 64) hidden columns
+                tma_load_2d(dst + u * KB_BYTES, &tmWa, fb, j * HC, kb * 64);
+                tma_load_2d(dst + u * KB_BYTES + CHUNK8K, &tmWa, fb, j * HC + 64, kb * 64);
+              }
             }
           }
+          __syncwarp();
           advance();
         }
       };
@@ -228,12 +236,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const uint32_t dst = next_stage();
           const uint32_t fb = smem_u32(&w_full[stage]);
           const int k0 = j * HC + t * 64;
-          if (!BWD) {                                       // W2 [256, R] K-major: 256 rows x 64 k
-            tma_load_2d(dst, &tmWb, fb, k0, 0);
-          } else {                                          // W1 [R, 256] read MN-major: 64 k-rows x (4 x 64) columns
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(fb, STAGE_BYTES);
+            if (!BWD) {                                     // W2 [256, R] K-major: 256 rows x 64 k
+              tma_load_2d(dst, &tmWb, fb, k0, 0);
+            } else {                                        // W1 [R, 256] read MN-major: 64 k-rows x (4 x 64) columns
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * CHUNK8K, &tmWb, fb, 64 * c, k0);
+              for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * CHUNK8K, &tmWb, fb, 64 * c, k0);
+            }
           }
+          __syncwarp();
           advance();
         }
       };
@@ -274,15 +286,30 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // All 32 lanes run the loop converged; one elected lane issues (elect_one_sync): inside `if (lane == 0)` ptxas
+    // wraps every UTCHMMA in an R2UR/ELECT waterfall of ~48 instructions, more than the 66 cycles a 128x128x16 MMA
+    // takes.  The weight stage that is needed NEXT is tested before the current stage's MMAs are issued, so the
+    // barrier round trip hides behind them.
+    {
       constexpr uint32_t idesc1 = umma_idesc_bf16(BM, HC, 0, BWD ? 1 : 0);
       constexpr uint32_t idesc2 = umma_idesc_bf16(BM, DM, 0, BWD ? 1 : 0);
       constexpr uint32_t b_lbo = BWD ? CHUNK8K : 16;
-      constexpr uint32_t b_kstep = BWD ? 2048 : 32;
+      constexpr uint32_t b_kstep16 = (BWD ? 2048 : 32) >> 4;
+      const uint64_t a_desc0 = umma_smem_desc(0, 16, 1024);
+      const uint64_t b_desc0 = umma_smem_desc(0, b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t n1[2] = {0u, 0u}, nh[2] = {0u, 0u};
       uint32_t t_par = 0;
+      uint32_t ready = mbar_test(smem_u32(&w_full[0]), 0u);
+      // wait for the current weight stage (tested one step ahead), test the next one, return the stage's address
+      auto acquire_stage = [&]() -> uint32_t {
+        if (!ready) mbar_wait(smem_u32(&w_full[stage]), phase);
+        const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+        const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
+        ready = mbar_test(smem_u32(&w_full[nstage]), nphase);
+        return ring + stage * STAGE_BYTES;
+      };
       auto advance = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1u; } };
       auto gemm1 = [&](int j) {
         const int b = j & 1;
@@ -291,23 +318,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * HC);
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(smem_u32(&w_full[stage]), phase);
+          const uint32_t wb = acquire_stage();
           tc_fence_after();
-          const uint32_t wb = ring + stage * STAGE_BYTES;
+          const uint64_t ad = a_desc0 + ((xa + 2 * t * KB_BYTES) >> 4);
+          const uint64_t bd = b_desc0 + (wb >> 4);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int kb = 2 * t + u;
+            for (int u = 0; u < 2; ++u) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = umma_smem_desc(xa + kb * KB_BYTES + k * 32, 16, 1024);
-              const uint64_t bd = umma_smem_desc(wb + u * KB_BYTES + k * b_kstep, b_lbo, 1024);
-              umma_bf16_ss(d_tmem, ad, bd, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(d_tmem, ad + u * (KB_BYTES >> 4) + k * 2, bd + u * (KB_BYTES >> 4) + k * b_kstep16, idesc1,
+                             (t > 0 || u > 0 || k > 0) ? 1u : 0u);
             }
+            umma_commit(smem_u32(&w_empty[stage]));
           }
-          umma_commit(smem_u32(&w_empty[stage]));
+          __syncwarp();
           advance();
         }
-        umma_commit(smem_u32(&acc1_full[b]));
+        if (elect_one_sync()) {
+          umma_commit(smem_u32(&acc1_full[b]));
+          if (j == NC - 1) umma_commit(smem_u32(&x_empty));             // x tile free once the last GEMM1 retires
+        }
+        __syncwarp();
       };
       auto gemm2 = [&](int j) {
         const int b = j & 1;
@@ -317,30 +349,32 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ACC2_COL;
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(smem_u32(&w_full[stage]), phase);
+          const uint32_t wb = acquire_stage();
           tc_fence_after();
-          const uint32_t wb = ring + stage * STAGE_BYTES;
+          const uint64_t ad = a_desc0 + ((hb(b) + t * KB_BYTES) >> 4);
+          const uint64_t bd = b_desc0 + (wb >> 4);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_smem_desc(hb(b) + t * KB_BYTES + k * 32, 16, 1024);
-            const uint64_t bd = umma_smem_desc(wb + k * b_kstep, b_lbo, 1024);
-            umma_bf16_ss(d_tmem, ad, bd, idesc2, (j > 0 || t > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(d_tmem, ad + k * 2, bd + k * b_kstep16, idesc2, (j > 0 || t > 0 || k > 0) ? 1u : 0u);
+            umma_commit(smem_u32(&w_empty[stage]));
           }
-          umma_commit(smem_u32(&w_empty[stage]));
+          __syncwarp();
           advance();
         }
-        umma_commit(smem_u32(&h_empty[b]));
+        if (elect_one_sync()) umma_commit(smem_u32(&h_empty[b]));
+        __syncwarp();
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, t_par ^= 1u) {
         mbar_wait(smem_u32(&x_full), t_par);
         tc_fence_after();
         for (int j = 0; j < NC; ++j) {
           gemm1(j);
-          if (j == NC - 1) umma_commit(smem_u32(&x_empty));             // x tile free once the last GEMM1 retires
           if (j >= 1) gemm2(j - 1);
         }
         gemm2(NC - 1);
-        umma_commit(smem_u32(&acc2_full));
+        if (elect_one_sync()) umma_commit(smem_u32(&acc2_full));
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

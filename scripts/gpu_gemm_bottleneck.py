@@ -53,6 +53,9 @@ def make(shape_name):
     if shape_name == "inproj":     # decoder input projection: K = 16
         return dict(M=2 * M, N=256, K=16, A=lambda: g(2 * M, 16), B=g(256, 16),
                     kw=lambda: dict(bias=torch.zeros(256, device="cuda")))
+    if shape_name in ("wgrad_fc1", "wgrad_fc2", "wgrad_qkv"):   # dW[n_out, k_in] += dy^T x, split-K over the tokens, fp32 atomics
+        n_out, k_in = {"wgrad_fc1": (1024, 256), "wgrad_fc2": (256, 1024), "wgrad_qkv": (768, 256)}[shape_name]
+        return dict(M=n_out, N=k_in, K=M, A=lambda: g(M, n_out), B=g(M, k_in), wgrad=True, kw=lambda: dict())
     if shape_name == "big":
         return dict(M=8192, N=8192, K=8192, A=lambda: g(8192, 8192), B=g(8192, 8192), kw=lambda: dict())
     if shape_name == "plain256":
@@ -67,13 +70,17 @@ def time_case(spec, dbg, nwg, iters=12, slots=0, cta2=0):
     ops.debug_set("nwg", nwg)
     ops.debug_set("slots", slots)
     sets = []
+    wg_out = torch.zeros(spec["M"], spec["N"], device="cuda") if spec.get("wgrad") else None
     for _ in range(SETS):
         kw = spec["kw"]()
-        sets.append((spec["A"](), kw, torch.empty(spec["M"], spec["N"], device="cuda",
-                                                     dtype=torch.float32 if spec.get("f32") else BF16)))
+        sets.append((spec["A"](), kw, None if spec.get("wgrad") else
+                     torch.empty(spec["M"], spec["N"], device="cuda", dtype=torch.float32 if spec.get("f32") else BF16)))
     def run(i):
         A, kw, out = sets[i % SETS]
-        if spec.get("f32"):
+        if spec.get("wgrad"):
+            tiles = ((spec["M"] + 127) // 128) * ((spec["N"] + 255) // 256)
+            ops.gemm(A, spec["B"], a_mn=True, b_mn=True, out_f32=wg_out, atomic=True, ksplit=max(1, 148 // tiles))
+        elif spec.get("f32"):
             ops.gemm(A, spec["B"], b_mn=spec.get("b_mn", False), out_f32=out, **kw)
         else:
             ops.gemm(A, spec["B"], b_mn=spec.get("b_mn", False), out=out, **kw)
@@ -101,13 +108,15 @@ def main():
         names = ("fc2", "qkv", "fc1", "big")
     if os.environ.get("SC_BOTTLENECK_SKINNY"):
         names = ("sym", "dsym", "inproj", "plain256")
+    if os.environ.get("SC_BOTTLENECK_WGRAD"):
+        names = ("wgrad_fc1", "wgrad_fc2", "wgrad_qkv", "fc2")
     for name in names:
         spec = make(name)
         rec = {}
         if os.environ.get("SC_BOTTLENECK_MMA"):
             # raw tensor-pipe rate: no loads, no epilogue work (bits 32 | 1), single CTA per tile and CTA pairs
             for cta2 in (0, 1):
-                for vn, bits in (("mma_only", 33), ("loads+mma", 1), ("full", 0)):
+                for vn, bits in (("mma_only", 33), ("loads+mma", 1), ("full", 0), ("spin.mma_only", 97), ("spin.loads+mma", 65), ("spin.full", 64)):
                     ops.debug_set("reset", 0)
                     try:
                         rec[f"cta2={cta2}.{vn}"] = round(time_case(spec, bits, 1, slots=2, cta2=cta2), 1)
@@ -118,7 +127,7 @@ def main():
             out[name] = rec
             print(name, json.dumps(rec), flush=True)
             continue
-        if os.environ.get("SC_BOTTLENECK_SKINNY"):
+        if os.environ.get("SC_BOTTLENECK_SKINNY") or os.environ.get("SC_BOTTLENECK_WGRAD"):
             for vn, bits in (("full", 0), ("epi_skip", 1), ("no_mma", 4), ("no_b", 16), ("epi_skip+no_b", 17), ("epi_skip+no_mma", 5),
                              ("loads_off", 32), ("loads_off+epi_skip", 33)):
                 try:
