@@ -300,6 +300,60 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One k-block for the single-CTA MMA issuer in ONE asm block: the non-blocking test of the NEXT stage's full barrier
+// is issued first, then the four K=16 MMAs of this stage and the commit that frees its shared-memory slot; the
+// predicate is only turned into a register at the end, so the ~150-cycle SYNCS round trip overlaps the MMA issue
+// instead of stalling the loop.  Returns 1 when the next stage has already landed.
+#define SC_UMMA4_BODY                                                         \
+  "setp.ne.b32 p, %7, 0;\n\t"                                                  \
+  "setp.eq.b32 t, 0, 0;\n\t"                                                   \
+  "cvt.u64.u32 sa, %4;\n\t"                                                    \
+  "cvt.u64.u32 sb, %5;\n\t"                                                    \
+  "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %6, p;\n\t"                \
+  "add.u64 a, %2, sa;\n\t"                                                     \
+  "add.u64 b, %3, sb;\n\t"                                                     \
+  "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %6, t;\n\t"                  \
+  "add.u64 a, a, sa;\n\t"                                                      \
+  "add.u64 b, b, sb;\n\t"                                                      \
+  "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %6, t;\n\t"                  \
+  "add.u64 a, a, sa;\n\t"                                                      \
+  "add.u64 b, b, sb;\n\t"                                                      \
+  "tcgen05.mma.cta_group::1.kind::f16 [%1], a, b, %6, t;\n\t"
+#define SC_UMMA4_OPERANDS                                                                                       \
+  "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(a_step), "r"(b_step), "r"(idesc), "r"(accumulate_first),          \
+      "r"(commit_bar), "r"(next_bar), "r"(next_parity)
+// kTest: test `next_bar` ahead of the MMAs (result returned); kCommit: commit to `commit_bar` after them.  Stages of
+// more than four MMAs chain a <true,false> block with a <false,true> block.
+template <bool kTest = true, bool kCommit = true>
+__device__ __forceinline__ uint32_t umma_kblock4_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t a_step,
+                                                         uint32_t b_step, uint32_t idesc, uint32_t accumulate_first,
+                                                         uint32_t commit_bar, uint32_t next_bar, uint32_t next_parity) {
+  uint32_t ready = 0;
+  if (kTest && kCommit) {
+    asm volatile("{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b, sa, sb;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t" SC_UMMA4_BODY
+                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+                 "selp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
+  } else if (kTest) {
+    asm volatile("{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b, sa, sb;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t" SC_UMMA4_BODY
+                 "selp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
+  } else if (kCommit) {
+    asm volatile("{\n\t.reg .pred p, t;\n\t.reg .b64 a, b, sa, sb;\n\t" SC_UMMA4_BODY
+                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+                 "mov.u32 %0, 0;\n\t}"
+                 : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p, t;\n\t.reg .b64 a, b, sa, sb;\n\t" SC_UMMA4_BODY
+                 "mov.u32 %0, 0;\n\t}"
+                 : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
+  }
+  return ready;
+}
+#undef SC_UMMA4_BODY
+#undef SC_UMMA4_OPERANDS
 // all prior tcgen05.mma of this thread arrive on `bar` when complete (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

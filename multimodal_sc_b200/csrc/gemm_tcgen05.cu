@@ -768,31 +768,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (!ready) mbar_wait(smem_u32(&full_bar[stage]), phase);
           const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
           const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
-          ready = mbar_test(smem_u32(&full_bar[nstage]), nphase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
           const uint64_t ad = a_desc0 + (a_addr >> 4);
           const uint64_t bd = b_desc0 + ((a_addr + A_BYTES) >> 4);
           const uint32_t first = (kb > it.kb_begin) ? 1u : 0u;
-          if (elect_one_sync()) {
-            if (!mma_off) {
+          if (!CTA2 && !rowsum && !mma_off) {
+            // common case: test of the next stage, four MMAs and the commit in one asm block (see common.cuh)
+            uint32_t r = 0;
+            if (elect_one_sync())
+              r = umma_kblock4_bf16_ss(d_tmem, ad, bd, a_step, b_step, idesc, first, smem_u32(&empty_bar[stage]),
+                                       smem_u32(&full_bar[nstage]), nphase);
+            ready = __shfl_sync(0xffffffffu, r, 0);            // elect.sync picks lane 0 of the converged warp
+          } else {
+            ready = mbar_test(smem_u32(&full_bar[nstage]), nphase);
+            if (elect_one_sync()) {
+              if (!mma_off) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint32_t acc = (k > 0) ? 1u : first;
-                if (CTA2) umma_bf16_ss_2sm(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
-                else umma_bf16_ss(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
-                if (rowsum) {
-                  constexpr uint32_t idesc_ones = umma_idesc_bf16(CTA2 ? 2 * BM : BM, 16, A_MN, 1);
-                  const uint64_t od = umma_smem_desc(ones_tile, CHUNK_BYTES, 1024);
-                  if (CTA2) umma_bf16_ss_2sm(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
-                  else umma_bf16_ss(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint32_t acc = (k > 0) ? 1u : first;
+                  if (CTA2) umma_bf16_ss_2sm(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
+                  else umma_bf16_ss(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
+                  if (rowsum) {
+                    constexpr uint32_t idesc_ones = umma_idesc_bf16(CTA2 ? 2 * BM : BM, 16, A_MN, 1);
+                    const uint64_t od = umma_smem_desc(ones_tile, CHUNK_BYTES, 1024);
+                    if (CTA2) umma_bf16_ss_2sm(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
+                    else umma_bf16_ss(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
+                  }
                 }
               }
+              // smem slot reusable (in both CTAs of a pair) when the MMAs retire
+              if (CTA2) umma_commit_2sm(smem_u32(&empty_bar[stage])); else umma_commit(smem_u32(&empty_bar[stage]));
             }
-            // smem slot reusable (in both CTAs of a pair) when the MMAs retire
-            if (CTA2) umma_commit_2sm(smem_u32(&empty_bar[stage])); else umma_commit(smem_u32(&empty_bar[stage]));
+            __syncwarp();
           }
-          __syncwarp();
           stage = nstage;
           phase = nphase;
         }

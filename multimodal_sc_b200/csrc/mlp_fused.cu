@@ -302,15 +302,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       uint32_t n1[2] = {0u, 0u}, nh[2] = {0u, 0u};
       uint32_t t_par = 0;
       uint32_t ready = mbar_test(smem_u32(&w_full[0]), 0u);
-      // wait for the current weight stage (tested one step ahead), test the next one, return the stage's address
+      int nstage = 0;
+      uint32_t nphase = 0;
+      // wait for the current weight stage (it was tested one stage ahead); note which stage comes next
       auto acquire_stage = [&]() -> uint32_t {
         if (!ready) mbar_wait(smem_u32(&w_full[stage]), phase);
-        const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
-        const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
-        ready = mbar_test(smem_u32(&w_full[nstage]), nphase);
+        nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+        nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
         return ring + stage * STAGE_BYTES;
       };
-      auto advance = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1u; } };
+      auto advance = [&]() { stage = nstage; phase = nphase; };
       auto gemm1 = [&](int j) {
         const int b = j & 1;
         mbar_wait(smem_u32(&acc1_empty[b]), (n1[b] & 1u) ^ 1u);
@@ -322,17 +323,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tc_fence_after();
           const uint64_t ad = a_desc0 + ((xa + 2 * t * KB_BYTES) >> 4);
           const uint64_t bd = b_desc0 + (wb >> 4);
+          uint32_t r = 0;
           if (elect_one_sync()) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ss(d_tmem, ad + u * (KB_BYTES >> 4) + k * 2, bd + u * (KB_BYTES >> 4) + k * b_kstep16, idesc1,
-                             (t > 0 || u > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(smem_u32(&w_empty[stage]));
+            // eight 128x128x16 MMAs: the next weight stage is tested ahead of the first four, the commit follows the last
+            r = umma_kblock4_bf16_ss<true, false>(d_tmem, ad, bd, 2u, b_kstep16, idesc1, t > 0 ? 1u : 0u,
+                                                  smem_u32(&w_empty[stage]), smem_u32(&w_full[nstage]), nphase);
+            umma_kblock4_bf16_ss<false, true>(d_tmem, ad + (KB_BYTES >> 4), bd + (KB_BYTES >> 4), 2u, b_kstep16, idesc1, 1u,
+                                              smem_u32(&w_empty[stage]), 0u, 0u);
           }
-          __syncwarp();
+          ready = __shfl_sync(0xffffffffu, r, 0);
           advance();
         }
         if (elect_one_sync()) {
@@ -353,13 +352,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tc_fence_after();
           const uint64_t ad = a_desc0 + ((hb(b) + t * KB_BYTES) >> 4);
           const uint64_t bd = b_desc0 + (wb >> 4);
-          if (elect_one_sync()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(d_tmem, ad + k * 2, bd + k * b_kstep16, idesc2, (j > 0 || t > 0 || k > 0) ? 1u : 0u);
-            umma_commit(smem_u32(&w_empty[stage]));
-          }
-          __syncwarp();
+          uint32_t r = 0;
+          if (elect_one_sync())
+            r = umma_kblock4_bf16_ss<true, true>(d_tmem, ad, bd, 2u, b_kstep16, idesc2, (j > 0 || t > 0) ? 1u : 0u,
+                                                 smem_u32(&w_empty[stage]), smem_u32(&w_full[nstage]), nphase);
+          ready = __shfl_sync(0xffffffffu, r, 0);
           advance();
         }
         if (elect_one_sync()) umma_commit(smem_u32(&h_empty[b]));
