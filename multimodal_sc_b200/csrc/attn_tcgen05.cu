@@ -97,38 +97,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tm_s = tmem, tm_o = tmem + 128;
   const int HD = p.H * 64;
 
+  // The two single-thread roles run their loops with the whole warp converged and let one elected lane issue
+  // (elect_one_sync, common.cuh): inside `if (lane == 0)` ptxas wraps each UTCHMMA / UTMALDG in an R2UR + ELECT
+  // waterfall of ~48 instructions, longer than the 66-cycle MMAs issued here.
   if (warp == 0) {
-    if (lane == 0) {
-      int n = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-        const int stage = n % STAGES;
-        const uint32_t ph = (n / STAGES) & 1;
-        const int h = item % p.H, row0 = (item / p.H) * 128;
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
+    int n = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
+      const int stage = n % STAGES;
+      const uint32_t ph = (n / STAGES) & 1;
+      const int h = item % p.H, row0 = (item / p.H) * 128;
+      const uint32_t fb = smem_u32(&full_bar[stage]);
+      mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
+      const uint32_t dst = smem + stage * kFwdStage;
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(fb, kFwdStage);
-        const uint32_t dst = smem + stage * kFwdStage;
         tma_load_2d(dst, &tmQKV, fb, h * 64, row0);
         tma_load_2d(dst + kTile, &tmQKV, fb, HD + h * 64, row0);
         tma_load_2d(dst + 2 * kTile, &tmQKV, fb, 2 * HD + h * 64, row0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-      int n = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-        const int stage = n % STAGES;
-        const uint32_t st = smem + stage * kFwdStage;
-        if (n == 0) {
-          mbar_wait(smem_u32(&full_bar[0]), 0);
-          tc_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+    int n = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
+      const int stage = n % STAGES;
+      const uint32_t st = smem + stage * kFwdStage;
+      if (n == 0) {
+        mbar_wait(smem_u32(&full_bar[0]), 0);
+        tc_fence_after();
+        if (elect_one_sync()) {
           mma_kk_64(tm_s, st, st + kTile, idesc_s, false);
           umma_commit(smem_u32(&s_full));
         }
-        mbar_wait(smem_u32(&p_full), n & 1);
-        tc_fence_after();
+        __syncwarp();
+      }
+      mbar_wait(smem_u32(&p_full), n & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
         // O = P V : A = P (K-major, two 64-key blocks), B = V tile [keys x d] as MN-major (N = d)
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -136,14 +143,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                        umma_smem_desc(st + 2 * kTile + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
         umma_commit(smem_u32(&o_full));
         umma_commit(smem_u32(&empty_bar[stage]));
-        if (item + static_cast<int>(gridDim.x) < p.num_items) {
-          const int ns = (n + 1) % STAGES;
-          const uint32_t nst = smem + ns * kFwdStage;
-          mbar_wait(smem_u32(&full_bar[ns]), ((n + 1) / STAGES) & 1);
-          tc_fence_after();
+      }
+      __syncwarp();
+      if (item + static_cast<int>(gridDim.x) < p.num_items) {
+        const int ns = (n + 1) % STAGES;
+        const uint32_t nst = smem + ns * kFwdStage;
+        mbar_wait(smem_u32(&full_bar[ns]), ((n + 1) / STAGES) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
           mma_kk_64(tm_s, nst, nst + kTile, idesc_s, false);
           umma_commit(smem_u32(&s_full));
         }
+        __syncwarp();
       }
     }
   } else {
@@ -273,42 +284,47 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
   const int HD = p.H * 64;
 
+  // single-thread roles: converged warp + one elected lane (see the forward kernel)
   if (warp == 0) {
-    if (lane == 0) {
-      int n = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-        const int stage = n & 1;
-        const uint32_t ph = (n >> 1) & 1;
-        const int h = item % p.H, row0 = (item / p.H) * 128;
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
+    int n = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
+      const int stage = n & 1;
+      const uint32_t ph = (n >> 1) & 1;
+      const int h = item % p.H, row0 = (item / p.H) * 128;
+      const uint32_t fb = smem_u32(&full_bar[stage]);
+      mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
+      const uint32_t dst = smem + stage * kBwdStage;
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(fb, kBwdStage);
-        const uint32_t dst = smem + stage * kBwdStage;
         tma_load_2d(dst, &tmQKV, fb, h * 64, row0);
         tma_load_2d(dst + kTile, &tmQKV, fb, HD + h * 64, row0);
         tma_load_2d(dst + 2 * kTile, &tmQKV, fb, 2 * HD + h * 64, row0);
         tma_load_2d(dst + 3 * kTile, &tmDO, fb, h * 64, row0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);     // A^T from P/dS (MN-major), B MN-major
-      constexpr uint32_t idesc_kt = umma_idesc_bf16(128, 64, 0, 1);     // A K-major, B MN-major
-      int n = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-        const int stage = n & 1;
-        const uint32_t st = smem + stage * kBwdStage;
-        const uint32_t sQ = st, sK = st + kTile, sV = st + 2 * kTile, sDO = st + 3 * kTile;
-        if (n == 0) {
-          mbar_wait(smem_u32(&full_bar[0]), 0);
-          tc_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);     // A^T from P/dS (MN-major), B MN-major
+    constexpr uint32_t idesc_kt = umma_idesc_bf16(128, 64, 0, 1);     // A K-major, B MN-major
+    int n = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
+      const int stage = n & 1;
+      const uint32_t st = smem + stage * kBwdStage;
+      const uint32_t sQ = st, sK = st + kTile, sV = st + 2 * kTile, sDO = st + 3 * kTile;
+      if (n == 0) {
+        mbar_wait(smem_u32(&full_bar[0]), 0);
+        tc_fence_after();
+        if (elect_one_sync()) {
           mma_kk_64(tm_s, sQ, sK, idesc_s, false);            // S  = Q K^T
           mma_kk_64(tm_dp, sDO, sV, idesc_s, false);          // dP = dO V^T
           umma_commit(smem_u32(&sdp_full));
         }
-        mbar_wait(smem_u32(&ds_full), n & 1);
-        tc_fence_after();
+        __syncwarp();
+      }
+      mbar_wait(smem_u32(&ds_full), n & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // dV[key, d] = sum_q P[q, key] dO[q, d] : A = P^T (MN-major: M = keys, 2 chunks of 64, K = queries)
@@ -329,15 +345,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         umma_commit(smem_u32(&grads_full));
         umma_commit(smem_u32(&empty_bar[stage]));
-        if (item + static_cast<int>(gridDim.x) < p.num_items) {
-          const int ns = (n + 1) & 1;
-          const uint32_t nst = smem + ns * kBwdStage;
-          mbar_wait(smem_u32(&full_bar[ns]), ((n + 1) >> 1) & 1);
-          tc_fence_after();
+      }
+      __syncwarp();
+      if (item + static_cast<int>(gridDim.x) < p.num_items) {
+        const int ns = (n + 1) & 1;
+        const uint32_t nst = smem + ns * kBwdStage;
+        mbar_wait(smem_u32(&full_bar[ns]), ((n + 1) >> 1) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
           mma_kk_64(tm_s, nst, nst + kTile, idesc_s, false);
           mma_kk_64(tm_dp, nst + 3 * kTile, nst + 2 * kTile, idesc_s, false);
           umma_commit(smem_u32(&sdp_full));
         }
+        __syncwarp();
       }
     }
   } else {
