@@ -169,12 +169,12 @@ int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f3
                          int64_t y_sb, int64_t y_sm, float* scale, int64_t B, int k, int kind,
                          const float* snr_db, float snr_db_scalar, uint64_t seed,
                          int64_t sample_offset, const float* noise, const float* fading,
-                         float eps, void* stream);
+                         float eps, const uint64_t* seed_dev, void* stream);
 /* dz = scale * (g - zn * mean(g * zn)),  g = dy (AWGN/none) or |h|^2/(|h|^2+sigma^2) dy (Rayleigh) */
 int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const float* z, int64_t z_sb,
                          int64_t z_sm, const float* scale, float* dz_f32, void* dz_bf16, int64_t B,
                          int k, int kind, const float* snr_db, float snr_db_scalar, uint64_t seed,
-                         int64_t sample_offset, const float* fading, void* stream);
+                         int64_t sample_offset, const float* fading, const uint64_t* seed_dev, void* stream);
 /* raw Philox words for parity tests: out u32 [n_quads,4], counters quad_offset.. */
 int sc_philox_words(uint32_t* out, int64_t n_quads, uint32_t stream_id, uint64_t seed,
                     int64_t quad_offset, void* stream);
@@ -222,8 +222,12 @@ int sc_ppo_loss(const float* head_out, int ld, const int64_t* actions, const flo
 
 /* a10: fused Adam over the flat parameter bucket; also refreshes the bf16 shadow copy.
  * g is multiplied by grad_scale (1/world_size) first. step >= 1. */
+/* step_dev (optional, device int64): the effective step is step + *step_dev, read in the kernel, so a captured CUDA
+ * graph advances the bias correction on every replay.  seed_dev of the channel kernels works the same way: the
+ * Philox key is seed + *seed_dev. */
 int sc_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
-                 float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
+                 float beta1, float beta2, float eps, int64_t step, float grad_scale, const int64_t* step_dev,
+                 void* stream);
 
 int sc_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 

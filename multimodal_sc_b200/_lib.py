@@ -67,9 +67,9 @@ _PROTOS = {
     "sc_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_colsum_bf16": [_P, _P, _I64, _I, _I64, _P],
     "sc_pnorm_channel_fwd": [_P, _I64, _I64, _P, _P, _I64, _I64, _P, _I64, _I, _I, _P, _F, _U64, _I64,
-                             _P, _P, _F, _P],
+                             _P, _P, _F, _P, _P],
     "sc_pnorm_channel_bwd": [_P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I64, _I, _I, _P, _F, _U64,
-                             _I64, _P, _P],
+                             _I64, _P, _P, _P],
     "sc_philox_words": [_P, _I64, _U32, _U64, _I64, _P],
     "sc_meanpool_fwd": [_P, _P, _P, _I64, _I, _I, _P],
     "sc_mse_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _I64, _F, _F, _P],
@@ -79,7 +79,7 @@ _PROTOS = {
     "sc_gae": [_P, _P, _P, _P, _P, _P, _P, _I, _I64, _F, _F, _P],
     "sc_adv_normalize": [_P, _P, _I64, _I64, _F, _P],
     "sc_ppo_loss": [_P, _I, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _F, _F, _F, _P],
-    "sc_adam_flat": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P],
+    "sc_adam_flat": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P, _P],
     "sc_cast_f32_bf16": [_P, _P, _I64, _P],
 }
 _RESTYPES = {"sc_last_error": C.c_char_p, "sc_launch_count": C.c_int64}

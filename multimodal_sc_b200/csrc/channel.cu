@@ -73,10 +73,19 @@ struct ChanArgs {
   int64_t B; int k; int kind;
   const float* snr_db; float snr_db_scalar;
   uint32_t key0, key1; int64_t sample_offset;
+  const uint64_t* seed_dev;                                 // optional device-side addend to the seed (CUDA-graph replays)
   const float* noise; const float* fading;
   float eps;
 };
 
+// Philox key of this launch: the by-value seed plus an optional device-side counter, so a captured graph draws fresh
+// noise on every replay (the counter is bumped by a kernel inside the graph)
+template <typename Args>
+__device__ __forceinline__ uint2 chan_key(const Args& a) {
+  uint64_t seed = (static_cast<uint64_t>(a.key1) << 32) | a.key0;
+  if (a.seed_dev) seed += *a.seed_dev;
+  return make_uint2(static_cast<uint32_t>(seed & 0xffffffffu), static_cast<uint32_t>(seed >> 32));
+}
 __device__ __forceinline__ float sigma_of(const float* snr_db, float snr_scalar, int64_t b) {
   const float s = snr_db ? snr_db[b] : snr_scalar;
   return exp10f(-s * 0.05f);
@@ -93,6 +102,7 @@ __device__ __forceinline__ float2 fading_of(const float* fading, int64_t b, int 
 
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_fwd_kernel(const ChanArgs a) {
+  const uint2 key = chan_key(a);
   __shared__ float sh[kThreads / 32];
   const int nv = a.k / 4;                                    // float4 per row
   for (int64_t row = blockIdx.x; row < a.B * 2; row += gridDim.x) {
@@ -115,7 +125,7 @@ pnorm_channel_fwd_kernel(const ChanArgs a) {
     float sigma = 0.f, hr = 1.f, hi = 0.f, inv_den = 1.f;
     if (a.kind != SC_CH_NONE) sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
     if (a.kind == SC_CH_RAYLEIGH) {
-      const float2 h = fading_of(a.fading, b, m, a.sample_offset, a.key0, a.key1);
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y);
       hr = h.x; hi = h.y;
       inv_den = 1.0f / (hr * hr + hi * hi + sigma * sigma);
     }
@@ -131,7 +141,7 @@ pnorm_channel_fwd_kernel(const ChanArgs a) {
         if (a.kind != SC_CH_NONE) {
           float4 n;
           if (a.noise) n = *reinterpret_cast<const float4*>(a.noise + row * a.k + q * 4);
-          else n = normal4(quad0 + q, 0u, a.key0, a.key1);
+          else n = normal4(quad0 + q, 0u, key.x, key.y);
           if (a.kind == SC_CH_AWGN) {
             o = make_float4(fmaf(sigma, n.x, s.x), fmaf(sigma, n.y, s.y), fmaf(sigma, n.z, s.z), fmaf(sigma, n.w, s.w));
           } else {
@@ -157,11 +167,13 @@ struct ChanBwdArgs {
   int64_t B; int k; int kind;
   const float* snr_db; float snr_db_scalar;
   uint32_t key0, key1; int64_t sample_offset;
+  const uint64_t* seed_dev;
   const float* fading;
 };
 
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_bwd_kernel(const ChanBwdArgs a) {
+  const uint2 key = chan_key(a);
   __shared__ float sh[kThreads / 32];
   const int nv = a.k / 4;
   for (int64_t row = blockIdx.x; row < a.B * 2; row += gridDim.x) {
@@ -173,7 +185,7 @@ pnorm_channel_bwd_kernel(const ChanBwdArgs a) {
     float gain = 1.f;
     if (a.kind == SC_CH_RAYLEIGH) {
       const float sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
-      const float2 h = fading_of(a.fading, b, m, a.sample_offset, a.key0, a.key1);
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y);
       const float h2 = h.x * h.x + h.y * h.y;
       gain = h2 / (h2 + sigma * sigma);
     }
@@ -225,6 +237,7 @@ constexpr int kWarpV = 16;                    // float4 per lane -> k <= 2048
 template <int NV>
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
+  const uint2 key = chan_key(a);
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -249,7 +262,7 @@ pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
     float sigma = 0.f, hr = 1.f, hi = 0.f, inv_den = 1.f;
     if (a.kind != SC_CH_NONE) sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
     if (a.kind == SC_CH_RAYLEIGH) {
-      const float2 h = fading_of(a.fading, b, m, a.sample_offset, a.key0, a.key1);
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y);
       hr = h.x; hi = h.y;
       inv_den = 1.0f / (hr * hr + hi * hi + sigma * sigma);
     }
@@ -265,7 +278,7 @@ pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
         if (a.kind != SC_CH_NONE) {
           float4 n;
           if (a.noise) n = *reinterpret_cast<const float4*>(a.noise + row * a.k + q * 4);
-          else n = normal4(quad0 + q, 0u, a.key0, a.key1);
+          else n = normal4(quad0 + q, 0u, key.x, key.y);
           if (a.kind == SC_CH_AWGN) {
             o = make_float4(fmaf(sigma, n.x, s.x), fmaf(sigma, n.y, s.y), fmaf(sigma, n.z, s.z), fmaf(sigma, n.w, s.w));
           } else {
@@ -285,6 +298,7 @@ pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
 template <int NV>
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_bwd_warp_kernel(const ChanBwdArgs a) {
+  const uint2 key = chan_key(a);
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -298,7 +312,7 @@ pnorm_channel_bwd_warp_kernel(const ChanBwdArgs a) {
     float gain = 1.f;
     if (a.kind == SC_CH_RAYLEIGH) {
       const float sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
-      const float2 h = fading_of(a.fading, b, m, a.sample_offset, a.key0, a.key1);
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y);
       const float h2 = h.x * h.x + h.y * h.y;
       gain = h2 / (h2 + sigma * sigma);
     }
@@ -346,7 +360,7 @@ extern "C" {
 int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f32, void* y_bf16, int64_t y_sb,
                          int64_t y_sm, float* scale, int64_t B, int k, int kind, const float* snr_db,
                          float snr_db_scalar, uint64_t seed, int64_t sample_offset, const float* noise,
-                         const float* fading, float eps, void* stream) {
+                         const float* fading, float eps, const uint64_t* seed_dev, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(z && (y_f32 || y_bf16), SC_E_SHAPE, "sc_pnorm_channel_fwd: null pointer");
@@ -361,7 +375,7 @@ int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f3
   a.scale = scale; a.B = B; a.k = k; a.kind = kind;
   a.snr_db = snr_db; a.snr_db_scalar = snr_db_scalar;
   a.key0 = (uint32_t)(seed & 0xffffffffu); a.key1 = (uint32_t)(seed >> 32);
-  a.sample_offset = sample_offset; a.noise = noise; a.fading = fading; a.eps = eps;
+  a.sample_offset = sample_offset; a.noise = noise; a.fading = fading; a.eps = eps; a.seed_dev = seed_dev;
   const int64_t rows = B * 2;
   if (k <= 1024) {                               // warp per row, 8 rows per CTA
     const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 8;
@@ -381,7 +395,7 @@ int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f3
 int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const float* z, int64_t z_sb, int64_t z_sm,
                          const float* scale, float* dz_f32, void* dz_bf16, int64_t B, int k, int kind,
                          const float* snr_db, float snr_db_scalar, uint64_t seed, int64_t sample_offset,
-                         const float* fading, void* stream) {
+                         const float* fading, const uint64_t* seed_dev, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(dy && z && scale && (dz_f32 || dz_bf16), SC_E_SHAPE, "sc_pnorm_channel_bwd: null pointer");
@@ -395,7 +409,7 @@ int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const floa
   a.dz_f32 = dz_f32; a.dz_bf16 = (bf16*)dz_bf16; a.B = B; a.k = k; a.kind = kind;
   a.snr_db = snr_db; a.snr_db_scalar = snr_db_scalar;
   a.key0 = (uint32_t)(seed & 0xffffffffu); a.key1 = (uint32_t)(seed >> 32);
-  a.sample_offset = sample_offset; a.fading = fading;
+  a.sample_offset = sample_offset; a.fading = fading; a.seed_dev = seed_dev;
   const int64_t rows = B * 2;
   if (k <= 1024) {
     const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 6;

@@ -363,7 +363,20 @@ ppo_loss_kernel(const float* __restrict__ ho, int ld, const int64_t* __restrict_
 __global__ void __launch_bounds__(kThreads)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             bf16* __restrict__ pb, int64_t n, float step_size, float b1, float b2, float eps, float inv_sqrt_bc2,
-            float grad_scale) {
+            float grad_scale, float lr, int64_t step, const int64_t* __restrict__ step_dev) {
+  if (step_dev) {
+    // graph replay: the step counter lives on the device; one thread per CTA redoes the host's double-precision
+    // bias corrections
+    __shared__ float bc[2];
+    if (threadIdx.x == 0) {
+      const double t = static_cast<double>(step + *step_dev);
+      bc[0] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), t)));
+      bc[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), t)));
+    }
+    __syncthreads();
+    step_size = bc[0];
+    inv_sqrt_bc2 = bc[1];
+  }
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -496,19 +509,20 @@ int sc_ppo_loss(const float* head_out, int ld, const int64_t* actions, const flo
 }
 
 int sc_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
-                 float beta2, float eps, int64_t step, float grad_scale, void* stream) {
+                 float beta2, float eps, int64_t step, float grad_scale, const int64_t* step_dev, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
-  SC_REQUIRE(p && g && m && v && n > 0 && step >= 1, SC_E_SHAPE, "sc_adam_flat: bad arguments");
+  SC_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || (step_dev && step >= 0)), SC_E_SHAPE, "sc_adam_flat: bad arguments");
   SC_REQUIRE(sc_aligned16(p) && sc_aligned16(g) && sc_aligned16(m) && sc_aligned16(v) &&
                  (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
              SC_E_ALIGN, "sc_adam_flat: unaligned pointer");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double tstep = (double)(step >= 1 ? step : 1);
+  const double bc1 = 1.0 - pow((double)beta1, tstep);
+  const double bc2 = 1.0 - pow((double)beta2, tstep);
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   adam_kernel<<<grid_for(n / 4 + 1, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, (bf16*)p_bf16, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
+      p, g, m, v, (bf16*)p_bf16, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, grad_scale, lr, step, step_dev);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_adam_flat");
   return SC_OK;

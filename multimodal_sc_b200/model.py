@@ -256,7 +256,8 @@ class Engine:
                           colsum=prev_bias_grad)
 
     # ---- forward --------------------------------------------------------------------------
-    def forward(self, cam, bev, snr_db, channel, seed, noise, fading, sample_offset, train, want_aux=False):
+    def forward(self, cam, bev, snr_db, channel, seed, noise, fading, sample_offset, train, want_aux=False,
+                seed_dev=None):
         sp, f = self.spec, self.flat
         B = cam.shape[0]
         A = self.arena(B)
@@ -285,7 +286,7 @@ class Engine:
         scale = A.buf("scale", (B, 2), F32)
         ops.pnorm_channel_fwd(z_mm, channel, snr_db, seed=seed or 0, sample_offset=sample_offset, noise=noise,
                               fading=fading, eps=sp.pnorm_eps, y_f32=y32, y_bf16=y16, scale=scale,
-                              z_strides=(k_sym, B * k_sym, B, k_sym))
+                              z_strides=(k_sym, B * k_sym, B, k_sym), seed_dev=seed_dev)
         # ---- decoder ----
         Sd = sp.dec_tokens
         Md = B * Sd
@@ -319,7 +320,7 @@ class Engine:
                         grad_scale=gs, t1=A["bev_enc.t"], seg_rows=sp.cam_tokens)
 
     # ---- backward -------------------------------------------------------------------------
-    def backward(self, A, B, dho, cam_unused, channel, snr_db, seed, fading, sample_offset):
+    def backward(self, A, B, dho, cam_unused, channel, snr_db, seed, fading, sample_offset, seed_dev=None):
         """dho: fp32 [B, A+1] = d loss / d head_out.  `dec.drecon` must hold d loss / d recon (l_sem()).
         Accumulates into flat.g32."""
         sp, f = self.spec, self.flat
@@ -353,7 +354,7 @@ class Engine:
         dz_mm = A.buf("dz_mm", (2, B, sp.k_sym))
         ops.pnorm_channel_bwd(dy, A["z_mm"], A["scale"], channel, snr_db, seed=seed or 0,
                               sample_offset=sample_offset, fading=fading, dz_bf16=dz_mm,
-                              z_strides=(sp.k_sym, B * sp.k_sym, B, sp.k_sym))
+                              z_strides=(sp.k_sym, B * sp.k_sym, B, sp.k_sym), seed_dev=seed_dev)
         # encoders
         M = B * S
         for mi, enc in enumerate(("cam_enc", "bev_enc")):

@@ -239,8 +239,9 @@ def colsum(x, out):
 
 @_profiled("pnorm_channel_fwd")
 def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, fading=None, eps=1e-12,
-                      y_f32=None, y_bf16=None, scale=None, z_strides=None, y_strides=None):
+                      y_f32=None, y_bf16=None, scale=None, z_strides=None, y_strides=None, seed_dev=None):
     """z fp32 logical [B,2,k] addressed with z_strides=(sb, sm) (default: contiguous [B,2,k]).
+    `seed_dev` (device int64 [1], optional) is added to `seed` inside the kernel (CUDA-graph replays).
     Returns (y_f32, y_bf16, scale)."""
     _cuda(z)
     assert z.dtype == F32
@@ -262,13 +263,14 @@ def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, f
     check(_lib.load().sc_pnorm_channel_fwd(ptr(z), z_strides[0], z_strides[1], ptr(y_f32), ptr(y_bf16),
                                            y_strides[0], y_strides[1], ptr(scale), B, k, SC_CH[kind],
                                            ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1), sample_offset,
-                                           ptr(noise), ptr(fading), eps, stream_ptr()), "sc_pnorm_channel_fwd")
+                                           ptr(noise), ptr(fading), eps, ptr(seed_dev), stream_ptr()),
+          "sc_pnorm_channel_fwd")
     return y_f32, y_bf16, scale
 
 
 @_profiled("pnorm_channel_bwd")
 def pnorm_channel_bwd(dy, z, scale, kind, snr_db, *, seed=0, sample_offset=0, fading=None, dz_f32=None,
-                      dz_bf16=None, z_strides=None, y_strides=None):
+                      dz_bf16=None, z_strides=None, y_strides=None, seed_dev=None):
     _cuda(dy, z, scale)
     assert dy.dtype == F32 and z.dtype == F32
     if z_strides is None:
@@ -285,7 +287,8 @@ def pnorm_channel_bwd(dy, z, scale, kind, snr_db, *, seed=0, sample_offset=0, fa
     check(_lib.load().sc_pnorm_channel_bwd(ptr(dy), y_strides[0], y_strides[1], ptr(z), z_strides[0],
                                            z_strides[1], ptr(scale), ptr(dz_f32), ptr(dz_bf16), B, k,
                                            SC_CH[kind], ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1),
-                                           sample_offset, ptr(fading), stream_ptr()), "sc_pnorm_channel_bwd")
+                                           sample_offset, ptr(fading), ptr(seed_dev), stream_ptr()),
+          "sc_pnorm_channel_bwd")
     return dz_f32, dz_bf16
 
 
@@ -438,8 +441,9 @@ def ppo_loss(head_out, actions, logp_old, adv, ret, n_actions, clip_eps, c_v, c_
 
 
 @_profiled("adam_flat")
-def adam_flat(p, g, m, v, p_bf16, lr, beta1, beta2, eps, step, grad_scale=1.0):
+def adam_flat(p, g, m, v, p_bf16, lr, beta1, beta2, eps, step, grad_scale=1.0, step_dev=None):
+    """`step_dev` (device int64 [1], optional): effective step = step + step_dev[0], read inside the kernel."""
     _cuda(p, g, m, v)
     n = p.numel()
     check(_lib.load().sc_adam_flat(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), n, lr, beta1, beta2, eps, step,
-                                   grad_scale, stream_ptr()), "sc_adam_flat")
+                                   grad_scale, ptr(step_dev), stream_ptr()), "sc_adam_flat")

@@ -70,31 +70,76 @@ class PPOAgent:
         dev = policy.device
         self.stats = torch.zeros(8, device=dev, dtype=F32)      # pi, v, ent, kl, clipfrac, l_sem, -, -
         self.sums = torch.zeros(2, device=dev, dtype=torch.float64)
+        # device-side mirror of step_count: the channel seed and Adam's bias correction read it inside the kernels,
+        # so a captured CUDA graph of the step advances both on every replay
+        self.dev_step = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._graphs = {}                                        # (B, sample_offset) -> (CUDAGraph, static inputs)
 
     # ---- one optimizer step on one (local) minibatch ---------------------------------------------
     def minibatch_step(self, cam, bev, actions, logp_old, adv, values_unused, ret, sample_offset: int = 0,
-                       sync_stats: bool = True):
-        """cam/bev fp32, actions int64, logp_old/adv/ret fp32 — all on the policy's device.
+                       sync_stats: bool = True, graph: bool = False):
+        """cam/bev fp32 or bf16, actions int64, logp_old/adv/ret fp32 — all on the policy's device.
         With world_size > 1 the arguments are this rank's shard of the global minibatch and
-        `sample_offset` is its first global sample index (noise counters are global)."""
+        `sample_offset` is its first global sample index (noise counters are global).
+        graph=True (single GPU): the step's ~130 launches are captured once per batch size in a CUDA graph and
+        replayed; the arguments are copied into the graph's static input buffers."""
+        if graph and self.world == 1:
+            return self._graphed_step(cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats)
+        self._step_body(cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters=False)
+        if not sync_stats:
+            return None
+        return self.read_stats()
+
+    def _step_body(self, cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters: bool):
+        """the kernel schedule of one optimizer step.  device_counters=True: seed and Adam step come from
+        self.dev_step inside the kernels (graph capture / replay), otherwise from the host's step_count."""
         sp, pol = self.spec, self.policy
         eng, flat = pol.engine, pol.flat
         Bl = cam.shape[0]
         flat.g32.zero_()
         self.stats.zero_()
-        seed = self.seed + self.step_count
-        ho, A = eng.forward(cam, bev, self.snr_db, self.channel, seed, None, None, sample_offset, train=True)
+        seed = self.seed if device_counters else self.seed + self.step_count
+        sdev = self.dev_step if device_counters else None
+        ho, A = eng.forward(cam, bev, self.snr_db, self.channel, seed, None, None, sample_offset, train=True,
+                            seed_dev=sdev)
         # l_sem is a mean over the GLOBAL minibatch: each rank contributes its share
         inv_m, sem_coef = dp.loss_scales(Bl, self.world, sp.c_sem)
         eng.l_sem(A, Bl, self.stats[5:6], grad_coef=sem_coef)
         dho = A.buf("ac.dho", tuple(ho.shape), F32)
         ops.ppo_loss(ho, actions, logp_old, adv, ret, sp.n_actions, sp.clip_eps, sp.c_v, sp.c_ent, inv_m,
                      dho=dho, stats=self.stats)
-        eng.backward(A, Bl, dho, None, self.channel, self.snr_db, seed, None, sample_offset)
+        eng.backward(A, Bl, dho, None, self.channel, self.snr_db, seed, None, sample_offset, seed_dev=sdev)
         dp.allreduce_flat_grads(flat.g32, self.pg)
-        self.step_count += 1
-        ops.adam_flat(flat.p32, flat.g32, flat.m, flat.v, flat.p16, sp.lr, sp.beta1, sp.beta2, sp.adam_eps,
-                      self.step_count, grad_scale=1.0)
+        if device_counters:
+            ops.adam_flat(flat.p32, flat.g32, flat.m, flat.v, flat.p16, sp.lr, sp.beta1, sp.beta2, sp.adam_eps,
+                          1, grad_scale=1.0, step_dev=self.dev_step)
+        else:
+            ops.adam_flat(flat.p32, flat.g32, flat.m, flat.v, flat.p16, sp.lr, sp.beta1, sp.beta2, sp.adam_eps,
+                          self.step_count + 1, grad_scale=1.0)
+        self.dev_step.add_(1)
+        if not device_counters:
+            self.step_count += 1
+
+    def _graphed_step(self, cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats):
+        key = (tuple(cam.shape), cam.dtype, tuple(bev.shape), bev.dtype, int(sample_offset))
+        entry = self._graphs.get(key)
+        if entry is None:
+            # the first step of this shape runs eagerly (allocates the activation arena, sets kernel attributes);
+            # then the same schedule is recorded, not executed, against static copies of the inputs
+            self._step_body(cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters=False)
+            static = [t.clone() for t in (cam, bev, actions, logp_old, adv, ret)]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body(*static, sample_offset, device_counters=True)
+            self._graphs[key] = (g, static)
+        else:
+            g, static = entry
+            for dst, src in zip(static, (cam, bev, actions, logp_old, adv, ret)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            g.replay()
+            self.step_count += 1
         if not sync_stats:
             return None
         return self.read_stats()
