@@ -141,6 +141,11 @@ def run_native(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there when
+    # NCCL_DEBUG is set) are pointed at stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
@@ -277,6 +282,8 @@ def run_native(a):
         line["cpu_baseline"] = cpu
     if a.debug_set:
         line["config"]["debug"] = list(a.debug_set)      # an A/B run, not a headline number
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
