@@ -15,7 +15,8 @@
 //   warp 3 / lane 0 : activation producer — the x (dy) tile, backward: the hpre chunks, loaded INTO the hidden buffer
 //   warp 1 / lane 0 : MMA issuer          — order G1(0) G1(1) G2(0) G1(2) G2(1) ... so the tensor pipe always has
 //                                          the next GEMM1 queued while the epilogue works on the previous chunk
-//   warp 2          : TMEM allocator      — 512 columns: two 128-col GEMM1 accumulators + the 256-col GEMM2 accumulator
+//   warp 2 / lane 0 : TMEM allocator (512 columns: two 128-col GEMM1 accumulators + the 256-col GEMM2 accumulator), then
+//                     chunk storer — h / dhpre by TMA straight from the operand buffer, frees the buffer afterwards
 //   warps 4-7 / 8-11: epilogue warpgroups — warpgroup w owns GEMM1 accumulator w and hidden buffer w (even / odd
 //                                          chunks); warpgroup 1 also drains the output accumulator once per tile
 // Shared memory: x tile 64 KB + two hidden buffers 2 x 32 KB + weight ring 96 KB + bias tiles 2 KB.  Nothing is
@@ -374,6 +375,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
       }
     }
+  } else if (warp == 2) {
+    // ===================== chunk storer =====================
+    // saves every finished hidden chunk (h forward, dhpre backward) straight from the operand buffer by TMA and frees
+    // the buffer once the store has read it.  A thread of its own: the epilogue warpgroups never wait for a store.
+    if (lane == 0) {
+      uint32_t nuse[2] = {0u, 0u};
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        for (int j = 0; j < NC; ++j) {
+          const int b = j & 1;
+          mbar_wait(smem_u32(&h_full[b]), nuse[b] & 1u);     // all 128 rows written and fenced
+          ++nuse[b];
+          if (p.store_h) {
+            tma_store_2d(&tmH, hb(b), j * HC, tile * BM);
+            tma_store_2d(&tmH, hb(b) + KB_BYTES, j * HC + 64, tile * BM);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          mbar_arrive(smem_u32(&h_empty[b]));
+        }
+      }
+      tma_store_wait_all();
+    }
   } else if (warp >= 4) {
     // ===================== epilogue warpgroups =====================
     const int wg = (warp - 4) >> 2;                          // 0: even chunks, 1: odd chunks + the output tile
@@ -467,17 +490,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_arrive(smem_u32(&acc1_empty[wg]));              // accumulator drained
         fence_proxy_async_smem();                            // operand buffer writes -> visible to UMMA / TMA
         mbar_arrive(smem_u32(&h_full[wg]));
-        if (wg_tid == 0) {
-          // one thread saves the chunk (h forward, dhpre backward) straight from the operand buffer
-          mbar_wait(smem_u32(&h_full[wg]), par);             // all 128 rows written and fenced
-          if (p.store_h) {
-            tma_store_2d(&tmH, hbuf, j * HC, tile * BM);
-            tma_store_2d(&tmH, hbuf + KB_BYTES, j * HC + 64, tile * BM);
-            tma_store_commit();
-            tma_store_wait_read<0>();
-          }
-          mbar_arrive(smem_u32(&h_empty[wg]));
-        }
       }
       if (wg == 1) {
         // ---- output tile: acc2 (+ b2 + residual) -> bf16, 32 bytes per row per step straight to global ----
@@ -536,7 +548,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_arrive(smem_u32(&acc2_empty));
       }
     }
-    if (wg_tid == 0) tma_store_wait_all();
   }
 
   tc_fence_before();

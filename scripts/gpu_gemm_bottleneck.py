@@ -56,6 +56,14 @@ def make(shape_name):
     if shape_name in ("wgrad_fc1", "wgrad_fc2", "wgrad_qkv"):   # dW[n_out, k_in] += dy^T x, split-K over the tokens, fp32 atomics
         n_out, k_in = {"wgrad_fc1": (1024, 256), "wgrad_fc2": (256, 1024), "wgrad_qkv": (768, 256)}[shape_name]
         return dict(M=n_out, N=k_in, K=M, A=lambda: g(M, n_out), B=g(M, k_in), wgrad=True, kw=lambda: dict())
+    if shape_name in ("proj_ln", "fc2_ln"):   # residual GEMM with the following LayerNorm fused into the epilogue
+        K = 256 if shape_name == "proj_ln" else 1024
+        def kw():
+            return dict(bias=torch.zeros(256, device="cuda"), resid=g(M, 256),
+                        ln=dict(gamma=torch.ones(256, device="cuda"), beta=torch.zeros(256, device="cuda"), eps=1e-5,
+                                y=torch.empty(M, 256, device="cuda", dtype=BF16), mean=torch.empty(M, device="cuda"),
+                                rstd=torch.empty(M, device="cuda")))
+        return dict(M=M, N=256, K=K, A=lambda: g(M, K), B=g(256, K), kw=kw)
     if shape_name == "big":
         return dict(M=8192, N=8192, K=8192, A=lambda: g(8192, 8192), B=g(8192, 8192), kw=lambda: dict())
     if shape_name == "plain256":
@@ -110,6 +118,8 @@ def main():
         names = ("sym", "dsym", "inproj", "plain256")
     if os.environ.get("SC_BOTTLENECK_WGRAD"):
         names = ("wgrad_fc1", "wgrad_fc2", "wgrad_qkv", "fc2")
+    if os.environ.get("SC_BOTTLENECK_LN"):
+        names = ("proj", "proj_ln", "fc2", "fc2_ln")
     for name in names:
         spec = make(name)
         rec = {}
@@ -127,7 +137,7 @@ def main():
             out[name] = rec
             print(name, json.dumps(rec), flush=True)
             continue
-        if os.environ.get("SC_BOTTLENECK_SKINNY") or os.environ.get("SC_BOTTLENECK_WGRAD"):
+        if os.environ.get("SC_BOTTLENECK_SKINNY") or os.environ.get("SC_BOTTLENECK_WGRAD") or os.environ.get("SC_BOTTLENECK_LN"):
             for vn, bits in (("full", 0), ("epi_skip", 1), ("no_mma", 4), ("no_b", 16), ("epi_skip+no_b", 17), ("epi_skip+no_mma", 5),
                              ("loads_off", 32), ("loads_off+epi_skip", 33)):
                 try:

@@ -28,6 +28,15 @@ mb = synthetic.minibatch(sp, B, seed=5, device="cuda", obs_dtype=torch.bfloat16)
 l0 = _lib.launch_count()
 ms = timeit(lambda: eng.forward(mb["cam"], mb["bev"], 10.0, "awgn", 77, None, None, 0, train=False))
 out["cfg2_fwd_b256_awgn10"] = {"ms": ms, "samples_per_s": B / ms * 1e3, "launches_per_fwd": (_lib.launch_count() - l0) // 25}
+# the same forward as one CUDA-graph replay (device-side seed counter: fresh noise on every replay)
+ctr = torch.zeros(1, device="cuda", dtype=torch.int64)
+body = lambda: (eng.forward(mb["cam"], mb["bev"], 10.0, "awgn", 77, None, None, 0, train=False, seed_dev=ctr), ctr.add_(1))
+body(); torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    body()
+ms = timeit(g.replay)
+out["cfg2_fwd_b256_awgn10_cuda_graph"] = {"ms": ms, "samples_per_s": B / ms * 1e3}
 
 # cfg4: Rayleigh sweep, B = 1024, fwd + L_sem + bwd of the semantic loss only
 B = 1024
