@@ -1,6 +1,7 @@
 // api.cu — library plumbing: error string, device check, launch counter, TMA descriptor
 // encoding through the driver entry point (no link-time dependency on libcuda).
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -16,6 +17,20 @@ void sc_set_error(const char* fmt, ...) {
 }
 
 void sc_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// programmatic dependent launch: -1 = not decided yet (SC_PDL=1 turns it on; default off: measured 1-3 % slower on
+// the PPO step, profiles/README.md)
+static std::atomic<int> g_pdl{-1};
+int sc_pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("SC_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+void sc_pdl_set(int v) { g_pdl.store(v ? 1 : 0, std::memory_order_relaxed); }
 
 struct DevInfo {
   int checked = 0;

@@ -90,6 +90,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tma_prefetch_desc(&tmO);
   }
   if (warp == 0) tmem_alloc<256>(smem_u32(&tmem_slot));
+  pdl_sync();                                   // no global-memory access above this line (common.cuh)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -277,6 +278,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tma_prefetch_desc(&tmDQKV);
   }
   if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_slot));
+  pdl_sync();                                   // no global-memory access above this line (common.cuh)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -527,11 +529,11 @@ int sc_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int S, int H,
   }
   if (g_attn_fwd_stages == 2) {
     const int grid = p.num_items < sc_num_sms() ? p.num_items : sc_num_sms();
-    attn_fwd_kernel<2><<<grid, kThreads, fwd_smem(2), (cudaStream_t)stream>>>(tmQKV, tmO, p);
+    sc_launch_kernel(attn_fwd_kernel<2>, dim3(grid), dim3(kThreads), fwd_smem(2), (cudaStream_t)stream, tmQKV, tmO, p);
   } else {
     const int cap = 2 * sc_num_sms();
     const int grid = p.num_items < cap ? p.num_items : cap;
-    attn_fwd_kernel<1><<<grid, kThreads, fwd_smem(1), (cudaStream_t)stream>>>(tmQKV, tmO, p);
+    sc_launch_kernel(attn_fwd_kernel<1>, dim3(grid), dim3(kThreads), fwd_smem(1), (cudaStream_t)stream, tmQKV, tmO, p);
   }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_attn_fwd");
@@ -564,7 +566,7 @@ int sc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
     attr = true;
   }
   const int grid = p.num_items < sc_num_sms() ? p.num_items : sc_num_sms();
-  attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(tmQKV, tmDO, tmDQKV, p);
+  sc_launch_kernel(attn_bwd_kernel, dim3(grid), dim3(kBwdThreads), kBwdSmem, (cudaStream_t)stream, tmQKV, tmDO, tmDQKV, p);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_attn_bwd");
   return SC_OK;

@@ -102,6 +102,7 @@ __device__ __forceinline__ float2 fading_of(const float* fading, int64_t b, int 
 
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_fwd_kernel(const ChanArgs a) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const uint2 key = chan_key(a);
   __shared__ float sh[kThreads / 32];
   const int nv = a.k / 4;                                    // float4 per row
@@ -173,6 +174,7 @@ struct ChanBwdArgs {
 
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_bwd_kernel(const ChanBwdArgs a) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const uint2 key = chan_key(a);
   __shared__ float sh[kThreads / 32];
   const int nv = a.k / 4;
@@ -220,6 +222,7 @@ pnorm_channel_bwd_kernel(const ChanBwdArgs a) {
 
 __global__ void philox_words_kernel(uint32_t* out, int64_t n_quads, uint32_t stream_id, uint32_t k0, uint32_t k1,
                                     int64_t quad_offset) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_quads;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const uint64_t q = static_cast<uint64_t>(quad_offset + i);
@@ -237,6 +240,7 @@ constexpr int kWarpV = 16;                    // float4 per lane -> k <= 2048
 template <int NV>
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const uint2 key = chan_key(a);
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -298,6 +302,7 @@ pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
 template <int NV>
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_bwd_warp_kernel(const ChanBwdArgs a) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const uint2 key = chan_key(a);
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -379,13 +384,13 @@ int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f3
   const int64_t rows = B * 2;
   if (k <= 1024) {                               // warp per row, 8 rows per CTA
     const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 8;
-    pnorm_channel_fwd_warp_kernel<8><<<(int)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+    sc_launch_kernel(pnorm_channel_fwd_warp_kernel<8>, dim3((int)(blocks < cap ? blocks : cap)), dim3(kThreads), 0, (cudaStream_t)stream, a);
   } else if (k <= kWarpV * 128) {
     const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 4;
-    pnorm_channel_fwd_warp_kernel<kWarpV><<<(int)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+    sc_launch_kernel(pnorm_channel_fwd_warp_kernel<kWarpV>, dim3((int)(blocks < cap ? blocks : cap)), dim3(kThreads), 0, (cudaStream_t)stream, a);
   } else {
     const int64_t cap = (int64_t)sc_num_sms() * 8;
-    pnorm_channel_fwd_kernel<<<(int)(rows < cap ? rows : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+    sc_launch_kernel(pnorm_channel_fwd_kernel, dim3((int)(rows < cap ? rows : cap)), dim3(kThreads), 0, (cudaStream_t)stream, a);
   }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_pnorm_channel_fwd");
@@ -413,13 +418,13 @@ int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const floa
   const int64_t rows = B * 2;
   if (k <= 1024) {
     const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 6;
-    pnorm_channel_bwd_warp_kernel<8><<<(int)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+    sc_launch_kernel(pnorm_channel_bwd_warp_kernel<8>, dim3((int)(blocks < cap ? blocks : cap)), dim3(kThreads), 0, (cudaStream_t)stream, a);
   } else if (k <= kWarpV * 128) {
     const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 3;
-    pnorm_channel_bwd_warp_kernel<kWarpV><<<(int)(blocks < cap ? blocks : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+    sc_launch_kernel(pnorm_channel_bwd_warp_kernel<kWarpV>, dim3((int)(blocks < cap ? blocks : cap)), dim3(kThreads), 0, (cudaStream_t)stream, a);
   } else {
     const int64_t cap = (int64_t)sc_num_sms() * 8;
-    pnorm_channel_bwd_kernel<<<(int)(rows < cap ? rows : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+    sc_launch_kernel(pnorm_channel_bwd_kernel, dim3((int)(rows < cap ? rows : cap)), dim3(kThreads), 0, (cudaStream_t)stream, a);
   }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_pnorm_channel_bwd");
@@ -433,7 +438,7 @@ int sc_philox_words(uint32_t* out, int64_t n_quads, uint32_t stream_id, uint64_t
   SC_REQUIRE(out && n_quads > 0, SC_E_SHAPE, "sc_philox_words: bad arguments");
   SC_REQUIRE(sc_aligned16(out), SC_E_ALIGN, "sc_philox_words: unaligned pointer");
   const int grid = (int)((n_quads + 255) / 256 < 1184 ? (n_quads + 255) / 256 : 1184);
-  philox_words_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n_quads, stream_id, (uint32_t)(seed & 0xffffffffu),
+  sc_launch_kernel(philox_words_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, out, n_quads, stream_id, (uint32_t)(seed & 0xffffffffu),
                                                               (uint32_t)(seed >> 32), quad_offset);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_philox_words");

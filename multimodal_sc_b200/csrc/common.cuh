@@ -49,6 +49,37 @@ int sc_encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, ui
 static inline bool sc_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ----------------------------------------------------------------------------------
+// launches: every kernel of the library goes through sc_launch_kernel.  With programmatic dependent launch (PDL,
+// opt-in: sc_debug_set("pdl", 1) or SC_PDL=1; measured slightly slower on the PPO step, so off by default) a kernel may become resident while its predecessor in
+// the stream is still draining: its prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+// predecessor's tail and the launch latency disappears.  The contract every kernel keeps: NO global-memory access
+// before pdl_wait(), and every CTA executes pdl_wait() -> completion of a grid implies completion of all earlier ones.
+// ----------------------------------------------------------------------------------
+int sc_pdl_enabled();                  // api.cu
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sc_launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  int n = 0;
+  if (sc_pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
+// ----------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -58,6 +89,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// ---- programmatic dependent launch ------------------------------------------------------
+// pdl_wait: blocks until the preceding grid in the stream has completed and its memory is visible (no-op when the
+// kernel was launched without the PDL attribute).  pdl_trigger: lets the NEXT kernel in the stream become resident.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
 
 // ---- mbarrier ---------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -164,6 +202,13 @@ __device__ __forceinline__ void tc_fence_after() {
 }
 
 // ---- TMA ------------------------------------------------------------------------------
+// L2 prefetch of one TMA box: the later cp.async.bulk.tensor of the same box hits L2, so the HBM latency is
+// taken off the shared-memory ring (bytes in flight are no longer bounded by the ring depth).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }

@@ -39,6 +39,7 @@ template <typename TI>
 __global__ void __launch_bounds__(kThreads)
 patchify_kernel(const TI* __restrict__ img, bf16* __restrict__ out, int64_t groups, int C, int H,
                 int W, int P) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const int Wt = W / P, Ht = H / P;
   const int K = C * P * P;
   const int K8 = K / 8;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int64_t M, float eps) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   constexpr int D = 256 * NCH;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -151,6 +153,7 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                      const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ colsum, int64_t M) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   constexpr int D = 256 * NCH;
   __shared__ float red[3][D];
   const int lane = threadIdx.x & 31;
@@ -247,6 +250,7 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 __global__ void __launch_bounds__(kThreads)
 colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t M, int N_total, int64_t ld,
               int64_t rows_per_block) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   extern __shared__ float sred[];          // [<= 1024]
   const int col0 = blockIdx.y * 1024;
   const int N = min(1024, N_total - col0);  // columns handled by this block
@@ -281,6 +285,7 @@ colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t M, in
 __global__ void __launch_bounds__(128)
 meanpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ out_bf16, float* __restrict__ out_f32,
                 int64_t B, int S, int D) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   __shared__ float red[4][1024];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nch = D / 256;
@@ -313,6 +318,7 @@ __global__ void __launch_bounds__(kThreads)
 mse_kernel(const bf16* __restrict__ r, const bf16* __restrict__ t, const bf16* __restrict__ t1,
            float* __restrict__ loss, bf16* __restrict__ dr, int64_t groups, float inv_numel, float grad_scale,
            int seg_rows, int D8) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   __shared__ float wsum[kThreads / 32];
   float acc = 0.f;
   for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
@@ -350,6 +356,7 @@ mse_kernel(const bf16* __restrict__ r, const bf16* __restrict__ t, const bf16* _
 
 __global__ void __launch_bounds__(kThreads)
 cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const int64_t groups = n / 8;
   for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
        g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -378,9 +385,9 @@ int sc_patchify_bf16(const void* img, int img_is_bf16, void* out, int64_t B, int
   const int64_t groups = B * C * H * (int64_t)W / 8;
   const int grid = persistent_blocks((groups + kThreads - 1) / kThreads, 8);
   if (img_is_bf16)
-    patchify_kernel<bf16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const bf16*)img, (bf16*)out, groups, C, H, W, P);
+    sc_launch_kernel(patchify_kernel<bf16>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const bf16*)img, (bf16*)out, groups, C, H, W, P);
   else
-    patchify_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float*)img, (bf16*)out, groups, C, H, W, P);
+    sc_launch_kernel(patchify_kernel<float>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const float*)img, (bf16*)out, groups, C, H, W, P);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_patchify_bf16");
   return SC_OK;
@@ -398,7 +405,7 @@ int sc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
   const int grid = persistent_blocks((M + 8 * 4 - 1) / (8 * 4), 3);
   cudaStream_t st = (cudaStream_t)stream;
 #define LN_FWD(T, NCH, R) \
-  layernorm_fwd_kernel<T, NCH, R><<<grid, kThreads, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, M, eps)
+  sc_launch_kernel(layernorm_fwd_kernel<T, NCH, R>, dim3(grid), dim3(kThreads), 0, st, (const T*)x, gamma, beta, (T*)y, mean, rstd, M, eps)
   if (io_f32) {
     if (D == 256) LN_FWD(float, 1, 4); else if (D == 512) LN_FWD(float, 2, 1); else LN_FWD(float, 4, 1);
   } else {
@@ -423,7 +430,7 @@ int sc_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
   const int grid = persistent_blocks((M + 8 * 4 - 1) / (8 * 4), 2);
   cudaStream_t st = (cudaStream_t)stream;
 #define LN_BWD(T, NCH, R)                                                                                  \
-  layernorm_bwd_kernel<T, NCH, R><<<grid, kThreads, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, \
+  sc_launch_kernel(layernorm_bwd_kernel<T, NCH, R>, dim3(grid), dim3(kThreads), 0, st, (const T*)dy, (const T*)x, mean, rstd, gamma, \
                                                              (const T*)dres, (T*)dx, dgamma, dbeta, colsum, M)
   if (io_f32) {
     if (D == 256) LN_BWD(float, 1, 2); else if (D == 512) LN_BWD(float, 2, 1); else LN_BWD(float, 4, 1);
@@ -448,7 +455,7 @@ int sc_colsum_bf16(const void* x, float* out, int64_t M, int N, int64_t ld, void
   int64_t rpb = (M + target - 1) / target;
   if (rpb < 32) rpb = 32;
   const dim3 grid((unsigned)((M + rpb - 1) / rpb), (unsigned)ychunks);
-  colsum_kernel<<<grid, kThreads, 1024 * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, out, M, N, ld, rpb);
+  sc_launch_kernel(colsum_kernel, dim3(grid), dim3(kThreads), 1024 * sizeof(float), (cudaStream_t)stream, (const bf16*)x, out, M, N, ld, rpb);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_colsum_bf16");
   return SC_OK;
@@ -462,7 +469,7 @@ int sc_meanpool_fwd(const void* x, void* out_bf16, float* out_f32, int64_t B, in
              (long long)B, S, D);
   SC_REQUIRE(sc_aligned16(x), SC_E_ALIGN, "sc_meanpool_fwd: unaligned pointer");
   const int grid = persistent_blocks(B, 16);
-  meanpool_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out_bf16, out_f32, B, S, D);
+  sc_launch_kernel(meanpool_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out_bf16, out_f32, B, S, D);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_meanpool_fwd");
   return SC_OK;
@@ -481,7 +488,7 @@ int sc_mse_fwd_bwd(const void* r, const void* t, const void* t1, int seg_rows, i
              "sc_mse_fwd_bwd: two-target mode needs numel %% (2*seg_rows*D) == 0");
   const int64_t groups = numel / 8;
   const int grid = persistent_blocks((groups + kThreads - 1) / kThreads, 8);
-  mse_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const bf16*)r, (const bf16*)t, (const bf16*)t1, loss_accum,
+  sc_launch_kernel(mse_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const bf16*)r, (const bf16*)t, (const bf16*)t1, loss_accum,
                                                           (bf16*)dr, groups, inv_numel, grad_scale, seg_rows,
                                                           D > 0 ? D / 8 : 1);
   sc_count_launch(1);
@@ -495,7 +502,7 @@ int sc_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
   SC_REQUIRE(src && dst && n > 0, SC_E_SHAPE, "sc_cast_f32_bf16: bad arguments");
   SC_REQUIRE(sc_aligned16(src) && sc_aligned16(dst), SC_E_ALIGN, "sc_cast_f32_bf16: unaligned pointer");
   const int grid = persistent_blocks((n / 8 + kThreads - 1) / kThreads, 8);
-  cast_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  sc_launch_kernel(cast_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, src, (bf16*)dst, n);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_cast_f32_bf16");
   return SC_OK;

@@ -115,7 +115,8 @@ struct GemmParams {
   //   4 = no MMAs issued, 8 = every tile loads A block 0 (no HBM reads), 16 = B tiles are not loaded,
   //   32 = no operand loads at all (MMAs run on stale shared memory),
   //   64 = producer / MMA threads hot-spin on their mbarriers (mbarrier.test_wait),
-  //   128 = CTA 0 prints the MMA warp's cycles per k-block
+  //   128 = CTA 0 prints the MMA warp's cycles per k-block,
+  //   256 = L2 prefetch of upcoming operand tiles (results stay correct; measured slower)
   int dbg;
 };
 
@@ -650,6 +651,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       st_shared_v4(ones_tile + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
+  // everything above touches only shared memory / TMEM / kernel parameters: with programmatic dependent launch it
+  // overlaps the tail of the preceding kernel.  Global memory is read or written only after this point.
+  pdl_sync();
   if (G::LN_TILES && p.ln_gamma) {                           // fused LayerNorm: gamma / beta of the 256 columns
     const uint32_t ln_base = smem_base + G::SMEM + G::RING + NWG * BIAS_TILE_BYTES;
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
@@ -686,7 +690,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const Item it = get_item(item);
         const int m0 = (p.dbg & 8) ? 0 : it.m_blk * BM;
         const int n0 = it.n_blk * BN + static_cast<int>(rank) * G::B_ROWS;   // pair: this CTA's half of B
+        // L2 prefetch (opt-in: gemm_dbg bit 256).  Activation-times-weight GEMMs: the A tile of this CTA's NEXT item
+        // is requested a whole tile ahead; split-K wgrad: both operands kPrefetchKb k-blocks ahead.  Measured NEGATIVE
+        // (profiles/README.md, r1 "L2 prefetch"): the whole step got 11 % slower, K = 1024 shapes and wgrads by
+        // 25-35 % -- the memory system, not the ring depth, is what these kernels wait for.
+        const bool l2_pf = !CTA2 && (p.dbg & 256);
+        if (l2_pf && p.ksplit == 1 && elect_one_sync()) {
+          const int nitem = item + cta_stride;
+          if (nitem < num_items) {
+            const Item nx = get_item(nitem);
+            const int nm0 = nx.m_blk * BM;
+            const int nkb = min(nx.kb_end - nx.kb_begin, 16);
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (A_MN == 0) {
+                tma_prefetch_l2_2d(&tmA, (nx.kb_begin + kb) * BK, nm0);
+              } else {
+                for (int c = 0; c < p.m_chunks; ++c) tma_prefetch_l2_2d(&tmA, nm0 + 64 * c, (nx.kb_begin + kb) * BK);
+              }
+            }
+          }
+        }
+        constexpr int kPrefetchKb = 6;
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
+          if (l2_pf && p.ksplit > 1 && kb + kPrefetchKb < it.kb_end && elect_one_sync()) {
+            const int pk0 = (kb + kPrefetchKb) * BK;
+            if (A_MN == 0) {
+              tma_prefetch_l2_2d(&tmA, pk0, m0);
+            } else {
+              for (int c = 0; c < p.m_chunks; ++c) tma_prefetch_l2_2d(&tmA, m0 + 64 * c, pk0);
+            }
+            if (B_MN == 0) {
+              tma_prefetch_l2_2d(&tmB, pk0, n0);
+            } else {
+              for (int c = 0; c < p.n_chunks; ++c) tma_prefetch_l2_2d(&tmB, n0 + 64 * c, pk0);
+            }
+          }
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
           if (!ready) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
@@ -1027,7 +1065,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
       return SC_E_LAUNCH;
     }
   } else {
-    kern<<<grid, threads, smem, st>>>(tmA, tmB, tmOut, tmAux, tmIn, p);
+    cudaError_t e = sc_launch_kernel(kern, dim3(grid), dim3(threads), smem, st, tmA, tmB, tmOut, tmAux, tmIn, p);
+    if (e != cudaSuccess) {
+      sc_set_error("sc_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
+      return SC_E_LAUNCH;
+    }
   }
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_gemm_bf16");
@@ -1037,10 +1079,14 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
 }  // namespace
 
 void sc_attn_debug_set_fwd_stages(int v);
+void sc_pdl_set(int v);
+void sc_mlp_debug_set(int v);
 
 extern "C" int sc_debug_set(const char* key, int64_t value) {
   if (!key) return SC_E_SHAPE;
   if (!strcmp(key, "attn_fwd_stages")) { sc_attn_debug_set_fwd_stages((int)value); return SC_OK; }
+  if (!strcmp(key, "pdl")) { sc_pdl_set((int)value); return SC_OK; }
+  if (!strcmp(key, "mlp_dbg")) { sc_mlp_debug_set((int)value); return SC_OK; }
   if (!strcmp(key, "a_lbo")) g_dbg.a_lbo = value;
   else if (!strcmp(key, "a_sbo")) g_dbg.a_sbo = value;
   else if (!strcmp(key, "a_kstep")) g_dbg.a_kstep = value;

@@ -56,13 +56,9 @@ struct MlpParams {
   bf16* hpre;                // fwd, optional: pre-activation copy [M, R]
   bf16* out;                 // fwd: out [M, 256];  bwd: dx [M, 256]
   int store_h;               // fwd: h is saved (TMA store from the operand buffer);  bwd: always 1 (dhpre)
+  int dbg;                   // sc_debug_set("mlp_dbg", bits): 1 = L2 prefetch of the next tile's inputs
 };
 
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -183,6 +179,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmH);
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
+  pdl_sync();                                               // no global-memory access above this line (common.cuh)
   if (!BWD) {                                               // b2 is the same for every tile
     for (int i = threadIdx.x; i < DM; i += THREADS)
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_base + OFF_BIAS2 + i * 4), "f"(p.b2 ? __ldg(p.b2 + i) : 0.f) : "memory");
@@ -272,6 +269,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (!BWD && p.resid) {
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmResid, kb * 64, row0);
+        }
+        // opt-in (mlp_dbg bit 1): the NEXT tile's inputs (x / dy, in backward its eight hpre chunks) requested into L2
+        // a whole tile ahead.  Measured negative (3.08 -> 3.26 ms per step, profiles/README.md).
+        const int next_tile = tile + static_cast<int>(gridDim.x);
+        if ((p.dbg & 1) && next_tile < p.tiles) {
+          const int nrow0 = next_tile * BM;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmX, kb * 64, nrow0);
+          if (BWD) {
+            for (int c = 0; c < 2 * NC; ++c) tma_prefetch_l2_2d(&tmHin, c * 64, nrow0);
+          }
         }
         if (BWD) {
           for (int j = 0; j < NC; ++j) {                    // hpre chunk j -> hidden buffer j & 1 (transformed in place)
@@ -558,6 +566,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
 }
 
+int g_mlp_dbg = 0;
+
 template <int BWD>
 int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmWa, const CUtensorMap& tmWb, const CUtensorMap& tmH,
                const CUtensorMap& tmHin, const CUtensorMap& tmResid, const MlpParams& p, cudaStream_t st,
@@ -574,9 +584,9 @@ int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmWa, const CUtensorMa
   }
   int grid = sc_num_sms();
   if (p.tiles < grid) grid = p.tiles;
-  kern<<<grid, THREADS, SMEM_TOTAL, st>>>(tmX, tmWa, tmWb, tmH, tmHin, tmResid, p);
+  cudaError_t e = sc_launch_kernel(kern, dim3(grid), dim3(THREADS), SMEM_TOTAL, st, tmX, tmWa, tmWb, tmH, tmHin, tmResid, p);
   sc_count_launch(1);
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     sc_set_error("%s: launch failed: %s", name, cudaGetErrorString(e));
     return SC_E_LAUNCH;
@@ -610,6 +620,7 @@ extern "C" int sc_mlp_fwd(const void* x, const void* w1, const float* b1, const 
   p.hpre = static_cast<bf16*>(hpre);
   p.out = static_cast<bf16*>(out);
   p.store_h = h != nullptr;
+  p.dbg = g_mlp_dbg;
   CUtensorMap tmX, tmWa, tmWb, tmH, tmHin, tmResid;
   memset(&tmH, 0, sizeof(tmH)); memset(&tmHin, 0, sizeof(tmHin)); memset(&tmResid, 0, sizeof(tmResid));
   if ((rc = sc_encode_tmap_2d_bf16(&tmX, x, DM, (uint64_t)M, DM * 2, 64, BM)) != SC_OK) return rc;
@@ -634,6 +645,7 @@ extern "C" int sc_mlp_bwd_dgrad(const void* dy, const void* w1, const void* w2, 
   p.M = M; p.R = R; p.tiles = static_cast<int>((M + BM - 1) / BM);
   p.out = static_cast<bf16*>(dx);
   p.store_h = 1;
+  p.dbg = g_mlp_dbg;
   CUtensorMap tmX, tmWa, tmWb, tmH, tmHin, tmResid;
   memset(&tmResid, 0, sizeof(tmResid));
   if ((rc = sc_encode_tmap_2d_bf16(&tmX, dy, DM, (uint64_t)M, DM * 2, 64, BM)) != SC_OK) return rc;
@@ -645,3 +657,5 @@ extern "C" int sc_mlp_bwd_dgrad(const void* dy, const void* w1, const void* w2, 
   if ((rc = sc_encode_tmap_2d_bf16(&tmHin, hpre, (uint64_t)R, (uint64_t)M, (uint64_t)R * 2, 64, BM)) != SC_OK) return rc;
   return launch_mlp<1>(tmX, tmWa, tmWb, tmH, tmHin, tmResid, p, static_cast<cudaStream_t>(stream), "sc_mlp_bwd_dgrad");
 }
+
+void sc_mlp_debug_set(int v) { g_mlp_dbg = v; }

@@ -24,6 +24,7 @@ __device__ __forceinline__ void load8f(const float* p, float (&x)[8]) {
 __global__ void __launch_bounds__(kThreads)
 heads_fwd_kernel(const bf16* __restrict__ trunk, const float* __restrict__ W, const float* __restrict__ bias,
                  float* __restrict__ out, int64_t B, int D, int A1) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kThreads)
 heads_bwd_kernel(const float* __restrict__ dho, const bf16* __restrict__ trunk, const float* __restrict__ W,
                  bf16* __restrict__ dtrunk_pre, float* __restrict__ dW, float* __restrict__ dbias, int64_t B,
                  int A1) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   constexpr int D = 256;
   __shared__ float sW[kMaxA1 * D];
   __shared__ float sdW[kMaxA1 * D];
@@ -118,6 +120,7 @@ heads_bwd_kernel(const float* __restrict__ dho, const bf16* __restrict__ trunk, 
 __global__ void __launch_bounds__(kThreads)
 sample_kernel(const float* __restrict__ ho, int ld, const float* __restrict__ u, int64_t* __restrict__ action,
               float* __restrict__ logp, int64_t B, int A) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   for (int64_t b = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; b < B;
        b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float* l = ho + b * ld;
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(1024)
 gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ done,
            const float* __restrict__ last_value, float* __restrict__ adv, float* __restrict__ ret,
            double* __restrict__ sums, int T, int64_t N, float gamma, float lam) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   __shared__ float sr[kGaeTC][33], sv[kGaeTC + 1][33], sd[kGaeTC][33], sa[kGaeTC][33];
   __shared__ double ssum[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(128)
 gae_thread_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ done,
                   const float* __restrict__ last_value, float* __restrict__ adv, float* __restrict__ ret,
                   double* __restrict__ sums, int T, int64_t N, float gamma, float lam) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   __shared__ double ssum[2];
   if (threadIdx.x < 2) ssum[threadIdx.x] = 0.0;
   __syncthreads();
@@ -278,6 +283,7 @@ gae_thread_kernel(const float* __restrict__ rew, const float* __restrict__ val, 
 __global__ void __launch_bounds__(kThreads)
 adv_normalize_kernel(float* __restrict__ adv, const double* __restrict__ sums, int64_t count, int64_t n,
                      float eps) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const double mean = sums[0] / static_cast<double>(count);
   double var = sums[1] / static_cast<double>(count) - mean * mean;
   var = var > 0.0 ? var : 0.0;
@@ -296,6 +302,7 @@ ppo_loss_kernel(const float* __restrict__ ho, int ld, const int64_t* __restrict_
                 const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
                 float* __restrict__ dho, float* __restrict__ stats, int64_t M, int A, float clip_eps, float c_v,
                 float c_ent, float inv_m) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   __shared__ float red[5][kThreads / 32];
   float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < M;
@@ -364,6 +371,7 @@ __global__ void __launch_bounds__(kThreads)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             bf16* __restrict__ pb, int64_t n, float step_size, float b1, float b2, float eps, float inv_sqrt_bc2,
             float grad_scale, float lr, int64_t step, const int64_t* __restrict__ step_dev) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   if (step_dev) {
     // graph replay: the step counter lives on the device; one thread per CTA redoes the host's double-precision
     // bias corrections
@@ -428,7 +436,7 @@ int sc_heads_fwd(const void* trunk, const float* W, const float* bias, float* he
   SC_REQUIRE(B > 0 && D % 256 == 0 && A1 >= 2 && A1 <= kMaxA1, SC_E_SHAPE, "sc_heads_fwd: B=%lld D=%d A1=%d",
              (long long)B, D, A1);
   SC_REQUIRE(sc_aligned16(trunk) && sc_aligned16(W), SC_E_ALIGN, "sc_heads_fwd: unaligned pointer");
-  heads_fwd_kernel<<<grid_for(B, 8, 8), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)trunk, W, bias, head_out,
+  sc_launch_kernel(heads_fwd_kernel, dim3(grid_for(B, 8, 8)), dim3(kThreads), 0, (cudaStream_t)stream, (const bf16*)trunk, W, bias, head_out,
                                                                             B, D, A1);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_heads_fwd");
@@ -443,7 +451,7 @@ int sc_heads_bwd(const float* dho, const void* trunk, const float* W, void* dtru
   SC_REQUIRE(B > 0 && D == 256 && A1 >= 2 && A1 <= kMaxA1, SC_E_SHAPE, "sc_heads_bwd: B=%lld D=%d A1=%d (D must be 256)",
              (long long)B, D, A1);
   SC_REQUIRE(sc_aligned16(trunk) && sc_aligned16(dtrunk_pre), SC_E_ALIGN, "sc_heads_bwd: unaligned pointer");
-  heads_bwd_kernel<<<grid_for(B, 64, 1), kThreads, 0, (cudaStream_t)stream>>>(dho, (const bf16*)trunk, W,
+  sc_launch_kernel(heads_bwd_kernel, dim3(grid_for(B, 64, 1)), dim3(kThreads), 0, (cudaStream_t)stream, dho, (const bf16*)trunk, W,
                                                                              (bf16*)dtrunk_pre, dW, dbias, B, A1);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_heads_bwd");
@@ -456,7 +464,7 @@ int sc_sample_action(const float* head_out, int ld, const float* u, int64_t* act
   if (rc != SC_OK) return rc;
   SC_REQUIRE(head_out && u && action && logp, SC_E_SHAPE, "sc_sample_action: null pointer");
   SC_REQUIRE(B > 0 && A >= 1 && ld >= A, SC_E_SHAPE, "sc_sample_action: B=%lld A=%d ld=%d", (long long)B, A, ld);
-  sample_kernel<<<grid_for(B, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(head_out, ld, u, action, logp, B, A);
+  sc_launch_kernel(sample_kernel, dim3(grid_for(B, kThreads, 8)), dim3(kThreads), 0, (cudaStream_t)stream, head_out, ld, u, action, logp, B, A);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_sample_action");
   return SC_OK;
@@ -470,12 +478,12 @@ int sc_gae(const float* rewards, const float* values, const float* dones, const 
   SC_REQUIRE(T > 0 && N > 0, SC_E_SHAPE, "sc_gae: T=%d N=%lld", T, (long long)N);
   if (N >= 16384) {
     // enough environments to fill the GPU with one thread each: fully coalesced streaming form
-    gae_thread_kernel<<<(int)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_value,
+    sc_launch_kernel(gae_thread_kernel, dim3((int)((N + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, rewards, values, dones, last_value,
                                                                                adv, ret, sums, T, N, gamma, lam);
   } else {
     // few environments (the PPO configs: 32..256): parallelise over time with the warp-shuffle scan
     const int grid = (int)((N + 31) / 32);
-    gae_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_value, adv, ret, sums, T, N,
+    sc_launch_kernel(gae_kernel, dim3(grid), dim3(1024), 0, (cudaStream_t)stream, rewards, values, dones, last_value, adv, ret, sums, T, N,
                                                         gamma, lam);
   }
   sc_count_launch(1);
@@ -487,7 +495,7 @@ int sc_adv_normalize(float* adv, const double* sums, int64_t count, int64_t n, f
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(adv && sums && count > 0 && n > 0, SC_E_SHAPE, "sc_adv_normalize: bad arguments");
-  adv_normalize_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(adv, sums, count, n, eps);
+  sc_launch_kernel(adv_normalize_kernel, dim3(grid_for(n, kThreads, 8)), dim3(kThreads), 0, (cudaStream_t)stream, adv, sums, count, n, eps);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_adv_normalize");
   return SC_OK;
@@ -501,7 +509,7 @@ int sc_ppo_loss(const float* head_out, int ld, const int64_t* actions, const flo
   SC_REQUIRE(head_out && actions && logp_old && adv && ret && dho && stats, SC_E_SHAPE, "sc_ppo_loss: null pointer");
   SC_REQUIRE(M > 0 && A >= 1 && A < kMaxA1 && ld >= A + 1, SC_E_SHAPE, "sc_ppo_loss: M=%lld A=%d ld=%d",
              (long long)M, A, ld);
-  ppo_loss_kernel<<<grid_for(M, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(
+  sc_launch_kernel(ppo_loss_kernel, dim3(grid_for(M, kThreads, 4)), dim3(kThreads), 0, (cudaStream_t)stream, 
       head_out, ld, actions, logp_old, adv, ret, dho, stats, M, A, clip_eps, c_v, c_ent, inv_m);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_ppo_loss");
@@ -521,7 +529,7 @@ int sc_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int
   const double bc2 = 1.0 - pow((double)beta2, tstep);
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  adam_kernel<<<grid_for(n / 4 + 1, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+  sc_launch_kernel(adam_kernel, dim3(grid_for(n / 4 + 1, kThreads, 8)), dim3(kThreads), 0, (cudaStream_t)stream, 
       p, g, m, v, (bf16*)p_bf16, n, step_size, beta1, beta2, eps, inv_sqrt_bc2, grad_scale, lr, step, step_dev);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_adam_flat");

@@ -95,14 +95,18 @@ def test_graphed_ppo_step_equals_eager(cuda_lib):
         assert ag.step_count == 3 and int(ag.dev_step) == 3
         return stats, pol.flat.p32.clone()
 
-    (s_e, p_e), (s_e2, p_e2), (s_g, p_g) = run(False), run(False), run(True)
+    (s_e, p_e), (s_e2, p_e2), (s_e3, p_e3), (s_g, p_g) = run(False), run(False), run(False), run(True)
     for k in s_e[0]:
         assert abs(s_e[0][k] - s_g[0][k]) <= 1e-6 + 1e-5 * abs(s_e[0][k]), (k, s_e[0][k], s_g[0][k])
     for i in (1, 2):
         for k in s_e[i]:
-            noise = abs(s_e[i][k] - s_e2[i][k])
-            assert abs(s_e[i][k] - s_g[i][k]) <= 5 * noise + 2e-4 + 2e-2 * abs(s_e[i][k]), (i, k, s_e[i][k], s_g[i][k], noise)
-    noise_p = float((p_e - p_e2).abs().mean())
+            # yardstick = the largest spread among three eager runs (a single pair can agree by chance); clipfrac is a
+            # count over B samples, so one sample on the clip boundary moves it by 1/B whatever the noise level
+            noise = max(abs(s_e[i][k] - s_e2[i][k]), abs(s_e[i][k] - s_e3[i][k]), abs(s_e2[i][k] - s_e3[i][k]))
+            quantum = 2.0 / B if k in ("clipfrac", "total") else 0.0
+            tol = 5 * noise + 2e-4 + 2e-2 * abs(s_e[i][k]) + (quantum if k == "clipfrac" else 0.0)
+            assert abs(s_e[i][k] - s_g[i][k]) <= tol, (i, k, s_e[i][k], s_g[i][k], noise)
+    noise_p = max(float((p_e - p_e2).abs().mean()), float((p_e - p_e3).abs().mean()))
     assert float((p_e - p_g).abs().mean()) <= 5 * noise_p + 1e-5, (float((p_e - p_g).abs().mean()), noise_p)
     assert float((p_e - p_g).abs().max()) <= 2 * 3 * SPEC.lr + 1e-6      # no element can move further than lr per step
 
