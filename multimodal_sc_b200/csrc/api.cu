@@ -32,6 +32,16 @@ int sc_pdl_enabled() {
 }
 void sc_pdl_set(int v) { g_pdl.store(v ? 1 : 0, std::memory_order_relaxed); }
 
+// traversal direction of the streaming kernels.  sc_debug_set("alternate", 1): consecutive launches walk their rows
+// in opposite directions, so a consumer starts with the rows its producer touched last (still in the 126 MB L2).
+static std::atomic<int> g_alt{0};
+static std::atomic<int> g_dir{0};
+void sc_alternate_set(int v) { g_alt.store(v ? 1 : 0); g_dir.store(0); }
+int sc_take_direction() {
+  if (!g_alt.load(std::memory_order_relaxed)) return 0;
+  return g_dir.fetch_xor(1, std::memory_order_relaxed) & 1;
+}
+
 struct DevInfo {
   int checked = 0;
   int major = 0;

@@ -59,6 +59,7 @@ struct FwdParams {
   int64_t M;
   int S, H, num_items;
   float scale_log2;        // log2(e) / sqrt(d)
+  int reverse;             // 1 = items are walked in descending order
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -106,7 +107,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
       const int stage = n % STAGES;
       const uint32_t ph = (n / STAGES) & 1;
-      const int h = item % p.H, row0 = (item / p.H) * 128;
+      const int ri = p.reverse ? p.num_items - 1 - item : item;
+      const int h = ri % p.H, row0 = (ri / p.H) * 128;
       const uint32_t fb = smem_u32(&full_bar[stage]);
       mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
       const uint32_t dst = smem + stage * kFwdStage;
@@ -167,7 +169,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int c_hi = two_seq ? c_lo + 2 : 4;
     int n = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-      const int h = item % p.H, row0 = (item / p.H) * 128;
+      const int ri = p.reverse ? p.num_items - 1 - item : item;
+      const int h = ri % p.H, row0 = (ri / p.H) * 128;
       mbar_wait(smem_u32(&s_full), n & 1);
       __syncwarp();
       tc_fence_after();
@@ -250,6 +253,7 @@ struct BwdParams {
   int S, H, num_items;
   float scale_log2;        // log2(e) / sqrt(d)
   float scale;             // 1 / sqrt(d)
+  int reverse;             // 1 = items are walked in descending order
 };
 
 constexpr int kBwdStage = 4 * kTile;                       // Q, K, V, dO
@@ -292,7 +296,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
       const int stage = n & 1;
       const uint32_t ph = (n >> 1) & 1;
-      const int h = item % p.H, row0 = (item / p.H) * 128;
+      const int ri = p.reverse ? p.num_items - 1 - item : item;
+      const int h = ri % p.H, row0 = (ri / p.H) * 128;
       const uint32_t fb = smem_u32(&full_bar[stage]);
       mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
       const uint32_t dst = smem + stage * kBwdStage;
@@ -373,7 +378,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const bool active = !two_seq || (r >> 6) == g;          // S = 64: a row only attends its own sequence's 64 keys
     int n = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-      const int h = item % p.H, row0 = (item / p.H) * 128;
+      const int ri = p.reverse ? p.num_items - 1 - item : item;
+      const int h = ri % p.H, row0 = (ri / p.H) * 128;
       const float lse2 = (row0 + r < p.M) ? p.lse[static_cast<int64_t>(row0 + r) * p.H + h] : 0.f;
       mbar_wait(smem_u32(&sdp_full), n & 1);
       __syncwarp();
@@ -519,6 +525,7 @@ int sc_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int S, int H,
   p.lse = lse; p.M = M; p.S = S; p.H = H;
   p.num_items = (int)((M + 127) / 128) * H;
   p.scale_log2 = kLog2e * 0.125f;
+  p.reverse = sc_take_direction();
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(1));
@@ -559,6 +566,7 @@ int sc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   p.num_items = (int)((M + 127) / 128) * H;
   p.scale_log2 = kLog2e * 0.125f;
   p.scale = 0.125f;
+  p.reverse = sc_take_direction();
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);

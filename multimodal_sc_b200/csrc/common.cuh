@@ -56,6 +56,7 @@ static inline bool sc_aligned16(const void* p) { return (reinterpret_cast<uintpt
 // before pdl_wait(), and every CTA executes pdl_wait() -> completion of a grid implies completion of all earlier ones.
 // ----------------------------------------------------------------------------------
 int sc_pdl_enabled();                  // api.cu
+int sc_take_direction();               // api.cu: 0 = ascending rows, 1 = descending (sc_debug_set("alternate", 1))
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t sc_launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                      const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, float* __restrict__ colsum, int64_t M) {
+                     float* __restrict__ dbeta, float* __restrict__ colsum, int64_t M, int reverse) {
   pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   constexpr int D = 256 * NCH;
   __shared__ float red[3][D];
@@ -169,7 +169,9 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 #pragma unroll
     for (int j = 0; j < 8; ++j) a_dg[c][j] = a_db[c][j] = a_cs[c][j] = 0.f;
   }
-  for (int64_t base = warp0 * R; base < M; base += nwarps * R) {
+  const int64_t last_base = (M - 1) / R * R;
+  for (int64_t fbase = warp0 * R; fbase < M; fbase += nwarps * R) {
+    const int64_t base = reverse ? last_base - fbase : fbase;       // descending row groups when asked to
     Raw8<T> rx[R][NCH], rdy[R][NCH], rres[R][NCH];
     float mu[R], rs[R];
 #pragma unroll
@@ -429,9 +431,10 @@ int sc_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
              SC_E_ALIGN, "sc_layernorm_bwd: unaligned pointer");
   const int grid = persistent_blocks((M + 8 * 4 - 1) / (8 * 4), 2);
   cudaStream_t st = (cudaStream_t)stream;
+  const int reverse = sc_take_direction();
 #define LN_BWD(T, NCH, R)                                                                                  \
   sc_launch_kernel(layernorm_bwd_kernel<T, NCH, R>, dim3(grid), dim3(kThreads), 0, st, (const T*)dy, (const T*)x, mean, rstd, gamma, \
-                                                             (const T*)dres, (T*)dx, dgamma, dbeta, colsum, M)
+                                                             (const T*)dres, (T*)dx, dgamma, dbeta, colsum, M, reverse)
   if (io_f32) {
     if (D == 256) LN_BWD(float, 1, 2); else if (D == 512) LN_BWD(float, 2, 1); else LN_BWD(float, 4, 1);
   } else {

@@ -118,6 +118,7 @@ struct GemmParams {
   //   128 = CTA 0 prints the MMA warp's cycles per k-block,
   //   256 = L2 prefetch of upcoming operand tiles (results stay correct; measured slower)
   int dbg;
+  int reverse;                  // 1 = items (and the k-blocks of a split-K item) are walked in descending order
 };
 
 struct Item {
@@ -672,7 +673,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int cta_stride = CTA2 ? static_cast<int>(gridDim.x) / 2 : static_cast<int>(gridDim.x);
   const int cta_first = CTA2 ? static_cast<int>(blockIdx.x) / 2 : static_cast<int>(blockIdx.x);
   auto get_item = [&](int item) {
-    Item it = decode_item(p, item);
+    Item it = decode_item(p, p.reverse ? num_items - 1 - item : item);
     if (CTA2) it.m_blk = it.m_blk * 2 + static_cast<int>(rank);
     return it;
   };
@@ -732,7 +733,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ready = mbar_test(smem_u32(&empty_bar[nstage]), nphase ^ 1u);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
-          const int k0 = kb * BK;
+          const int k0 = (p.reverse ? it.kb_end - 1 - (kb - it.kb_begin) : kb) * BK;
           if (elect_one_sync()) {
             if (p.dbg & 32) {                                   // no loads at all: raw MMA issue rate on stale smem
               if (!CTA2 || rank == 0) mbar_arrive(fb_local);
@@ -1028,7 +1029,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 struct DebugOverrides {
   int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0,
-          gemm_dbg = 0, slots = 0;
+          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 0;
 };
 DebugOverrides g_dbg;
 
@@ -1081,12 +1082,14 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
 void sc_attn_debug_set_fwd_stages(int v);
 void sc_pdl_set(int v);
 void sc_mlp_debug_set(int v);
+void sc_alternate_set(int v);
 
 extern "C" int sc_debug_set(const char* key, int64_t value) {
   if (!key) return SC_E_SHAPE;
   if (!strcmp(key, "attn_fwd_stages")) { sc_attn_debug_set_fwd_stages((int)value); return SC_OK; }
   if (!strcmp(key, "pdl")) { sc_pdl_set((int)value); return SC_OK; }
   if (!strcmp(key, "mlp_dbg")) { sc_mlp_debug_set((int)value); return SC_OK; }
+  if (!strcmp(key, "alternate")) { sc_alternate_set((int)value); return SC_OK; }
   if (!strcmp(key, "a_lbo")) g_dbg.a_lbo = value;
   else if (!strcmp(key, "a_sbo")) g_dbg.a_sbo = value;
   else if (!strcmp(key, "a_kstep")) g_dbg.a_kstep = value;
@@ -1096,6 +1099,8 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "max_ctas")) g_dbg.max_ctas = value;
   else if (!strcmp(key, "generic_epi")) g_dbg.generic_epi = value;
   else if (!strcmp(key, "cta2")) g_dbg.cta2 = value;
+  else if (!strcmp(key, "cta2_wgrad")) g_dbg.cta2_wgrad = value;
+  else if (!strcmp(key, "cta2_mink")) g_dbg.cta2_mink = value;
   else if (!strcmp(key, "nwg")) g_dbg.nwg = value;
   else if (!strcmp(key, "gemm_dbg")) g_dbg.gemm_dbg = value;
   else if (!strcmp(key, "slots")) g_dbg.slots = value;
@@ -1130,7 +1135,13 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
-  const bool cta2 = g_dbg.cta2 != 0;
+  // cta2_wgrad: CTA pairs (cta_group::2, 256 x 256 tile per pair, each CTA loads half of B) for the split-K weight
+  // gradients only: one long item per pair, so the accumulator hand-off that hurt the K = 256 shapes happens once, and
+  // the operand traffic from L2 per FLOP drops by a third
+  const bool cta2 = g_dbg.cta2 != 0 ||
+                    (g_dbg.cta2_wgrad != 0 && a_mn && b_mn && ksplit > 1 && M % (2 * BM) == 0 && N % BN == 0) ||
+                    (g_dbg.cta2_mink > 0 && !a_mn && K >= g_dbg.cta2_mink && ksplit <= 1 && !epi->ln_out &&
+                     M % (2 * BM) == 0 && N % BN == 0);
   p.tiles_m = cta2 ? static_cast<int>((M + 2 * BM - 1) / (2 * BM)) : static_cast<int>((M + BM - 1) / BM);
   p.tiles_n = static_cast<int>((N + BN - 1) / BN);
   p.kb_total = static_cast<int>((K + BK - 1) / BK);
@@ -1160,6 +1171,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   p.atomic = epi->atomic;
   p.colsum = epi->colsum;
   p.dbg = static_cast<int>(g_dbg.gemm_dbg);
+  p.reverse = sc_take_direction();
   SC_REQUIRE(!epi->colsum || (a_mn == 1 && epi->out_f32 && !epi->out_bf16), SC_E_SHAPE,
              "sc_gemm_bf16: colsum needs a_mn = 1 and an fp32-only output (the wgrad form)");
   p.vec_ok = (N % 8 == 0) && (epi->ldo % 8 == 0) && sc_aligned16(epi->bias) && sc_aligned16(epi->rowadd) &&

@@ -56,6 +56,7 @@ struct MlpParams {
   bf16* hpre;                // fwd, optional: pre-activation copy [M, R]
   bf16* out;                 // fwd: out [M, 256];  bwd: dx [M, 256]
   int store_h;               // fwd: h is saved (TMA store from the operand buffer);  bwd: always 1 (dhpre)
+  int reverse;               // 1 = row tiles are walked in descending order
   int dbg;                   // sc_debug_set("mlp_dbg", bits): 1 = L2 prefetch of the next tile's inputs
 };
 
@@ -261,7 +262,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       uint32_t t_par = 0;
       uint32_t nuse[2] = {0u, 0u};
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, t_par ^= 1u) {
-        const int row0 = tile * BM;
+        const int row0 = (p.reverse ? p.tiles - 1 - tile : tile) * BM;
         mbar_wait(smem_u32(&x_empty), t_par ^ 1u);
         mbar_arrive_expect_tx(smem_u32(&x_full), XA_BYTES);
 #pragma unroll
@@ -274,7 +275,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         // a whole tile ahead.  Measured negative (3.08 -> 3.26 ms per step, profiles/README.md).
         const int next_tile = tile + static_cast<int>(gridDim.x);
         if ((p.dbg & 1) && next_tile < p.tiles) {
-          const int nrow0 = next_tile * BM;
+          const int nrow0 = (p.reverse ? p.tiles - 1 - next_tile : next_tile) * BM;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmX, kb * 64, nrow0);
           if (BWD) {
@@ -284,6 +285,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (BWD) {
           for (int j = 0; j < NC; ++j) {                    // hpre chunk j -> hidden buffer j & 1 (transformed in place)
             const int b = j & 1;
+            // mlp_dbg bit 2: the chunk that will be loaded two turns from now is requested into L2 while this one
+            // waits for its buffer (short distance: ~2 chunk times, ~100 KB per CTA in flight)
+            if (p.dbg & 2) {
+              const int jn = j + 2;
+              const int ptile = jn < NC ? tile : tile + static_cast<int>(gridDim.x);
+              if (ptile < p.tiles) {
+                const int prow0 = (p.reverse ? p.tiles - 1 - ptile : ptile) * BM;
+                tma_prefetch_l2_2d(&tmHin, (jn % NC) * HC, prow0);
+                tma_prefetch_l2_2d(&tmHin, (jn % NC) * HC + 64, prow0);
+              }
+            }
             mbar_wait(smem_u32(&h_empty[b]), (nuse[b] & 1u) ^ 1u);
             ++nuse[b];
             mbar_arrive_expect_tx(smem_u32(&hin_full[b]), HB_BYTES);
@@ -395,8 +407,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(smem_u32(&h_full[b]), nuse[b] & 1u);     // all 128 rows written and fenced
           ++nuse[b];
           if (p.store_h) {
-            tma_store_2d(&tmH, hb(b), j * HC, tile * BM);
-            tma_store_2d(&tmH, hb(b) + KB_BYTES, j * HC + 64, tile * BM);
+            tma_store_2d(&tmH, hb(b), j * HC, (p.reverse ? p.tiles - 1 - tile : tile) * BM);
+            tma_store_2d(&tmH, hb(b) + KB_BYTES, j * HC + 64, (p.reverse ? p.tiles - 1 - tile : tile) * BM);
             tma_store_commit();
             tma_store_wait_read<0>();
           }
@@ -421,7 +433,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t nuse = 0;                                       // chunks this warpgroup has processed
     uint32_t t_par = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, t_par ^= 1u) {
-      const int64_t grow = static_cast<int64_t>(tile) * BM + r;
+      const int64_t grow = static_cast<int64_t>(p.reverse ? p.tiles - 1 - tile : tile) * BM + r;
       const bool row_ok = grow < p.M;
       for (int j = wg; j < NC; j += 2, ++nuse) {
         const uint32_t par = nuse & 1u;
@@ -621,6 +633,7 @@ extern "C" int sc_mlp_fwd(const void* x, const void* w1, const float* b1, const 
   p.out = static_cast<bf16*>(out);
   p.store_h = h != nullptr;
   p.dbg = g_mlp_dbg;
+  p.reverse = sc_take_direction();
   CUtensorMap tmX, tmWa, tmWb, tmH, tmHin, tmResid;
   memset(&tmH, 0, sizeof(tmH)); memset(&tmHin, 0, sizeof(tmHin)); memset(&tmResid, 0, sizeof(tmResid));
   if ((rc = sc_encode_tmap_2d_bf16(&tmX, x, DM, (uint64_t)M, DM * 2, 64, BM)) != SC_OK) return rc;
@@ -646,6 +659,7 @@ extern "C" int sc_mlp_bwd_dgrad(const void* dy, const void* w1, const void* w2, 
   p.out = static_cast<bf16*>(dx);
   p.store_h = 1;
   p.dbg = g_mlp_dbg;
+  p.reverse = sc_take_direction();
   CUtensorMap tmX, tmWa, tmWb, tmH, tmHin, tmResid;
   memset(&tmResid, 0, sizeof(tmResid));
   if ((rc = sc_encode_tmap_2d_bf16(&tmX, dy, DM, (uint64_t)M, DM * 2, 64, BM)) != SC_OK) return rc;

@@ -61,6 +61,26 @@ def timed(n):
     return e0.elapsed_time(e1) / n
 
 
+# numerics: one step from identical state under each configuration -> same statistics, same gradients up to the
+# order of the fp32 atomics
+state = {k: v.clone() for k, v in pol.state_dict().items()}
+ref, checks = None, {}
+for name, d in configs:
+    configure(d)
+    pol.load_state_dict(state)
+    pol.flat.m.zero_()
+    pol.flat.v.zero_()
+    ag.step_count = 0
+    ag.dev_step.zero_()
+    step(0)
+    torch.cuda.synchronize()
+    g, st = pol.flat.g32.clone(), ag.stats.clone()
+    if ref is None:
+        ref = (g, st)
+    checks[name] = {"grad_max_abs_diff": float((g - ref[0]).abs().max()), "grad_max_abs": float(ref[0].abs().max()),
+                    "stats_max_abs_diff": float((st - ref[1]).abs().max())}
+print("checks:", json.dumps(checks))
+
 res, tables = {}, {}
 for rep in range(3):
     for name, d in configs:
