@@ -59,16 +59,23 @@ int sc_pdl_enabled();                  // api.cu
 int sc_take_direction();               // api.cu: 0 = ascending rows, 1 = descending (sc_debug_set("alternate", 1))
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
-static inline cudaError_t sc_launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                           cudaStream_t st, Args&&... args) {
+static inline cudaError_t sc_launch_kernel_cluster(void (*kern)(KArgs...), int cluster_x, dim3 grid, dim3 block,
+                                                   size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   int n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
   if (sc_pdl_enabled()) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
@@ -77,6 +84,11 @@ static inline cudaError_t sc_launch_kernel(void (*kern)(KArgs...), dim3 grid, di
   cfg.attrs = at;
   cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sc_launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t st, Args&&... args) {
+  return sc_launch_kernel_cluster(kern, 1, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 #endif
 
@@ -219,6 +231,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// Multicast load: the box lands at the same CTA-relative offset in every CTA of `cta_mask` and completes bytes on the
+// mbarrier at the same offset in each of them (every destination CTA has posted its own expect_tx).
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst_smem, const CUtensorMap* tm, uint32_t bar, int32_t c0,
+                                               int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
 
@@ -370,15 +393,25 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
       "r"(commit_bar), "r"(next_bar), "r"(next_parity)
 // kTest: test `next_bar` ahead of the MMAs (result returned); kCommit: commit to `commit_bar` after them.  Stages of
 // more than four MMAs chain a <true,false> block with a <false,true> block.
-template <bool kTest = true, bool kCommit = true>
+// kMc: the commit arrives on `commit_bar` in BOTH CTAs of a 2-CTA cluster (operand stages filled by multicast TMA are
+// free only when both consumers have read them).
+#define SC_COMMIT_LOCAL "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+#define SC_COMMIT_MC2                                                                                            \
+  "{\n\t.reg .b16 cm;\n\tmov.b16 cm, 3;\n\t"                                                                    \
+  "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], cm;\n\t}\n\t"
+template <bool kTest = true, bool kCommit = true, bool kMc = false>
 __device__ __forceinline__ uint32_t umma_kblock4_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t a_step,
                                                          uint32_t b_step, uint32_t idesc, uint32_t accumulate_first,
                                                          uint32_t commit_bar, uint32_t next_bar, uint32_t next_parity) {
   uint32_t ready = 0;
-  if (kTest && kCommit) {
+  if (kTest && kCommit && kMc) {
     asm volatile("{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b, sa, sb;\n\t"
-                 "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t" SC_UMMA4_BODY
-                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t" SC_UMMA4_BODY SC_COMMIT_MC2
+                 "selp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
+  } else if (kTest && kCommit) {
+    asm volatile("{\n\t.reg .pred p, q, t;\n\t.reg .b64 a, b, sa, sb;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t" SC_UMMA4_BODY SC_COMMIT_LOCAL
                  "selp.u32 %0, 1, 0, q;\n\t}"
                  : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
   } else if (kTest) {
@@ -386,9 +419,12 @@ __device__ __forceinline__ uint32_t umma_kblock4_bf16_ss(uint32_t d_tmem, uint64
                  "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n\t" SC_UMMA4_BODY
                  "selp.u32 %0, 1, 0, q;\n\t}"
                  : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
+  } else if (kCommit && kMc) {
+    asm volatile("{\n\t.reg .pred p, t;\n\t.reg .b64 a, b, sa, sb;\n\t" SC_UMMA4_BODY SC_COMMIT_MC2
+                 "mov.u32 %0, 0;\n\t}"
+                 : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
   } else if (kCommit) {
-    asm volatile("{\n\t.reg .pred p, t;\n\t.reg .b64 a, b, sa, sb;\n\t" SC_UMMA4_BODY
-                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+    asm volatile("{\n\t.reg .pred p, t;\n\t.reg .b64 a, b, sa, sb;\n\t" SC_UMMA4_BODY SC_COMMIT_LOCAL
                  "mov.u32 %0, 0;\n\t}"
                  : "=r"(ready) : SC_UMMA4_OPERANDS : "memory");
   } else {
@@ -400,6 +436,8 @@ __device__ __forceinline__ uint32_t umma_kblock4_bf16_ss(uint32_t d_tmem, uint64
 }
 #undef SC_UMMA4_BODY
 #undef SC_UMMA4_OPERANDS
+#undef SC_COMMIT_LOCAL
+#undef SC_COMMIT_MC2
 // all prior tcgen05.mma of this thread arrive on `bar` when complete (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

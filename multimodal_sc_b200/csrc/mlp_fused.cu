@@ -57,7 +57,7 @@ struct MlpParams {
   bf16* out;                 // fwd: out [M, 256];  bwd: dx [M, 256]
   int store_h;               // fwd: h is saved (TMA store from the operand buffer);  bwd: always 1 (dhpre)
   int reverse;               // 1 = row tiles are walked in descending order
-  int dbg;                   // sc_debug_set("mlp_dbg", bits): 1 = L2 prefetch of the next tile's inputs
+  int dbg;                   // sc_debug_set("mlp_dbg", bits): 1 / 2 = L2 prefetch variants (negative), 4 = no weight multicast
 };
 
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -134,7 +134,11 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   return make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
 }
 
-template <int BWD>
+// MC = 1 (backward only): the kernel runs as clusters of two CTAs that share every weight stage.  Each CTA loads one
+// half of the stage and multicasts it into both shared memories; a stage is released when BOTH MMA warps have
+// committed (w_empty counts 2, the commit is multicast).  The weights are 1 MB of the 1.6 MB that a 128-row tile pulls
+// through L2, and the chip-wide L2 throughput (~6300 B/clk) is what bounds this kernel.
+template <int BWD, int MC>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWa,
                  const __grid_constant__ CUtensorMap tmWb, const __grid_constant__ CUtensorMap tmH,
@@ -162,7 +166,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(smem_u32(&x_empty), 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&w_full[s]), 1);
-      mbar_init(smem_u32(&w_empty[s]), 1);
+      mbar_init(smem_u32(&w_empty[s]), MC ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&acc1_full[b]), 1);
@@ -187,8 +191,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();                               // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
   const uint32_t xa = smem_base + OFF_XA;
   const uint32_t ring = smem_base + OFF_RING;
@@ -220,6 +226,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               const int kb = 2 * t + u;
               if (!BWD) {                                   // W1 [R, 256] K-major: 128 hidden rows x 64 k
                 tma_load_2d(dst + u * KB_BYTES, &tmWa, fb, kb * 64, j * HC);
+              } else if (MC) {                              // this CTA's half of the stage, delivered to both CTAs
+                if (u == static_cast<int>(crank)) {
+                  tma_load_2d_mc(dst + u * KB_BYTES, &tmWa, fb, j * HC, kb * 64, 3);
+                  tma_load_2d_mc(dst + u * KB_BYTES + CHUNK8K, &tmWa, fb, j * HC + 64, kb * 64, 3);
+                }
               } else {                                      // W2 [256, R] read MN-major: 64 k-rows x (2 x 64) hidden columns
                 tma_load_2d(dst + u * KB_BYTES, &tmWa, fb, j * HC, kb * 64);
                 tma_load_2d(dst + u * KB_BYTES + CHUNK8K, &tmWa, fb, j * HC + 64, kb * 64);
@@ -239,6 +250,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             mbar_arrive_expect_tx(fb, STAGE_BYTES);
             if (!BWD) {                                     // W2 [256, R] K-major: 256 rows x 64 k
               tma_load_2d(dst, &tmWb, fb, k0, 0);
+            } else if (MC) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const int cc = 2 * static_cast<int>(crank) + c;
+                tma_load_2d_mc(dst + cc * CHUNK8K, &tmWb, fb, 64 * cc, k0, 3);
+              }
             } else {                                        // W1 [R, 256] read MN-major: 64 k-rows x (4 x 64) columns
 #pragma unroll
               for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * CHUNK8K, &tmWb, fb, 64 * c, k0);
@@ -316,6 +333,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       constexpr uint32_t idesc2 = umma_idesc_bf16(BM, DM, 0, BWD ? 1 : 0);
       constexpr uint32_t b_lbo = BWD ? CHUNK8K : 16;
       constexpr uint32_t b_kstep16 = (BWD ? 2048 : 32) >> 4;
+      // descriptors carry the 18-bit CTA-local address only: inside a cluster the shared::cta window of rank r starts
+      // at r << 24, and those upper bits would spill into the descriptor's LBO field (seen as wrong second 64-column
+      // chunks of MN-major operands on rank 1)
       const uint64_t a_desc0 = umma_smem_desc(0, 16, 1024);
       const uint64_t b_desc0 = umma_smem_desc(0, b_lbo, 1024);
       int stage = 0;
@@ -342,15 +362,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int t = 0; t < 2; ++t) {
           const uint32_t wb = acquire_stage();
           tc_fence_after();
-          const uint64_t ad = a_desc0 + ((xa + 2 * t * KB_BYTES) >> 4);
-          const uint64_t bd = b_desc0 + (wb >> 4);
+          const uint64_t ad = a_desc0 + (((xa + 2 * t * KB_BYTES) & 0x3FFFFu) >> 4);
+          const uint64_t bd = b_desc0 + ((wb & 0x3FFFFu) >> 4);
           uint32_t r = 0;
           if (elect_one_sync()) {
             // eight 128x128x16 MMAs: the next weight stage is tested ahead of the first four, the commit follows the last
             r = umma_kblock4_bf16_ss<true, false>(d_tmem, ad, bd, 2u, b_kstep16, idesc1, t > 0 ? 1u : 0u,
                                                   smem_u32(&w_empty[stage]), smem_u32(&w_full[nstage]), nphase);
-            umma_kblock4_bf16_ss<false, true>(d_tmem, ad + (KB_BYTES >> 4), bd + (KB_BYTES >> 4), 2u, b_kstep16, idesc1, 1u,
-                                              smem_u32(&w_empty[stage]), 0u, 0u);
+            umma_kblock4_bf16_ss<false, true, MC != 0>(d_tmem, ad + (KB_BYTES >> 4), bd + (KB_BYTES >> 4), 2u, b_kstep16,
+                                                       idesc1, 1u, smem_u32(&w_empty[stage]), 0u, 0u);
           }
           ready = __shfl_sync(0xffffffffu, r, 0);
           advance();
@@ -371,12 +391,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int t = 0; t < 2; ++t) {
           const uint32_t wb = acquire_stage();
           tc_fence_after();
-          const uint64_t ad = a_desc0 + ((hb(b) + t * KB_BYTES) >> 4);
-          const uint64_t bd = b_desc0 + (wb >> 4);
+          const uint64_t ad = a_desc0 + (((hb(b) + t * KB_BYTES) & 0x3FFFFu) >> 4);
+          const uint64_t bd = b_desc0 + ((wb & 0x3FFFFu) >> 4);
           uint32_t r = 0;
           if (elect_one_sync())
-            r = umma_kblock4_bf16_ss<true, true>(d_tmem, ad, bd, 2u, b_kstep16, idesc2, (j > 0 || t > 0) ? 1u : 0u,
-                                                 smem_u32(&w_empty[stage]), smem_u32(&w_full[nstage]), nphase);
+            r = umma_kblock4_bf16_ss<true, true, MC != 0>(d_tmem, ad, bd, 2u, b_kstep16, idesc2, (j > 0 || t > 0) ? 1u : 0u,
+                                                          smem_u32(&w_empty[stage]), smem_u32(&w_full[nstage]), nphase);
           ready = __shfl_sync(0xffffffffu, r, 0);
           advance();
         }
@@ -572,6 +592,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();                               // the peer may still multicast commits into this CTA
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -580,12 +601,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
 int g_mlp_dbg = 0;
 
-template <int BWD>
-int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmWa, const CUtensorMap& tmWb, const CUtensorMap& tmH,
-               const CUtensorMap& tmHin, const CUtensorMap& tmResid, const MlpParams& p, cudaStream_t st,
-               const char* name) {
+template <int BWD, int MC>
+int launch_mlp_impl(const CUtensorMap& tmX, const CUtensorMap& tmWa, const CUtensorMap& tmWb, const CUtensorMap& tmH,
+                    const CUtensorMap& tmHin, const CUtensorMap& tmResid, const MlpParams& p, cudaStream_t st,
+                    const char* name) {
   static bool attr_set = false;
-  auto kern = mlp_fused_kernel<BWD>;
+  auto kern = mlp_fused_kernel<BWD, MC>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) {
@@ -596,7 +617,9 @@ int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmWa, const CUtensorMa
   }
   int grid = sc_num_sms();
   if (p.tiles < grid) grid = p.tiles;
-  cudaError_t e = sc_launch_kernel(kern, dim3(grid), dim3(THREADS), SMEM_TOTAL, st, tmX, tmWa, tmWb, tmH, tmHin, tmResid, p);
+  if (MC) grid &= ~1;                 // whole pairs; tiles is even, so both CTAs of a pair walk the same number of tiles
+  cudaError_t e = sc_launch_kernel_cluster(kern, MC ? 2 : 1, dim3(grid), dim3(THREADS), SMEM_TOTAL, st, tmX, tmWa, tmWb,
+                                           tmH, tmHin, tmResid, p);
   sc_count_launch(1);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -604,6 +627,16 @@ int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmWa, const CUtensorMa
     return SC_E_LAUNCH;
   }
   return SC_OK;
+}
+
+template <int BWD>
+int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmWa, const CUtensorMap& tmWb, const CUtensorMap& tmH,
+               const CUtensorMap& tmHin, const CUtensorMap& tmResid, const MlpParams& p, cudaStream_t st,
+               const char* name) {
+  // backward: weight stages shared by CTA pairs (multicast) whenever the tiles split evenly; mlp_dbg bit 4 = off
+  if (BWD && p.tiles >= 2 && p.tiles % 2 == 0 && !(g_mlp_dbg & 4))
+    return launch_mlp_impl<BWD, BWD ? 1 : 0>(tmX, tmWa, tmWb, tmH, tmHin, tmResid, p, st, name);
+  return launch_mlp_impl<BWD, 0>(tmX, tmWa, tmWb, tmH, tmHin, tmResid, p, st, name);
 }
 
 int check_common(const char* name, int64_t M, int D, int R) {
