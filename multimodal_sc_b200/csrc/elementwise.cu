@@ -32,41 +32,6 @@ inline int persistent_blocks(int64_t work_blocks, int per_sm) {
   return static_cast<int>(work_blocks < cap ? (work_blocks > 0 ? work_blocks : 1) : cap);
 }
 
-// ------------------------------------------------------------------------------------------
-// patchify + cast: one thread per 8 output features (always inside one image row)
-// ------------------------------------------------------------------------------------------
-template <typename TI>
-__global__ void __launch_bounds__(kThreads)
-patchify_kernel(const TI* __restrict__ img, bf16* __restrict__ out, int64_t groups, int C, int H,
-                int W, int P) {
-  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
-  const int Wt = W / P, Ht = H / P;
-  const int K = C * P * P;
-  const int K8 = K / 8;
-  const int P8 = P / 8;
-  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
-       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int kg = static_cast<int>(g % K8);
-    const int64_t tok = g / K8;
-    const int px0 = (kg % P8) * 8;
-    const int py = (kg / P8) % P;
-    const int c = kg / (P8 * P);
-    const int tx = static_cast<int>(tok % Wt);
-    const int ty = static_cast<int>((tok / Wt) % Ht);
-    const int64_t b = tok / (Wt * Ht);
-    const TI* src = img + ((b * C + c) * H + (ty * P + py)) * static_cast<int64_t>(W) + tx * P + px0;
-    float x[8];
-    load8(src, x);
-    store8(out + g * 8, x);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, lane owns NCH chunks of 8 contiguous elements (D = 256*NCH).
-// Each warp handles R rows per iteration and issues all of their 16-byte loads before touching any
-// of them: with 1 row in flight per warp the kernels sat at ~3 TB/s (latency-bound), R rows put
-// R x more bytes in flight per SM.
-// ------------------------------------------------------------------------------------------
 template <typename T> struct Raw8;
 template <> struct Raw8<bf16> { uint4 v; };
 template <> struct Raw8<float> { float4 a, b; };
@@ -83,6 +48,58 @@ __device__ __forceinline__ void cvt_raw(const Raw8<bf16>& r, float (&x)[8]) {
 __device__ __forceinline__ void cvt_raw(const Raw8<float>& r, float (&x)[8]) {
   x[0] = r.a.x; x[1] = r.a.y; x[2] = r.a.z; x[3] = r.a.w; x[4] = r.b.x; x[5] = r.b.y; x[6] = r.b.z; x[7] = r.b.w;
 }
+
+// ------------------------------------------------------------------------------------------
+// patchify + cast: one thread per 8 output features (always inside one image row)
+// ------------------------------------------------------------------------------------------
+template <typename TI>
+__global__ void __launch_bounds__(kThreads)
+patchify_kernel(const TI* __restrict__ img, bf16* __restrict__ out, int64_t groups, int C, int H,
+                int W, int P) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
+  const int Wt = W / P, Ht = H / P;
+  const int K = C * P * P;
+  const int K8 = K / 8;
+  const int P8 = P / 8;
+  // kUnroll independent 16-byte loads are issued before the first store: with one load in flight per thread the
+  // kernel sat at 2.6 TB/s (latency-bound; every warp request touches 16 lines of a strided image row set)
+  constexpr int kUnroll = 4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t g0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g0 < groups; g0 += stride * kUnroll) {
+    Raw8<TI> raw[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t g = g0 + u * stride;
+      if (g < groups) {
+        const int kg = static_cast<int>(g % K8);
+        const int64_t tok = g / K8;
+        const int px0 = (kg % P8) * 8;
+        const int py = (kg / P8) % P;
+        const int c = kg / (P8 * P);
+        const int tx = static_cast<int>(tok % Wt);
+        const int ty = static_cast<int>((tok / Wt) % Ht);
+        const int64_t b = tok / (Wt * Ht);
+        ld_raw(img + ((b * C + c) * H + (ty * P + py)) * static_cast<int64_t>(W) + tx * P + px0, raw[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t g = g0 + u * stride;
+      if (g < groups) {
+        float x[8];
+        cvt_raw(raw[u], x);
+        store8(out + g * 8, x);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, lane owns NCH chunks of 8 contiguous elements (D = 256*NCH).
+// Each warp handles R rows per iteration and issues all of their 16-byte loads before touching any
+// of them: with 1 row in flight per warp the kernels sat at ~3 TB/s (latency-bound), R rows put
+// R x more bytes in flight per SM.
+// ------------------------------------------------------------------------------------------
 
 template <typename T, int NCH, int R>
 __global__ void __launch_bounds__(kThreads, 3)
@@ -323,28 +340,45 @@ mse_kernel(const bf16* __restrict__ r, const bf16* __restrict__ t, const bf16* _
   pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   __shared__ float wsum[kThreads / 32];
   float acc = 0.f;
-  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < groups;
-       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float a[8], b[8], d[8];
-    load8(r + g * 8, a);
-    if (t1) {
-      // r rows are (sample, modality, token); targets are two [samples*seg_rows, D] matrices
-      const int64_t row = g / D8;
-      const int c8 = static_cast<int>(g % D8);
-      const int64_t smp = row / (2 * seg_rows);
-      const int rem = static_cast<int>(row % (2 * seg_rows));
-      const bf16* tb = rem < seg_rows ? t : t1;
-      load8(tb + ((smp * seg_rows + (rem % seg_rows)) * D8 + c8) * 8, b);
-    } else {
-      load8(t + g * 8, b);
+  // four independent (recon, target) load pairs in flight per thread before the first use (latency-bound otherwise)
+  constexpr int kUnroll = 4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t g0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g0 < groups; g0 += stride * kUnroll) {
+    Raw8<bf16> ra[kUnroll], rb[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t g = g0 + u * stride;
+      if (g < groups) {
+        ld_raw(r + g * 8, ra[u]);
+        if (t1) {
+          // r rows are (sample, modality, token); targets are two [samples*seg_rows, D] matrices
+          const int64_t row = g / D8;
+          const int c8 = static_cast<int>(g % D8);
+          const int64_t smp = row / (2 * seg_rows);
+          const int rem = static_cast<int>(row % (2 * seg_rows));
+          const bf16* tb = rem < seg_rows ? t : t1;
+          ld_raw(tb + ((smp * seg_rows + (rem % seg_rows)) * D8 + c8) * 8, rb[u]);
+        } else {
+          ld_raw(t + g * 8, rb[u]);
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float e = a[j] - b[j];
-      acc = fmaf(e, e, acc);
-      d[j] = 2.0f * e * grad_scale;
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t g = g0 + u * stride;
+      if (g < groups) {
+        float a[8], b[8], d[8];
+        cvt_raw(ra[u], a);
+        cvt_raw(rb[u], b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float e = a[j] - b[j];
+          acc = fmaf(e, e, acc);
+          d[j] = 2.0f * e * grad_scale;
+        }
+        if (dr) store8(dr + g * 8, d);
+      }
     }
-    if (dr) store8(dr + g * 8, d);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
