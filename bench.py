@@ -243,15 +243,24 @@ def run_native(a):
     tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
     if os.path.exists(tpath) and B == MB_PER_GPU:
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
-    roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all operand-major variants)",
-            "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
-            "algorithmic_bytes_per_launch": g_by / max(g_n, 1),
-            "hbm_view": {"note": "the D=256 GEMMs sit below the ridge point (AI 128-205 FLOP/B < 214), so their "
-                                 "attainable bound is the HBM roofline; same launches, algorithmic bytes / time",
-                         "achieved_gbs": g_by / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0, "peak_gbs": peaks["hbm_gbs"],
-                         "frac": (g_by / (g_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if g_ms > 0 else 0.0},
-            "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+    # which roof binds: arithmetic intensity of the launches (algorithmic FLOP / algorithmic bytes, each operand read
+    # once, each result written once) against the ridge point of the measured peaks.  The D = 256 GEMMs of this model
+    # sit below the ridge (AI ~150 < ~214 FLOP/B), so the attainable rate is AI x HBM bandwidth, not the tensor peak;
+    # both views are reported and `bound` names the binding one.
+    ai = g_fl / max(g_by, 1.0)
+    ridge = peaks["tf_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    gbs = g_by / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
+    tensor_view = {"achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                   "frac": achieved / peaks["tf_sustained"]}
+    hbm_view = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+    bound = "hbm" if ai < ridge else "tensor"
+    main = hbm_view if bound == "hbm" else tensor_view
+    roof = {"bound": bound, "kernel": "gemm_tcgen05_kernel (all operand-major variants)",
+            "achieved": main["achieved"], "peak": main["peak"], "unit": main["unit"], "frac": main["frac"],
+            "traffic": traffic, "algorithmic_bytes_per_launch": g_by / max(g_n, 1),
+            "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+            "tensor_view": tensor_view, "hbm_view": hbm_view,
+            "peak_source": peaks["source"] + "; tensor view uses the sustained bf16 figure (kernels timed inside a long step)",
             "launches_per_step": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / max(step_ms_prof, 1e-9),
             "algorithmic_flops_per_step": g_fl,
             "by_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),

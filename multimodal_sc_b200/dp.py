@@ -37,6 +37,53 @@ def allreduce_flat_grads(g32: torch.Tensor, pg=None) -> torch.Tensor:
     return g32
 
 
+def grad_buckets(offsets, numel: int):
+    """Contiguous regions of the flat gradient bucket in the order backward COMPLETES them.
+
+    `offsets`: name -> (offset, n) in flat order (cam_enc.*, bev_enc.*, dec.*, ac.*).  Backward runs
+    heads -> decoder -> channel -> camera encoder -> BEV encoder, so the [dec.*, ac.*] tail is final first, then the
+    camera-encoder region, then the BEV-encoder region.  Returns [(name, lo, hi)] covering [0, numel) exactly once."""
+    first = {}
+    for name, (off, _) in offsets.items():
+        top = name.split(".")[0]
+        grp = top if top in ("cam_enc", "bev_enc") else "dec"
+        first.setdefault(grp, off)
+    cam, bev, dec = first["cam_enc"], first["bev_enc"], first["dec"]
+    assert cam == 0 and cam < bev < dec < numel, (cam, bev, dec, numel)
+    return [("dec", dec, numel), ("cam_enc", cam, bev), ("bev_enc", bev, dec)]
+
+
+class OverlappedGradAllReduce:
+    """All-reduce of the flat gradient bucket in the regions of grad_buckets(), each launched (async) as soon as
+    backward has finished writing it, so the decoder's 2.5 M gradients cross NVLink while the encoders' backward
+    kernels run.  ready(name) is called by Engine.backward on the compute stream; finish() joins before Adam.
+    With world_size 1 every call is a no-op."""
+
+    def __init__(self, g32: torch.Tensor, offsets, pg=None):
+        self.g32, self.pg = g32, pg
+        self.world, _ = world_info(pg)
+        self.buckets = {name: (lo, hi) for name, lo, hi in grad_buckets(offsets, g32.numel())}
+        self.pending = []
+        self.done = set()
+
+    def ready(self, name: str):
+        if self.world == 1:
+            return
+        lo, hi = self.buckets[name]
+        assert name not in self.done, f"bucket {name} reduced twice"
+        self.done.add(name)
+        self.pending.append(dist.all_reduce(self.g32[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def finish(self):
+        if self.world == 1:
+            return
+        assert self.done == set(self.buckets), f"buckets not reduced: {set(self.buckets) - self.done}"
+        for w in self.pending:
+            w.wait()                      # the current stream waits for the collective (no host block on NCCL)
+        self.pending.clear()
+        self.done.clear()
+
+
 def global_adv_moments(sums: torch.Tensor, local_count: int, pg=None):
     """sums = float64 [sum A, sum A^2] over the local shard -> (global sums, global count)."""
     world, _ = world_info(pg)

@@ -360,9 +360,11 @@ class Engine:
                         grad_scale=gs, t1=A["bev_enc.t"], seg_rows=sp.cam_tokens)
 
     # ---- backward -------------------------------------------------------------------------
-    def backward(self, A, B, dho, cam_unused, channel, snr_db, seed, fading, sample_offset, seed_dev=None):
+    def backward(self, A, B, dho, cam_unused, channel, snr_db, seed, fading, sample_offset, seed_dev=None,
+                 grad_ready=None):
         """dho: fp32 [B, A+1] = d loss / d head_out.  `dec.drecon` must hold d loss / d recon (l_sem()).
-        Accumulates into flat.g32."""
+        Accumulates into flat.g32.  `grad_ready(name)` is called on the compute stream as soon as the gradient
+        region `name` of dp.grad_buckets() ("dec", "cam_enc", "bev_enc") is final (data-parallel overlap)."""
         sp, f = self.spec, self.flat
         D, S, C, Sd = sp.d_model, sp.cam_tokens, sp.c_sym, sp.dec_tokens
         Md = B * Sd
@@ -391,6 +393,9 @@ class Engine:
         ops.colsum(cur.view(B, Sd * D), f.g("dec.pos").view(-1))
         dy = A.buf("dy", (B, 2, sp.k_sym), F32)
         self._linear_bwd(cur, A["y16"].view(Md, C), "dec.in_proj", bias_colsum=False, out_f32=dy.view(Md, C))
+        if grad_ready is not None:
+            self._join_side()
+            grad_ready("dec")
         # channel
         dz_mm = A.buf("dz_mm", (2, B, sp.k_sym))
         ops.pnorm_channel_bwd(dy, A["z_mm"], A["scale"], channel, snr_db, seed=seed or 0,
@@ -415,7 +420,13 @@ class Engine:
                 cur, nxt = nxt, cur
             ops.colsum(cur.view(B, S * D), f.g(f"{enc}.pos").view(-1))
             self._linear_bwd(cur, A[f"{enc}.tok"], f"{enc}.patch_embed", bias_colsum=False)
-        if self._side_done:                       # join: the flat gradient bucket is complete on the current stream
+            if grad_ready is not None:
+                self._join_side()
+                grad_ready(enc)
+        self._join_side()                         # the flat gradient bucket is complete on the current stream
+
+    def _join_side(self):
+        if self._side_done:
             torch.cuda.current_stream(self.device).wait_event(self._side_done[-1])
 
 

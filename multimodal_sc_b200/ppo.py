@@ -5,13 +5,16 @@ Drop-in for `oracle/ppo.py: PPOAgent` (same constructor arguments, `update(rollo
 trainer).  One optimizer step is a fixed kernel schedule on the current stream:
 
     memset(flat grad, stats) -> Engine.forward -> sc_mse_fwd_bwd -> sc_ppo_loss -> Engine.backward
-      -> [NCCL all-reduce of the flat fp32 bucket, data-parallel only] -> sc_adam_flat
+      -> [NCCL all-reduce of the flat fp32 bucket, data-parallel only; SC_DP_OVERLAP=1 launches it in three regions,
+          each as soon as backward has finished writing it] -> sc_adam_flat
 
 Data parallelism: every rank holds whole trajectories; the only data-path
 collectives are the flat-gradient all-reduce (one per optimizer step) and a 2-double all-reduce
 of (sum A, sum A^2) per rollout for the global advantage normalisation.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -74,6 +77,10 @@ class PPOAgent:
         # so a captured CUDA graph of the step advances both on every replay
         self.dev_step = torch.zeros(1, device=dev, dtype=torch.int64)
         self._graphs = {}                                        # (B, sample_offset) -> (CUDAGraph, static inputs)
+        self._overlap = None                                     # dp.OverlappedGradAllReduce, built on first use
+        # opt-in: measured 2 % SLOWER at 2 GPUs (21.6 -> 22.0-22.3 ms): the NCCL kernels take SMs away from the
+        # persistent one-CTA-per-SM GEMMs, whose displaced CTAs then run as a second wave (profiles/README.md)
+        self.overlap_allreduce = os.environ.get("SC_DP_OVERLAP", "0") != "0"
 
     # ---- one optimizer step on one (local) minibatch ---------------------------------------------
     def minibatch_step(self, cam, bev, actions, logp_old, adv, values_unused, ret, sample_offset: int = 0,
@@ -108,8 +115,17 @@ class PPOAgent:
         dho = A.buf("ac.dho", tuple(ho.shape), F32)
         ops.ppo_loss(ho, actions, logp_old, adv, ret, sp.n_actions, sp.clip_eps, sp.c_v, sp.c_ent, inv_m,
                      dho=dho, stats=self.stats)
-        eng.backward(A, Bl, dho, None, self.channel, self.snr_db, seed, None, sample_offset, seed_dev=sdev)
-        dp.allreduce_flat_grads(flat.g32, self.pg)
+        # data parallel, overlap mode: the decoder's gradients are all-reduced while the encoders' backward still runs,
+        # the camera encoder's while the BEV encoder's runs (three contiguous regions of the flat bucket, dp.grad_buckets)
+        if self.world > 1 and self._overlap is None:
+            self._overlap = dp.OverlappedGradAllReduce(flat.g32, flat.offsets, self.pg)
+        ov = self._overlap if (self.world > 1 and self.overlap_allreduce) else None
+        eng.backward(A, Bl, dho, None, self.channel, self.snr_db, seed, None, sample_offset, seed_dev=sdev,
+                     grad_ready=ov.ready if ov is not None else None)
+        if ov is not None:
+            ov.finish()
+        else:
+            dp.allreduce_flat_grads(flat.g32, self.pg)
         if device_counters:
             ops.adam_flat(flat.p32, flat.g32, flat.m, flat.v, flat.p16, sp.lr, sp.beta1, sp.beta2, sp.adam_eps,
                           1, grad_scale=1.0, step_dev=self.dev_step)

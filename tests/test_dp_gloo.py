@@ -93,3 +93,66 @@ def test_shard_bounds_cover_everything():
             spans = [dp.shard_bounds(n, w, r) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+# ---- bucketed all-reduce launched as backward completes each region -------------------------
+def test_grad_buckets_cover_flat_bucket_in_backward_order():
+    from multimodal_sc_b200.model import FlatParams
+    flat = FlatParams(SPEC, "cpu")
+    b = dp.grad_buckets(flat.offsets, flat.numel)
+    assert [n for n, _, _ in b] == ["dec", "cam_enc", "bev_enc"]          # the order backward finishes them
+    spans = sorted((lo, hi) for _, lo, hi in b)
+    assert spans[0][0] == 0 and spans[-1][1] == flat.numel
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))   # no gap, no overlap
+    reg = {n: (lo, hi) for n, lo, hi in b}
+    for name, (off, n) in flat.offsets.items():
+        top = name.split(".")[0]
+        lo, hi = reg[top if top in ("cam_enc", "bev_enc") else "dec"]
+        assert lo <= off and off + n <= hi, name
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from multimodal_sc_b200.model import FlatParams
+        flat = FlatParams(SPEC, "cpu")
+        g = torch.Generator().manual_seed(7 + rank)
+        flat.g32.copy_(torch.randn(flat.numel, generator=g))
+        whole = flat.g32.clone()
+        ov = dp.OverlappedGradAllReduce(flat.g32, flat.offsets)
+        for name in ("dec", "cam_enc", "bev_enc"):                         # Engine.backward's call order
+            ov.ready(name)
+        ov.finish()
+        dp.allreduce_flat_grads(whole)
+        ok = torch.equal(flat.g32, whole)
+        # a second step reuses the object; a bucket announced twice or a missing bucket must be refused
+        ov.ready("dec")
+        try:
+            ov.ready("dec")
+            twice = False
+        except AssertionError:
+            twice = True
+        try:
+            ov.finish()
+            missing = False
+        except AssertionError:
+            missing = True
+        if rank == 0:
+            q.put((ok, twice, missing))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_bucket_allreduce_equals_single_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, twice, missing = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert ok and twice and missing
