@@ -31,12 +31,13 @@ extern "C" {
 #define SC_E_LAUNCH (-4)
 #define SC_E_DRIVER (-5)
 
-#define SC_ABI_VERSION 1
+#define SC_ABI_VERSION 2
 
 /* channel kinds (SPEC v0 a4) */
 #define SC_CH_NONE 0
 #define SC_CH_AWGN 1
 #define SC_CH_RAYLEIGH 2
+#define SC_CH_RICIAN 3   /* block Rician fading: h = sqrt(K/(K+1)) + sqrt(1/(K+1)) CN(0,1), MMSE-equalised like Rayleigh */
 
 /* activation ids for the GEMM epilogue */
 #define SC_ACT_NONE 0
@@ -164,16 +165,18 @@ int sc_colsum_bf16(const void* x, float* out, int64_t M, int N, int64_t ld, void
  * scale: fp32 [B,2] = rsqrt(mean z^2 + eps), saved for backward.
  * snr_db: device fp32 [B] or null (then snr_db_scalar is used).
  * noise / fading: optional explicit tensors (fp32 [B,2,k] / [B,2,2]) replacing the Philox draw.
- * y_f32 / y_bf16: either may be null.  Counter layout: see oracle/philox.py. */
+ * y_f32 / y_bf16: either may be null.  Counter layout: see oracle/philox.py.
+ * rician_k: linear K-factor of SC_CH_RICIAN (>= 0; ignored by the other kinds; K = 0 is Rayleigh).  An explicit
+ * `fading` tensor is the channel coefficient h itself for both fading kinds. */
 int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f32, void* y_bf16,
-                         int64_t y_sb, int64_t y_sm, float* scale, int64_t B, int k, int kind,
+                         int64_t y_sb, int64_t y_sm, float* scale, int64_t B, int k, int kind, float rician_k,
                          const float* snr_db, float snr_db_scalar, uint64_t seed,
                          int64_t sample_offset, const float* noise, const float* fading,
                          float eps, const uint64_t* seed_dev, void* stream);
-/* dz = scale * (g - zn * mean(g * zn)),  g = dy (AWGN/none) or |h|^2/(|h|^2+sigma^2) dy (Rayleigh) */
+/* dz = scale * (g - zn * mean(g * zn)),  g = dy (AWGN/none) or |h|^2/(|h|^2+sigma^2) dy (Rayleigh / Rician) */
 int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const float* z, int64_t z_sb,
                          int64_t z_sm, const float* scale, float* dz_f32, void* dz_bf16, int64_t B,
-                         int k, int kind, const float* snr_db, float snr_db_scalar, uint64_t seed,
+                         int k, int kind, float rician_k, const float* snr_db, float snr_db_scalar, uint64_t seed,
                          int64_t sample_offset, const float* fading, const uint64_t* seed_dev, void* stream);
 /* raw Philox words for parity tests: out u32 [n_quads,4], counters quad_offset.. */
 int sc_philox_words(uint32_t* out, int64_t n_quads, uint32_t stream_id, uint64_t seed,

@@ -12,7 +12,8 @@ import torch
 
 LIB_PATH = Path(__file__).resolve().parent / "libsemcom_sm100.so"
 
-SC_CH = {"none": 0, "awgn": 1, "rayleigh": 2}
+ABI_VERSION = 2          # SC_ABI_VERSION in include/semcom_sm100.h (2: rician_k argument of the channel entry points)
+SC_CH = {"none": 0, "awgn": 1, "rayleigh": 2, "rician": 3}
 SC_ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2}
 
 
@@ -66,9 +67,9 @@ _PROTOS = {
     "sc_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _F, _I, _P],
     "sc_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_colsum_bf16": [_P, _P, _I64, _I, _I64, _P],
-    "sc_pnorm_channel_fwd": [_P, _I64, _I64, _P, _P, _I64, _I64, _P, _I64, _I, _I, _P, _F, _U64, _I64,
+    "sc_pnorm_channel_fwd": [_P, _I64, _I64, _P, _P, _I64, _I64, _P, _I64, _I, _I, _F, _P, _F, _U64, _I64,
                              _P, _P, _F, _P, _P],
-    "sc_pnorm_channel_bwd": [_P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I64, _I, _I, _P, _F, _U64,
+    "sc_pnorm_channel_bwd": [_P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I64, _I, _I, _F, _P, _F, _U64,
                              _I64, _P, _P, _P],
     "sc_philox_words": [_P, _I64, _U32, _U64, _I64, _P],
     "sc_meanpool_fwd": [_P, _P, _P, _I64, _I, _I, _P],
@@ -120,6 +121,9 @@ def load() -> C.CDLL:
             continue
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.sc_version() != ABI_VERSION:   # a stale .so would be called with the wrong argument lists
+        raise SemcomError(f"{LIB_PATH.name} has ABI version {lib.sc_version()}, this package needs {ABI_VERSION}: "
+                          "rebuild with `python -m multimodal_sc_b200.build --force`")
     _lib = lib
     return lib
 

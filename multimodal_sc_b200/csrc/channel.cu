@@ -70,7 +70,7 @@ struct ChanArgs {
   const float* z; int64_t z_sb, z_sm;
   float* y_f32; bf16* y_bf16; int64_t y_sb, y_sm;
   float* scale;
-  int64_t B; int k; int kind;
+  int64_t B; int k; int kind; float rician_k;
   const float* snr_db; float snr_db_scalar;
   uint32_t key0, key1; int64_t sample_offset;
   const uint64_t* seed_dev;                                 // optional device-side addend to the seed (CUDA-graph replays)
@@ -90,14 +90,23 @@ __device__ __forceinline__ float sigma_of(const float* snr_db, float snr_scalar,
   const float s = snr_db ? snr_db[b] : snr_scalar;
   return exp10f(-s * 0.05f);
 }
+// channel coefficient of (sample b, modality m): explicit tensor, or CN(0,1) from Philox stream 1 (Rayleigh), or
+// sqrt(K/(K+1)) + sqrt(1/(K+1)) CN(0,1) (Rician, line of sight on the real axis; K = 0 is Rayleigh)
 __device__ __forceinline__ float2 fading_of(const float* fading, int64_t b, int m, int64_t sample_offset,
-                                            uint32_t k0, uint32_t k1) {
+                                            uint32_t k0, uint32_t k1, int kind, float rician_k) {
   if (fading) return make_float2(fading[(b * 2 + m) * 2], fading[(b * 2 + m) * 2 + 1]);
   const uint64_t j = static_cast<uint64_t>(sample_offset + b) * 2 + m;
   const uint4 w = philox4x32_10(make_uint4(static_cast<uint32_t>(j), 1u, static_cast<uint32_t>(j >> 32), 0u), k0, k1);
   float hr, hi;
   box_muller(w.x, w.y, hr, hi);
-  return make_float2(hr * 0.70710678118654752f, hi * 0.70710678118654752f);
+  hr *= 0.70710678118654752f;
+  hi *= 0.70710678118654752f;
+  if (kind == SC_CH_RICIAN) {
+    const float los = sqrtf(rician_k / (rician_k + 1.0f)), sc = sqrtf(1.0f / (rician_k + 1.0f));
+    hr = los + sc * hr;
+    hi = sc * hi;
+  }
+  return make_float2(hr, hi);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -125,8 +134,8 @@ pnorm_channel_fwd_kernel(const ChanArgs a) {
     if (threadIdx.x == 0 && a.scale) a.scale[row] = scale;
     float sigma = 0.f, hr = 1.f, hi = 0.f, inv_den = 1.f;
     if (a.kind != SC_CH_NONE) sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
-    if (a.kind == SC_CH_RAYLEIGH) {
-      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y);
+    if (a.kind >= SC_CH_RAYLEIGH) {
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y, a.kind, a.rician_k);
       hr = h.x; hi = h.y;
       inv_den = 1.0f / (hr * hr + hi * hi + sigma * sigma);
     }
@@ -165,7 +174,7 @@ struct ChanBwdArgs {
   const float* z; int64_t z_sb, z_sm;
   const float* scale;
   float* dz_f32; bf16* dz_bf16;
-  int64_t B; int k; int kind;
+  int64_t B; int k; int kind; float rician_k;
   const float* snr_db; float snr_db_scalar;
   uint32_t key0, key1; int64_t sample_offset;
   const uint64_t* seed_dev;
@@ -185,9 +194,9 @@ pnorm_channel_bwd_kernel(const ChanBwdArgs a) {
     const float* gr = a.dy + b * a.y_sb + m * a.y_sm;
     const float scale = a.scale[row];
     float gain = 1.f;
-    if (a.kind == SC_CH_RAYLEIGH) {
+    if (a.kind >= SC_CH_RAYLEIGH) {
       const float sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
-      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y);
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y, a.kind, a.rician_k);
       const float h2 = h.x * h.x + h.y * h.y;
       gain = h2 / (h2 + sigma * sigma);
     }
@@ -265,8 +274,8 @@ pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
     if (lane == 0 && a.scale) a.scale[row] = scale;
     float sigma = 0.f, hr = 1.f, hi = 0.f, inv_den = 1.f;
     if (a.kind != SC_CH_NONE) sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
-    if (a.kind == SC_CH_RAYLEIGH) {
-      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y);
+    if (a.kind >= SC_CH_RAYLEIGH) {
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y, a.kind, a.rician_k);
       hr = h.x; hi = h.y;
       inv_den = 1.0f / (hr * hr + hi * hi + sigma * sigma);
     }
@@ -315,9 +324,9 @@ pnorm_channel_bwd_warp_kernel(const ChanBwdArgs a) {
     const float* gr = a.dy + b * a.y_sb + m * a.y_sm;
     const float scale = a.scale[row];
     float gain = 1.f;
-    if (a.kind == SC_CH_RAYLEIGH) {
+    if (a.kind >= SC_CH_RAYLEIGH) {
       const float sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
-      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y);
+      const float2 h = fading_of(a.fading, b, m, a.sample_offset, key.x, key.y, a.kind, a.rician_k);
       const float h2 = h.x * h.x + h.y * h.y;
       gain = h2 / (h2 + sigma * sigma);
     }
@@ -353,7 +362,7 @@ pnorm_channel_bwd_warp_kernel(const ChanBwdArgs a) {
 int check_common(const char* nm, int64_t B, int k, int kind, int64_t sb, int64_t sm) {
   SC_REQUIRE(B > 0 && k > 0 && k % 4 == 0 && k <= kMaxV * kThreads * 4, SC_E_SHAPE,
              "%s: B=%lld k=%d (need k %% 4 == 0 and k <= %d)", nm, (long long)B, k, kMaxV * kThreads * 4);
-  SC_REQUIRE(kind >= SC_CH_NONE && kind <= SC_CH_RAYLEIGH, SC_E_SHAPE, "%s: unknown channel kind %d", nm, kind);
+  SC_REQUIRE(kind >= SC_CH_NONE && kind <= SC_CH_RICIAN, SC_E_SHAPE, "%s: unknown channel kind %d", nm, kind);
   SC_REQUIRE(sb % 4 == 0 && sm % 4 == 0, SC_E_ALIGN, "%s: strides must be multiples of 4 elements", nm);
   return SC_OK;
 }
@@ -363,13 +372,15 @@ int check_common(const char* nm, int64_t B, int k, int kind, int64_t sb, int64_t
 extern "C" {
 
 int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f32, void* y_bf16, int64_t y_sb,
-                         int64_t y_sm, float* scale, int64_t B, int k, int kind, const float* snr_db,
+                         int64_t y_sm, float* scale, int64_t B, int k, int kind, float rician_k,
+                         const float* snr_db,
                          float snr_db_scalar, uint64_t seed, int64_t sample_offset, const float* noise,
                          const float* fading, float eps, const uint64_t* seed_dev, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(z && (y_f32 || y_bf16), SC_E_SHAPE, "sc_pnorm_channel_fwd: null pointer");
   if ((rc = check_common("sc_pnorm_channel_fwd", B, k, kind, z_sb, z_sm)) != SC_OK) return rc;
+  SC_REQUIRE(kind != SC_CH_RICIAN || rician_k >= 0.f, SC_E_SHAPE, "sc_pnorm_channel_fwd: rician_k must be >= 0");
   if ((rc = check_common("sc_pnorm_channel_fwd", B, k, kind, y_sb, y_sm)) != SC_OK) return rc;
   SC_REQUIRE(sc_aligned16(z) && sc_aligned16(y_f32) && sc_aligned16(noise) &&
                  (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
@@ -377,7 +388,7 @@ int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f3
   ChanArgs a;
   a.z = z; a.z_sb = z_sb; a.z_sm = z_sm;
   a.y_f32 = y_f32; a.y_bf16 = (bf16*)y_bf16; a.y_sb = y_sb; a.y_sm = y_sm;
-  a.scale = scale; a.B = B; a.k = k; a.kind = kind;
+  a.scale = scale; a.B = B; a.k = k; a.kind = kind; a.rician_k = rician_k;
   a.snr_db = snr_db; a.snr_db_scalar = snr_db_scalar;
   a.key0 = (uint32_t)(seed & 0xffffffffu); a.key1 = (uint32_t)(seed >> 32);
   a.sample_offset = sample_offset; a.noise = noise; a.fading = fading; a.eps = eps; a.seed_dev = seed_dev;
@@ -398,20 +409,21 @@ int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f3
 }
 
 int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const float* z, int64_t z_sb, int64_t z_sm,
-                         const float* scale, float* dz_f32, void* dz_bf16, int64_t B, int k, int kind,
+                         const float* scale, float* dz_f32, void* dz_bf16, int64_t B, int k, int kind, float rician_k,
                          const float* snr_db, float snr_db_scalar, uint64_t seed, int64_t sample_offset,
                          const float* fading, const uint64_t* seed_dev, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(dy && z && scale && (dz_f32 || dz_bf16), SC_E_SHAPE, "sc_pnorm_channel_bwd: null pointer");
   if ((rc = check_common("sc_pnorm_channel_bwd", B, k, kind, z_sb, z_sm)) != SC_OK) return rc;
+  SC_REQUIRE(kind != SC_CH_RICIAN || rician_k >= 0.f, SC_E_SHAPE, "sc_pnorm_channel_bwd: rician_k must be >= 0");
   if ((rc = check_common("sc_pnorm_channel_bwd", B, k, kind, y_sb, y_sm)) != SC_OK) return rc;
   SC_REQUIRE(sc_aligned16(dy) && sc_aligned16(z) && sc_aligned16(dz_f32) &&
                  (reinterpret_cast<uintptr_t>(dz_bf16) & 7) == 0,
              SC_E_ALIGN, "sc_pnorm_channel_bwd: unaligned pointer");
   ChanBwdArgs a;
   a.dy = dy; a.y_sb = y_sb; a.y_sm = y_sm; a.z = z; a.z_sb = z_sb; a.z_sm = z_sm; a.scale = scale;
-  a.dz_f32 = dz_f32; a.dz_bf16 = (bf16*)dz_bf16; a.B = B; a.k = k; a.kind = kind;
+  a.dz_f32 = dz_f32; a.dz_bf16 = (bf16*)dz_bf16; a.B = B; a.k = k; a.kind = kind; a.rician_k = rician_k;
   a.snr_db = snr_db; a.snr_db_scalar = snr_db_scalar;
   a.key0 = (uint32_t)(seed & 0xffffffffu); a.key1 = (uint32_t)(seed >> 32);
   a.sample_offset = sample_offset; a.fading = fading; a.seed_dev = seed_dev;

@@ -2,7 +2,7 @@
 
 Drop-in for the oracle's `nn.Module` API (upstream /root/reference/README.md:1-2
 has no code, so the API is the one `oracle/model.py` fixes): same constructor, same
-`forward(cam, bev, snr_db, *, channel, seed, noise, fading, sample_offset) -> (logits, value, aux)`,
+`forward(cam, bev, snr_db, *, channel, seed, noise, fading, sample_offset, rician_k) -> (logits, value, aux)`,
 same `act()`, same `state_dict()` keys and shapes.
 
 B200-first layout instead of a module-per-layer autograd graph:
@@ -147,6 +147,7 @@ class Engine:
         self.fused_mlp = os.environ.get("SC_FUSED_MLP", "1") != "0"
         # SC_FUSED_LN=0: every LayerNorm forward is its own kernel instead of a GEMM epilogue
         self.fused_ln = os.environ.get("SC_FUSED_LN", "1") != "0"
+        self.rician_k = spec.rician_k          # K-factor used when channel == "rician" (SemComPolicy.forward may override)
         # SC_WGRAD_STREAM=1: the four weight-gradient GEMMs of every block run on a second stream, so the HBM-bound
         # LayerNorm-backward kernels of the dgrad chain (no shared memory, no TMEM) co-run with them and the tail of
         # one GEMM-class kernel overlaps the ramp-up of the next.  Block-parity scratch sets + events keep it race-free.
@@ -324,7 +325,7 @@ class Engine:
         y16 = A.buf("y16", (B, 2, k_sym))
         y32 = A.buf("y32", (B, 2, k_sym), F32) if want_aux else None
         scale = A.buf("scale", (B, 2), F32)
-        ops.pnorm_channel_fwd(z_mm, channel, snr_db, seed=seed or 0, sample_offset=sample_offset, noise=noise,
+        ops.pnorm_channel_fwd(z_mm, channel, snr_db, rician_k=self.rician_k, seed=seed or 0, sample_offset=sample_offset, noise=noise,
                               fading=fading, eps=sp.pnorm_eps, y_f32=y32, y_bf16=y16, scale=scale,
                               z_strides=(k_sym, B * k_sym, B, k_sym), seed_dev=seed_dev)
         # ---- decoder ----
@@ -398,7 +399,7 @@ class Engine:
             grad_ready("dec")
         # channel
         dz_mm = A.buf("dz_mm", (2, B, sp.k_sym))
-        ops.pnorm_channel_bwd(dy, A["z_mm"], A["scale"], channel, snr_db, seed=seed or 0,
+        ops.pnorm_channel_bwd(dy, A["z_mm"], A["scale"], channel, snr_db, rician_k=self.rician_k, seed=seed or 0,
                               sample_offset=sample_offset, fading=fading, dz_bf16=dz_mm,
                               z_strides=(sp.k_sym, B * sp.k_sym, B, sp.k_sym), seed_dev=seed_dev)
         # encoders
@@ -440,6 +441,7 @@ class _PolicyFn(torch.autograd.Function):
     def forward(ctx, policy, cam, bev, kw, *params):
         eng = policy.engine
         B = cam.shape[0]
+        eng.rician_k = kw["rician_k"]
         ho, A = eng.forward(cam, bev, kw["snr_db"], kw["channel"], kw["seed"], kw["noise"], kw["fading"],
                             kw["sample_offset"], train=True, want_aux=True)
         lsem = torch.zeros(1, device=cam.device)
@@ -454,6 +456,7 @@ class _PolicyFn(torch.autograd.Function):
         saved = flat.g32
         flat.g32 = torch.zeros_like(saved)                  # scratch bucket for this backward
         try:
+            eng.rician_k = kw["rician_k"]
             eng.l_sem(A, B, torch.zeros(1, device=dho.device), grad_coef=float(dlsem))
             eng.backward(A, B, dho.contiguous().float(), None, kw["channel"], kw["snr_db"], kw["seed"],
                          kw["fading"], kw["sample_offset"])
@@ -490,23 +493,26 @@ class SemComPolicy(nn.Module):
         self.sync()
         return r
 
-    def _kw(self, snr_db, channel, seed, noise, fading, sample_offset):
+    def _kw(self, snr_db, channel, seed, noise, fading, sample_offset, rician_k=None):
+        if channel not in ("none", "awgn", "rayleigh", "rician"):
+            raise ValueError(f"unknown channel kind {channel!r}")
         if channel != "none" and seed is None and noise is None:
             raise ValueError("channel needs seed= or noise=")
-        if channel == "rayleigh" and seed is None and fading is None:
-            raise ValueError("rayleigh channel needs seed= or fading=")
+        if channel in ("rayleigh", "rician") and seed is None and fading is None:
+            raise ValueError(f"{channel} channel needs seed= or fading=")
         if torch.is_tensor(snr_db):
             snr_db = snr_db.to(self.device, F32).contiguous()
             if snr_db.dim() == 0:
                 snr_db = float(snr_db)
         return dict(snr_db=snr_db, channel=channel, seed=seed,
+                    rician_k=self.spec.rician_k if rician_k is None else float(rician_k),
                     noise=None if noise is None else noise.to(self.device, F32).contiguous(),
                     fading=None if fading is None else fading.to(self.device, F32).contiguous(),
                     sample_offset=sample_offset)
 
     def forward(self, cam, bev, snr_db, *, channel: str = "awgn", seed=None, noise=None, fading=None,
-                sample_offset: int = 0):
-        kw = self._kw(snr_db, channel, seed, noise, fading, sample_offset)
+                sample_offset: int = 0, rician_k=None):
+        kw = self._kw(snr_db, channel, seed, noise, fading, sample_offset, rician_k)
         # observations may be fp32 or bf16 (the first kernel casts to bf16 either way)
         cam = cam.to(self.device, cam.dtype if cam.dtype == BF16 else F32).contiguous()
         bev = bev.to(self.device, bev.dtype if bev.dtype == BF16 else F32).contiguous()
@@ -515,6 +521,7 @@ class SemComPolicy(nn.Module):
             ho, lsem = _PolicyFn.apply(self, cam, bev, kw, *self.parameters())
             arena = self.engine.arena(B)
         else:
+            self.engine.rician_k = kw["rician_k"]
             ho, arena = self.engine.forward(cam, bev, kw["snr_db"], channel, seed, kw["noise"], kw["fading"],
                                             sample_offset, train=False, want_aux=True)
             ho = ho.clone()

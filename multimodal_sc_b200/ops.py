@@ -239,7 +239,8 @@ def colsum(x, out):
 
 @_profiled("pnorm_channel_fwd")
 def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, fading=None, eps=1e-12,
-                      y_f32=None, y_bf16=None, scale=None, z_strides=None, y_strides=None, seed_dev=None):
+                      y_f32=None, y_bf16=None, scale=None, z_strides=None, y_strides=None, seed_dev=None,
+                      rician_k=0.0):
     """z fp32 logical [B,2,k] addressed with z_strides=(sb, sm) (default: contiguous [B,2,k]).
     `seed_dev` (device int64 [1], optional) is added to `seed` inside the kernel (CUDA-graph replays).
     Returns (y_f32, y_bf16, scale)."""
@@ -262,7 +263,7 @@ def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, f
         assert snr_t.dtype == F32 and snr_t.numel() == B and snr_t.is_cuda
     check(_lib.load().sc_pnorm_channel_fwd(ptr(z), z_strides[0], z_strides[1], ptr(y_f32), ptr(y_bf16),
                                            y_strides[0], y_strides[1], ptr(scale), B, k, SC_CH[kind],
-                                           ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1), sample_offset,
+                                           float(rician_k), ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1), sample_offset,
                                            ptr(noise), ptr(fading), eps, ptr(seed_dev), stream_ptr()),
           "sc_pnorm_channel_fwd")
     return y_f32, y_bf16, scale
@@ -270,7 +271,7 @@ def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, f
 
 @_profiled("pnorm_channel_bwd")
 def pnorm_channel_bwd(dy, z, scale, kind, snr_db, *, seed=0, sample_offset=0, fading=None, dz_f32=None,
-                      dz_bf16=None, z_strides=None, y_strides=None, seed_dev=None):
+                      dz_bf16=None, z_strides=None, y_strides=None, seed_dev=None, rician_k=0.0):
     _cuda(dy, z, scale)
     assert dy.dtype == F32 and z.dtype == F32
     if z_strides is None:
@@ -286,7 +287,7 @@ def pnorm_channel_bwd(dy, z, scale, kind, snr_db, *, seed=0, sample_offset=0, fa
     snr_t, snr_s = (snr_db, 0.0) if torch.is_tensor(snr_db) else (None, float(snr_db))
     check(_lib.load().sc_pnorm_channel_bwd(ptr(dy), y_strides[0], y_strides[1], ptr(z), z_strides[0],
                                            z_strides[1], ptr(scale), ptr(dz_f32), ptr(dz_bf16), B, k,
-                                           SC_CH[kind], ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1),
+                                           SC_CH[kind], float(rician_k), ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1),
                                            sample_offset, ptr(fading), ptr(seed_dev), stream_ptr()),
           "sc_pnorm_channel_bwd")
     return dz_f32, dz_bf16

@@ -41,6 +41,7 @@ class SpecV0:
     init_std: float = 0.02
     # channel
     pnorm_eps: float = 1e-12
+    rician_k: float = 4.0          # linear K-factor (6 dB) of the "rician" channel kind
     # PPO
     gamma: float = 0.99
     lam: float = 0.95

@@ -60,9 +60,21 @@ def rayleigh(zn: torch.Tensor, sigma: torch.Tensor, noise: torch.Tensor,
     return torch.stack([yr, yi], dim=-1).reshape(B, M, k)
 
 
+def rician_fading(h0: torch.Tensor, k_factor: float) -> torch.Tensor:
+    """CN(0,1) block-fading draws h0[B,2,2] -> Rician coefficients with linear K-factor `k_factor`:
+    h = sqrt(K/(K+1)) + sqrt(1/(K+1)) h0 (line of sight on the real axis, E|h|^2 = 1).  K = 0 returns h0 (Rayleigh).
+    SURVEY.md §8f rank 3; no upstream code exists (/root/reference/README.md:1-2)."""
+    k = torch.tensor(float(k_factor), dtype=torch.float32)
+    los, sc = torch.sqrt(k / (k + 1.0)), torch.sqrt(1.0 / (k + 1.0))
+    h = h0.to(torch.float32) * sc
+    h = torch.stack([h[..., 0] + los, h[..., 1]], dim=-1)
+    return h.to(h0.dtype)
+
+
 def channel_forward(z: torch.Tensor, snr_db, kind: str, *, seed=None, noise=None, fading=None,
-                    sample_offset: int = 0, eps: float = 1e-12):
-    """z[B,2,k] -> (y[B,2,k], zn).  kind in {"awgn", "rayleigh", "none"}."""
+                    sample_offset: int = 0, eps: float = 1e-12, rician_k: float = 4.0):
+    """z[B,2,k] -> (y[B,2,k], zn).  kind in {"awgn", "rayleigh", "rician", "none"}.  An explicit `fading` tensor is the
+    channel coefficient h itself for both fading kinds."""
     B, M, k = z.shape
     zn = power_normalize(z, eps)
     if kind == "none":
@@ -79,6 +91,12 @@ def channel_forward(z: torch.Tensor, snr_db, kind: str, *, seed=None, noise=None
             if seed is None:
                 raise ValueError("rayleigh channel needs seed= or fading=")
             fading = make_fading(seed, B, sample_offset).to(z.device)
+        return rayleigh(zn, sigma, noise, fading), zn
+    if kind == "rician":                                      # same receiver, line-of-sight component added to h
+        if fading is None:
+            if seed is None:
+                raise ValueError("rician channel needs seed= or fading=")
+            fading = rician_fading(make_fading(seed, B, sample_offset), rician_k).to(z.device)
         return rayleigh(zn, sigma, noise, fading), zn
     raise ValueError(f"unknown channel kind {kind!r}")
 

@@ -165,12 +165,13 @@ class SemComPolicy(nn.Module):
                     p.copy_(w * std)
 
     def forward(self, cam, bev, snr_db, *, channel: str = "awgn", seed=None, noise=None,
-                fading=None, sample_offset: int = 0):
+                fading=None, sample_offset: int = 0, rician_k=None):
         z_c, t_c = self.cam_enc(cam)
         z_b, t_b = self.bev_enc(bev)
         z = torch.stack([z_c, z_b], dim=1)                  # [B,2,k]
         y, zn = ch.channel_forward(z, snr_db, channel, seed=seed, noise=noise, fading=fading,
-                                   sample_offset=sample_offset, eps=self.spec.pnorm_eps)
+                                   sample_offset=sample_offset, eps=self.spec.pnorm_eps,
+                                   rician_k=self.spec.rician_k if rician_k is None else rician_k)
         f, recon = self.dec(y)
         logits, value = self.ac(f)
         l_sem = semantic_distortion(recon, torch.cat([t_c, t_b], dim=1))

@@ -44,7 +44,7 @@ def test_philox_words_bit_exact(cuda_lib):
         assert np.array_equal(got, ref), (seed, stream, off)
 
 
-@pytest.mark.parametrize("kind", ["none", "awgn", "rayleigh"])
+@pytest.mark.parametrize("kind", ["none", "awgn", "rayleigh", "rician"])
 @pytest.mark.parametrize("B,off", [(1, 0), (7, 3), (64, 100000)])
 def test_pnorm_channel_fwd_bwd_philox(cuda_lib, kind, B, off):
     from multimodal_sc_b200 import ops
@@ -56,12 +56,13 @@ def test_pnorm_channel_fwd_bwd_philox(cuda_lib, kind, B, off):
     seed = 1234
     # oracle
     zr = z.clone().requires_grad_(True)
-    y_ref, zn_ref = och.channel_forward(zr, snr, kind, seed=seed, sample_offset=off)
+    rk = 2.5                                                  # Rician K-factor (ignored by the other kinds)
+    y_ref, zn_ref = och.channel_forward(zr, snr, kind, seed=seed, sample_offset=off, rician_k=rk)
     (y_ref * dy).sum().backward()
     # native
     zc, dyc, snrc = z.cuda(), dy.cuda(), snr.cuda()
-    y, _, scale = ops.pnorm_channel_fwd(zc, kind, snrc, seed=seed, sample_offset=off)
-    dz, _ = ops.pnorm_channel_bwd(dyc, zc, scale, kind, snrc, seed=seed, sample_offset=off)
+    y, _, scale = ops.pnorm_channel_fwd(zc, kind, snrc, seed=seed, sample_offset=off, rician_k=rk)
+    dz, _ = ops.pnorm_channel_bwd(dyc, zc, scale, kind, snrc, seed=seed, sample_offset=off, rician_k=rk)
     _close(y, y_ref, 1e-5, 2e-5, f"y {kind}")
     _close(dz, zr.grad, 1e-5, 2e-5, f"dz {kind}")
     ref_scale = torch.rsqrt(z.pow(2).mean(-1) + SPEC.pnorm_eps)
@@ -84,6 +85,23 @@ def test_pnorm_channel_explicit_noise_and_strides(cuda_lib):
                           z_strides=(k, B * k, B, k))
     _close(yf, y_ref, 1e-5, 2e-5, "rayleigh explicit")
     _close_scaled(yb, y_ref, 1e-2, "rayleigh bf16")
+
+
+def test_rician_k0_is_rayleigh_and_large_k_is_awgn_like(cuda_lib):
+    """K = 0 reproduces the Rayleigh outputs bit for bit (0 + 1 * h); K -> inf is a unit-gain channel whose MMSE
+    output is zn / (1 + sigma^2) + noise term, i.e. the AWGN output scaled by 1 / (1 + sigma^2)."""
+    from multimodal_sc_b200 import ops
+    B, k = 9, SPEC.k_sym
+    z = (torch.randn(B, 2, k, generator=torch.Generator().manual_seed(4)) * 0.7).cuda()
+    y_ray, _, _ = ops.pnorm_channel_fwd(z, "rayleigh", 5.0, seed=77)
+    y_k0, _, _ = ops.pnorm_channel_fwd(z, "rician", 5.0, seed=77, rician_k=0.0)
+    assert torch.equal(y_ray, y_k0)
+    y_awgn, _, _ = ops.pnorm_channel_fwd(z, "awgn", 5.0, seed=77)
+    y_inf, _, _ = ops.pnorm_channel_fwd(z, "rician", 5.0, seed=77, rician_k=1e12)
+    sigma2 = 10.0 ** (-0.5)
+    _close(y_inf, y_awgn / (1.0 + sigma2), 1e-4, 1e-5, "rician K=inf vs awgn")
+    with pytest.raises(Exception):
+        ops.pnorm_channel_fwd(z, "rician", 5.0, seed=77, rician_k=-1.0)
 
 
 def test_channel_unit_power_and_snr(cuda_lib):

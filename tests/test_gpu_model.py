@@ -52,7 +52,7 @@ def test_state_dict_roundtrip(cuda_lib):
     o2.load_state_dict({k: v.cpu() for k, v in sd_n.items()})     # loads back the other way
 
 
-@pytest.mark.parametrize("channel,B", [("awgn", 4), ("rayleigh", 3), ("none", 2)])
+@pytest.mark.parametrize("channel,B", [("awgn", 4), ("rayleigh", 3), ("rician", 3), ("none", 2)])
 def test_forward_parity(cuda_lib, channel, B):
     o, n = _pair()
     cam, bev = _inputs(B)

@@ -62,7 +62,27 @@ def test_channel_invariants():
     assert torch.equal(y, och.power_normalize(z))
 
 
-@pytest.mark.parametrize("kind", ["awgn", "rayleigh"])
+def test_rician_channel_pins():
+    """h = sqrt(K/(K+1)) + sqrt(1/(K+1)) CN(0,1).  E|h|^2 = 1 for every K, the mean of h is the
+    line-of-sight term, K = 0 is the Rayleigh draw itself, and with no noise the MMSE receiver inverts h exactly."""
+    h0 = och.make_fading(11, 200000)
+    assert torch.equal(och.rician_fading(h0, 0.0), h0)
+    for K in (0.5, 4.0, 30.0):
+        h = och.rician_fading(h0, K)
+        assert abs(float(h.pow(2).sum(-1).mean()) - 1.0) < 5e-3
+        assert abs(float(h[..., 0].mean()) - (K / (K + 1)) ** 0.5) < 5e-3 and abs(float(h[..., 1].mean())) < 5e-3
+        assert abs(float(h[..., 1].var()) - 0.5 / (K + 1)) < 5e-3
+    z = torch.randn(16, 2, SPEC.k_sym)
+    y, zn = och.channel_forward(z, 300.0, "rician", seed=3, rician_k=4.0)
+    assert torch.allclose(y, zn, atol=1e-4)
+    y0, _ = och.channel_forward(z, 7.0, "rician", seed=3, rician_k=0.0)
+    yr, _ = och.channel_forward(z, 7.0, "rayleigh", seed=3)
+    assert torch.equal(y0, yr)
+    with pytest.raises(ValueError):
+        och.channel_forward(z, 10.0, "rician")
+
+
+@pytest.mark.parametrize("kind", ["awgn", "rayleigh", "rician"])
 def test_channel_gradcheck_fp64(kind):
     z = torch.randn(2, 2, 8, dtype=torch.float64, requires_grad=True)
     noise = torch.randn(2, 2, 8, dtype=torch.float64)
