@@ -45,8 +45,11 @@ template <int CTA2, int NWG, int SLOTS> struct Geo {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING = NWG * 4 * SLOTS * EPI_SLOT_BYTES;
   // one bias tile per warpgroup; the 1-warpgroup / 4-slot geometry also parks LayerNorm gamma and beta (fused LN)
-  static constexpr int LN_TILES = (NWG == 1 && SLOTS == 4 && !CTA2) ? 2 : 0;
-  static constexpr int BIAS = (NWG + LN_TILES) * BIAS_TILE_BYTES;
+  // (the 2-warpgroup / 2-slot geometry runs the fused LayerNorm with the row split between the warpgroups: columns
+  //  0-127 / 128-255, partial row statistics exchanged through LN_XCHG bytes of shared memory, double-buffered by tile)
+  static constexpr int LN_TILES = (!CTA2 && ((NWG == 1 && SLOTS == 4) || (NWG == 2 && SLOTS == 2))) ? 2 : 0;
+  static constexpr int LN_XCHG = (!CTA2 && NWG == 2 && SLOTS == 2) ? 2 * 2 * BM * 8 : 0;
+  static constexpr int BIAS = (NWG + LN_TILES) * BIAS_TILE_BYTES + LN_XCHG;
   static constexpr int STAGES_FIT = (SMEM_LIMIT - STATIC_SMEM_RESERVE - RING - BIAS) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int SMEM = STAGES * STAGE_BYTES;
@@ -119,6 +122,7 @@ struct GemmParams {
   //   256 = L2 prefetch of upcoming operand tiles (results stay correct; measured slower)
   int dbg;
   int reverse;                  // 1 = items (and the k-blocks of a split-K item) are walked in descending order
+  int ln_split;                 // fused LayerNorm with the row split between two epilogue warpgroups (NWG = 2, SLOTS = 2)
 };
 
 struct Item {
@@ -598,6 +602,139 @@ __device__ __forceinline__ void staged_tile_ln(const GemmParams& p, const CUtens
   }
 }
 
+// Fused LayerNorm with the row split between two epilogue warpgroups (2 slots per warp): warpgroup `half` owns columns
+// half*128 .. +127 of every row, i.e. chunks 2*half, 2*half+1 and the 16-column steps 8*half .. +7.  Pass 1 as in
+// staged_tile_ln over the own half; the partial (sum x, sum x^2) of a row are exchanged with the partner warp (same TMEM
+// lane quarter, other warpgroup) through `xchg` (double-buffered by tile parity) around a 64-thread named barrier; pass 2
+// normalises the own half.  One warpgroup needed ~9 us per 128x256 tile (one warp per scheduler, dependency-bound),
+// which kept the K = 256 residual GEMMs below their HBM bound.
+__device__ __forceinline__ void staged_tile_ln_split(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmLn,
+                                                     const CUtensorMap* tmIn, uint32_t t_addr, uint32_t ring, uint32_t in_bar0,
+                                                     uint32_t bias_tile, uint32_t gamma_tile, uint32_t beta_tile, uint32_t xchg,
+                                                     int lane, int half, int quarter, int row0, int64_t row, bool row_ok,
+                                                     uint32_t tile_parity, const NextTile& next) {
+  const bool no_tma = (p.dbg & 2) != 0;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  const int sbase = half * 8, cbase = half * 2;
+  auto lds4 = [&](uint32_t addr) {
+    const uint4 w = ld_shared_v4(addr);
+    return make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+  };
+  uint32_t v[2][16];
+  float4 bv[2][4];
+  uint64_t s1 = pk2(0.f, 0.f), s2 = s1;
+  auto issue = [&](int sl, uint32_t (&vv)[16], float4 (&bb)[4]) {        // sl: local step 0..7
+    const int s = sbase + sl;
+    tmem_ld_32x32b_x16(t_addr + s * 16, vv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bb[q] = lds4(bias_tile + s * 64 + q * 16);
+  };
+  auto pass1 = [&](int sl, const uint32_t (&vv)[16], const float4 (&bb)[4]) {
+    const int c = sl >> 2, h = sl & 3;                                   // local chunk (slot) and 16-column group in it
+    const uint32_t row_o = ring + c * EPI_SLOT_BYTES + lane * 128;
+    const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+    uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
+    if (!no_tma) {
+      i0 = ld_shared_v4(row_o + pa);
+      i1 = ld_shared_v4(row_o + pb);
+    }
+    const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = bb[j >> 1];
+      uint64_t x = add2(pk2u(vv[2 * j], vv[2 * j + 1]), (j & 1) ? pk2(b.z, b.w) : pk2(b.x, b.y));
+      x = add2(x, unpack2_bf16(iw[j]));
+      o[j] = pack2_bf16(x);
+      const uint64_t xr = unpack2_bf16(o[j]);
+      s1 = add2(s1, xr);
+      s2 = fma2(xr, xr, s2);
+    }
+    st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
+    st_shared_v4(row_o + pb, o[4], o[5], o[6], o[7]);
+  };
+  issue(0, v[0], bv[0]);
+#pragma unroll 1
+  for (int sl = 0; sl < 8; sl += 2) {
+    if ((sl & 3) == 0) {
+      if (!no_tma) mbar_wait(in_bar0 + (sl >> 2) * 8, tile_parity);
+      __syncwarp();
+    }
+    tmem_ld_wait();
+    issue(sl + 1, v[1], bv[1]);
+    pass1(sl, v[0], bv[0]);
+    tmem_ld_wait();
+    if (sl + 2 < 8) issue(sl + 2, v[0], bv[0]);
+    pass1(sl + 1, v[1], bv[1]);
+    if ((sl & 3) == 2) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && !no_tma) {
+        tma_store_2d(tmOut, ring + (sl >> 2) * EPI_SLOT_BYTES, (cbase + (sl >> 2)) * 64, row0);
+        tma_store_commit();
+      }
+    }
+  }
+  // exchange the partial row statistics with the warp that owns the other half of these 32 rows
+  float a0, a1, q0, q1;
+  upk2(s1, a0, a1);
+  upk2(s2, q0, q1);
+  const uint32_t xb = xchg + tile_parity * (2 * BM * 8);
+  const int r = quarter * 32 + lane;
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xb + (half * BM + r) * 8), "f"(a0 + a1), "f"(q0 + q1) : "memory");
+  named_bar_sync(3 + quarter, 64);
+  float o0, o1;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o0), "=f"(o1) : "r"(xb + ((half ^ 1) * BM + r) * 8) : "memory");
+  // both halves add in the same order (half 0 first) so the two warps normalise with bit-identical statistics
+  const float sum = half == 0 ? (a0 + a1) + o0 : o0 + (a0 + a1);
+  const float sq = half == 0 ? (q0 + q1) + o1 : o1 + (q0 + q1);
+  const float mean = sum * (1.0f / BN);
+  const float var = fmaxf(sq * (1.0f / BN) - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + p.ln_eps);
+  if (row_ok && half == 0) {
+    if (p.ln_mean) p.ln_mean[row] = mean;
+    if (p.ln_rstd) p.ln_rstd[row] = rstd;
+  }
+  const uint64_t rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    if (lane == 0) tma_store_wait_read<1>();                   // the x store of local chunk c has read the slot
+    __syncwarp();
+    const uint32_t row_o = ring + c * EPI_SLOT_BYTES + lane * 128;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int s = sbase + c * 4 + h;
+      const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+      const uint4 i0 = ld_shared_v4(row_o + pa), i1 = ld_shared_v4(row_o + pb);
+      const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+      uint32_t o[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 g = lds4(gamma_tile + s * 64 + q * 16), b = lds4(beta_tile + s * 64 + q * 16);
+        o[2 * q] = pack2_bf16(fma2(fma2(unpack2_bf16(iw[2 * q]), rs2, nm2), pk2(g.x, g.y), pk2(b.x, b.y)));
+        o[2 * q + 1] = pack2_bf16(fma2(fma2(unpack2_bf16(iw[2 * q + 1]), rs2, nm2), pk2(g.z, g.w), pk2(b.z, b.w)));
+      }
+      st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
+      st_shared_v4(row_o + pb, o[4], o[5], o[6], o[7]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && !no_tma) {
+      tma_store_2d(tmLn, ring + c * EPI_SLOT_BYTES, (cbase + c) * 64, row0);
+      tma_store_commit();
+    }
+  }
+  // both slots are free once the LayerNorm stores have read them: the next tile's residual chunks of this half
+  if (lane == 0 && !no_tma && next.valid) {
+    tma_store_wait_read<0>();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      mbar_arrive_expect_tx(in_bar0 + c * 8, EPI_SLOT_BYTES);
+      tma_load_2d(ring + c * EPI_SLOT_BYTES, tmIn, in_bar0 + c * 8, next.n0 + (cbase + c) * 64, next.in_row0);
+    }
+  }
+}
+
 template <int A_MN, int B_MN, int CTA2, int NWG, int SLOTS>
 __global__ void __launch_bounds__(128 + NWG * 128, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -632,7 +769,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[s]), 128 * ncta);   // pair: both CTAs' epilogue warpgroups arrive on the leader's
+      // pair: both CTAs' epilogue warpgroups arrive on the leader's; split LayerNorm: both warpgroups drain every tile
+      mbar_init(smem_u32(&tmem_empty_bar[s]), 128 * ncta * (p.ln_split ? 2 : 1));
     }
     for (int w = 0; w < MAX_EPI_WARPS; ++w)
       for (int s = 0; s < MAX_SLOTS; ++s) mbar_init(smem_u32(&epi_in_bar[w][s]), 1);
@@ -869,8 +1007,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int wg = ew >> 2;
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int stride2 = NWG * cta_stride;
-    const int first = cta_first + wg * cta_stride;
+    // split LayerNorm: the two warpgroups work on the SAME tile (columns 0-127 / 128-255) instead of alternate tiles
+    const bool ln_split = (NWG == 2 && SLOTS == 2 && !CTA2) && p.ln_split != 0;
+    const int stride2 = ln_split ? cta_stride : NWG * cta_stride;
+    const int first = ln_split ? cta_first : cta_first + wg * cta_stride;
     // pair: the leader's MMA thread waits for BOTH CTAs' epilogues -> arrive on the leader's barrier
     auto release_acc = [&](int as) {
       const uint32_t local = smem_u32(&tmem_empty_bar[as]);
@@ -943,12 +1083,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int c = 0; c < PRE; ++c) {
           mbar_arrive_expect_tx(ib0 + c * 8, EPI_SLOT_BYTES);
-          tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib0 + c * 8, it.n_blk * BN + c * 64, in_row(it.m_blk * BM + q * 32));
+          tma_load_2d(ring + c * EPI_SLOT_BYTES, &tmIn, ib0 + c * 8, it.n_blk * BN + c * 64 + (ln_split ? wg * 128 : 0),
+                      in_row(it.m_blk * BM + q * 32));
         }
       }
-      int n = wg;
+      int n = ln_split ? 0 : wg;
       uint32_t tile_parity = 0;
-      for (int item = first; item < num_items; item += stride2, n += NWG, tile_parity ^= 1u) {
+      for (int item = first; item < num_items; item += stride2, n += (ln_split ? 1 : NWG), tile_parity ^= 1u) {
         const Item it = get_item(item);
         const int as = n & 1;
         const uint32_t t_addr = t_lane + static_cast<uint32_t>(as * BN);
@@ -994,8 +1135,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           case KIND_RESID_LN:
             if constexpr (G::LN_TILES != 0) {
               const uint32_t ln_base = smem_base + G::SMEM + G::RING + NWG * BIAS_TILE_BYTES;
-              staged_tile_ln(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, bias_tile, ln_base, ln_base + BIAS_TILE_BYTES, lane,
-                             row0, static_cast<int64_t>(row0) + lane, static_cast<int64_t>(row0) + lane < p.M, tile_parity, next);
+              if constexpr (G::LN_XCHG != 0) {
+                if (ln_split)
+                  staged_tile_ln_split(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, bias_tile, ln_base, ln_base + BIAS_TILE_BYTES,
+                                       ln_base + 2 * BIAS_TILE_BYTES, lane, wg, q, row0, static_cast<int64_t>(row0) + lane,
+                                       static_cast<int64_t>(row0) + lane < p.M, tile_parity, next);
+              } else {
+                staged_tile_ln(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, bias_tile, ln_base, ln_base + BIAS_TILE_BYTES, lane,
+                               row0, static_cast<int64_t>(row0) + lane, static_cast<int64_t>(row0) + lane < p.M, tile_parity, next);
+              }
             }
             break;
           default:         SC_TILE(KIND_GEN); break;
@@ -1005,7 +1153,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         release_acc(as);
         // input chunks of this warp's next tile that could not be requested inside the tile: the slots are free once
         // the stores that read them have drained
-        if (has_in && lane == 0 && next.valid) {
+        if (has_in && lane == 0 && next.valid && !ln_split) {
           tma_store_wait_read<0>();
 #pragma unroll
           for (int c = (SLOTS == 4 ? 3 : 0); c < PRE; ++c) {
@@ -1029,7 +1177,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 struct DebugOverrides {
   int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0,
-          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 0;
+          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 0, ln_split = 1;
 };
 DebugOverrides g_dbg;
 
@@ -1101,6 +1249,7 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "cta2")) g_dbg.cta2 = value;
   else if (!strcmp(key, "cta2_wgrad")) g_dbg.cta2_wgrad = value;
   else if (!strcmp(key, "cta2_mink")) g_dbg.cta2_mink = value;
+  else if (!strcmp(key, "ln_split")) g_dbg.ln_split = value;
   else if (!strcmp(key, "nwg")) g_dbg.nwg = value;
   else if (!strcmp(key, "gemm_dbg")) g_dbg.gemm_dbg = value;
   else if (!strcmp(key, "slots")) g_dbg.slots = value;
@@ -1270,8 +1419,12 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   const bool short_k = K <= 256 && p.epi_mode != EPI_GENERIC;
   const bool light_in = short_k && p.epi_mode == EPI_IN && p.epi_kind == KIND_RESID;
   const bool fused_ln = p.epi_kind == KIND_RESID_LN && p.epi_mode == EPI_IN;       // needs 1 warpgroup x 4 slots
-  const int nwg = fused_ln ? 1 : (g_dbg.nwg ? (g_dbg.nwg == 2 ? 2 : 1) : ((short_k && !light_in) ? 2 : 1));
-  const int slots = fused_ln ? 4 : (g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2));
+  // fused LayerNorm: the row split between two warpgroups (2 slots each) unless sc_debug_set("ln_split", 0) asks for the
+  // one-warpgroup / 4-slot form
+  // (measured: K <= 256 shapes gain 4-7 %, the K = 1024 fc2 shape loses 2-4 % -> short K only; ln_split = 2 forces it)
+  p.ln_split = (fused_ln && (g_dbg.ln_split == 2 || (g_dbg.ln_split == 1 && K <= 256))) ? 1 : 0;
+  const int nwg = fused_ln ? (p.ln_split ? 2 : 1) : (g_dbg.nwg ? (g_dbg.nwg == 2 ? 2 : 1) : ((short_k && !light_in) ? 2 : 1));
+  const int slots = fused_ln ? (p.ln_split ? 2 : 4) : (g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2));
 #define SC_LAUNCH1(AM, BMJ, C2, W, S) launch<AM, BMJ, C2, W, S>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st)
 #define SC_LAUNCH(AM, BMJ)                                                                          \
   (nwg == 2 ? (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 2, 4) : SC_LAUNCH1(AM, BMJ, 0, 2, 2))           \
