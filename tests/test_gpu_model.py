@@ -235,3 +235,58 @@ def test_forward_matches_committed_golden_vectors(cuda_lib):
             assert abs(float(aux["l_sem"]) - float(g[f"fwd_{kind}_l_sem"])) < 2e-2 * float(g[f"fwd_{kind}_l_sem"])
             assert _rel(aux["y"][:, :, :8], g[f"fwd_{kind}_y_head"]) < 2e-2
             assert _rel(aux["z"][:, :, :8], g[f"fwd_{kind}_z_head"]) < 2e-2
+
+
+@pytest.mark.parametrize("name,switches", [
+    ("single-CTA wgrads", {"cta2_wgrad": 0}),
+    ("one-warpgroup fused LayerNorm", {"ln_split": 0}),
+    ("split fused LayerNorm on every K", {"ln_split": 2}),
+    ("fused-MLP backward without weight multicast", {"mlp_dbg": 4}),
+    ("programmatic dependent launch", {"pdl": 1}),
+    ("alternating traversal direction", {"alternate": 1}),
+    ("L2 prefetch switches", {"gemm_dbg": 256, "mlp_dbg": 3}),
+    ("wgrads on a side stream", {"side_stream": 1}),
+])
+def test_schedule_switches_preserve_results(cuda_lib, name, switches):
+    """Every schedule / kernel-variant switch of the library (profiles/README.md, negative-results table) computes the
+    same PPO step as the default configuration: loss statistics and the flat gradient bucket agree to bf16 level.  B = 256 so that the encoder GEMMs have 128 row tiles (pairs, multicast and both
+    traversal directions are exercised on more than one tile per CTA)."""
+    from multimodal_sc_b200 import ops, synthetic
+    from multimodal_sc_b200.model import SemComPolicy
+    from multimodal_sc_b200.ppo import PPOAgent
+    B = 256
+    mb = synthetic.minibatch(SPEC, B, seed=21, device="cuda")
+    defaults = {"cta2_wgrad": 1, "ln_split": 1, "mlp_dbg": 0, "pdl": 0, "alternate": 0, "gemm_dbg": 0}
+
+    def run(sw):
+        for k, v in {**defaults, **{k: v for k, v in sw.items() if k in defaults}}.items():
+            ops.debug_set(k, v)
+        pol = SemComPolicy(SPEC, seed=0)
+        if sw.get("side_stream"):
+            pol.engine.wgrad_stream = torch.cuda.Stream()
+        ag = PPOAgent(pol, SPEC, minibatch=B, seed=5)
+        grads = {}
+        orig = ops.adam_flat
+
+        def spy(p32, g32, *a, **k):
+            grads["g"] = g32.clone()
+            return orig(p32, g32, *a, **k)
+
+        ops.adam_flat = spy
+        try:
+            st = ag.minibatch_step(mb["cam"], mb["bev"], mb["actions"], mb["logp_old"], mb["adv"], None, mb["ret"])
+        finally:
+            ops.adam_flat = orig
+            for k, v in defaults.items():
+                ops.debug_set(k, v)
+        return st, grads["g"]
+
+    st0, g0 = run({})
+    st1, g1 = run(switches)
+    # the LayerNorm variants add the row statistics in a different order: an rstd one ulp off flips individual bf16
+    # roundings downstream, so the yardstick is bf16-level agreement, far below the damage a protocol bug does
+    for k in st0:
+        assert abs(st0[k] - st1[k]) <= 1e-4 + 2e-3 * abs(st0[k]), (name, k, st0[k], st1[k])
+    scale = float(g0.abs().max())
+    assert float((g0 - g1).abs().max()) <= 2e-2 * scale, (name, float((g0 - g1).abs().max()), scale)
+    assert float((g0 - g1).abs().mean()) <= 5e-4 * scale, (name, float((g0 - g1).abs().mean()), scale)
