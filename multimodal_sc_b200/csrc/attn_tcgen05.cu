@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQKV, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], sdp_full, ds_full, grads_full;
+  __shared__ __align__(8) uint64_t full_bar[2], drained_bar[2], sdp_full, ds_full, grads_full;
   __shared__ uint32_t tmem_slot;
   __shared__ float delta_part[2][128];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -272,7 +272,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&drained_bar[s]), 256); }
     mbar_init(smem_u32(&sdp_full), 1);
     mbar_init(smem_u32(&ds_full), 256);
     mbar_init(smem_u32(&grads_full), 1);
@@ -292,14 +292,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   // single-thread roles: converged warp + one elected lane (see the forward kernel)
   if (warp == 0) {
+    // Loads AND gradient stores.  The compute warpgroups stage dQ / dK / dV of item n in the Q / K / V slots of the
+    // item's own load stage and arrive on drained_bar[stage]; this warp then stores them, waits until the stores have
+    // read shared memory, and only then loads item n + 2 into the stage.  The store latency sits on this warp, one
+    // item of slack ahead of the MMA warp, instead of in front of the next item's softmax.
+    auto coords = [&](int it, int& h, int& row0) {
+      const int ri = p.reverse ? p.num_items - 1 - it : it;
+      h = ri % p.H;
+      row0 = (ri / p.H) * 128;
+    };
+    auto store_item = [&](int k) {                            // k-th item of this CTA
+      int h, row0;
+      coords(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), h, row0);
+      const uint32_t stg = smem + (k & 1) * kBwdStage;
+      mbar_wait(smem_u32(&drained_bar[k & 1]), (k >> 1) & 1);
+      if (lane == 0) {
+        tma_store_2d(&tmDQKV, stg + 2 * kTile, 2 * HD + h * 64, row0);    // dV
+        tma_store_2d(&tmDQKV, stg + kTile, HD + h * 64, row0);            // dK
+        tma_store_2d(&tmDQKV, stg, h * 64, row0);                         // dQ
+        tma_store_commit();
+        tma_store_wait_read<0>();
+      }
+      __syncwarp();
+    };
     int n = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
       const int stage = n & 1;
-      const uint32_t ph = (n >> 1) & 1;
-      const int ri = p.reverse ? p.num_items - 1 - item : item;
-      const int h = ri % p.H, row0 = (ri / p.H) * 128;
+      int h, row0;
+      coords(item, h, row0);
       const uint32_t fb = smem_u32(&full_bar[stage]);
-      mbar_wait(smem_u32(&empty_bar[stage]), ph ^ 1u);
+      if (n >= 2) store_item(n - 2);                          // frees the stage
       const uint32_t dst = smem + stage * kBwdStage;
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(fb, kBwdStage);
@@ -310,6 +332,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       __syncwarp();
     }
+    for (int k = n >= 2 ? n - 2 : 0; k < n; ++k) store_item(k);
+    if (lane == 0) tma_store_wait_all();
   } else if (warp == 1) {
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);     // A^T from P/dS (MN-major), B MN-major
@@ -351,7 +375,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                        umma_smem_desc(sK + k * 2048, 8192, 1024), idesc_kt, k > 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&grads_full));
-        umma_commit(smem_u32(&empty_bar[stage]));
+        // (the stage is released by the store thread: the gradient tiles are staged in this stage's Q / K / V slots)
       }
       __syncwarp();
       if (item + static_cast<int>(gridDim.x) < p.num_items) {
@@ -384,7 +408,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(smem_u32(&sdp_full), n & 1);
       __syncwarp();
       tc_fence_after();
-      compute_barrier256();                    // previous item's TMA stores have finished reading p_buf / ds_buf
+      // (no barrier here: p_buf / ds_buf were last read by the previous item's gradient MMAs, and every thread has
+      //  waited on grads_full before it left that item; the gradient staging no longer aliases these buffers)
       // pass 1: P (bf16 -> smem, kept packed in registers) and this warpgroup's part of delta = rowsum(P o dP)
       uint32_t pk[32];
       float delta = 0.f;
@@ -437,14 +462,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(&ds_full));
-      // drain: WG0 takes dV and the first 32 columns of dQ, WG1 takes dK and the last 32 columns of dQ;
-      // staging aliases p_buf / ds_buf once the MMAs are complete
+      // drain: WG0 takes dV and the first 32 columns of dQ, WG1 takes dK and the last 32 columns of dQ.  Staging = the
+      // V / K / Q slots of THIS item's load stage: once the gradient MMAs are complete nothing reads them any more, and
+      // the stage is handed back to the producer only after the TMA stores have read it.  (Staging in p_buf / ds_buf
+      // put the store's read latency and a 256-thread barrier in front of the next item's softmax.)
       mbar_wait(smem_u32(&grads_full), n & 1);
       __syncwarp();
       tc_fence_after();
+      const uint32_t stg = smem + (n & 1) * kBwdStage;
       {
         const uint32_t src = (g == 0 ? tm_dv : tm_dk) + lane_off;
-        const uint32_t dst = p_buf + g * kTile;
+        const uint32_t dst = stg + (g == 0 ? 2 * kTile : kTile);
         uint32_t o0[32], o1[32];
         tmem_ld_32x32b_x32(src, o0);
         tmem_ld_32x32b_x32(src + 32, o1);
@@ -465,7 +493,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         uint32_t oq[32];
         tmem_ld_32x32b_x32(tm_dq + lane_off + g * 32, oq);
         tmem_ld_wait();
-        const uint32_t dq_dst = p_buf + 2 * kTile;
+        const uint32_t dq_dst = stg;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           st_shared_v4(sw128(dq_dst, r, 4 * g + i),
@@ -476,16 +504,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      compute_barrier256();
-      if (threadIdx.x == 64) {
-        tma_store_2d(&tmDQKV, p_buf, 2 * HD + h * 64, row0);              // dV
-        tma_store_2d(&tmDQKV, p_buf + kTile, HD + h * 64, row0);          // dK
-        tma_store_2d(&tmDQKV, p_buf + 2 * kTile, h * 64, row0);           // dQ
-        tma_store_commit();
-        tma_store_wait_read<0>();
-      }
+      mbar_arrive(smem_u32(&drained_bar[n & 1]));             // warp 0 stores the tiles and recycles the stage
     }
-    if (threadIdx.x == 64) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
