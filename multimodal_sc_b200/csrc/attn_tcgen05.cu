@@ -212,7 +212,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tmem_ld_32x32b_x32(tm_o + lane_off, o0);
       tmem_ld_32x32b_x32(tm_o + lane_off + 32, o1);
       tmem_ld_wait();
-      compute_barrier();                                    // previous TMA store has finished reading o_buf
+      // the previous item's TMA store must have read o_buf: the issuing thread waits for it HERE, a whole softmax after
+      // it issued the store (waiting right after the issue put the read latency on that warp in every item)
+      if (threadIdx.x == 64) tma_store_wait_read<0>();
+      compute_barrier();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         st_shared_v4(sw128(o_buf, r, i),
@@ -231,7 +234,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (threadIdx.x == 64) {
         tma_store_2d(&tmO, o_buf, h * 64, row0);
         tma_store_commit();
-        tma_store_wait_read<0>();
       }
     }
     if (threadIdx.x == 64) tma_store_wait_all();
