@@ -176,7 +176,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_init(smem_u32(&hin_full[b]), 1);
     }
     mbar_init(smem_u32(&acc2_full), 1);
-    mbar_init(smem_u32(&acc2_empty), 128);
+    mbar_init(smem_u32(&acc2_empty), 256);                   // both warpgroups drain half of the output tile
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWa);
@@ -531,8 +531,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         fence_proxy_async_smem();                            // operand buffer writes -> visible to UMMA / TMA
         mbar_arrive(smem_u32(&h_full[wg]));
       }
-      if (wg == 1) {
-        // ---- output tile: acc2 (+ b2 + residual) -> bf16, 32 bytes per row per step straight to global ----
+      {
+        // ---- output tile: acc2 (+ b2 + residual) -> bf16, 32 bytes per row per step straight to global.  Each
+        //      warpgroup takes 128 of the 256 columns (warpgroup 0 would otherwise idle from its last chunk until
+        //      the next tile's first GEMM1) ----
         mbar_wait(smem_u32(&acc2_full), t_par);
         tc_fence_after();
         bf16* out_row = p.out + grow * DM;
@@ -574,14 +576,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             st_global_v4(out_row + s * 16 + 8, o[4], o[5], o[6], o[7]);
           }
         };
-        issue(0, v[0], bv[0], iv[0]);
+        const int s_lo = wg * (DM / 32), s_hi = s_lo + DM / 32;
+        issue(s_lo, v[0], bv[0], iv[0]);
 #pragma unroll 1
-        for (int s = 0; s < DM / 16; s += 2) {
+        for (int s = s_lo; s < s_hi; s += 2) {
           tmem_ld_wait();
           issue(s + 1, v[1], bv[1], iv[1]);
           process(s, v[0], bv[0], iv[0]);
           tmem_ld_wait();
-          if (s + 2 < DM / 16) issue(s + 2, v[0], bv[0], iv[0]);
+          if (s + 2 < s_hi) issue(s + 2, v[0], bv[0], iv[0]);
           process(s + 1, v[1], bv[1], iv[1]);
         }
         tc_fence_before();
