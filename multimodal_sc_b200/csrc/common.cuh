@@ -438,6 +438,13 @@ __device__ __forceinline__ uint32_t umma_kblock4_bf16_ss(uint32_t d_tmem, uint64
 #undef SC_UMMA4_OPERANDS
 #undef SC_COMMIT_LOCAL
 #undef SC_COMMIT_MC2
+// the same, arriving on the barrier at this offset in BOTH CTAs of a 2-CTA cluster (cta_group::1 MMAs)
+__device__ __forceinline__ void umma_commit_mc2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
 // all prior tcgen05.mma of this thread arrive on `bar` when complete (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

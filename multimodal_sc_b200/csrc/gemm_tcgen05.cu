@@ -29,6 +29,11 @@ constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;                 // 16384
 // CTA2 = 0: one CTA per tile (cta_group::1), B tile 256 x 64 per stage (48 KB stages).
+// CTA2 = 2: a cluster of two INDEPENDENT CTAs (cta_group::1, own accumulators and epilogues) that work on the same N tile
+//           of two consecutive 128-row blocks and share the B (weight) tile of every stage: each CTA loads half of it
+//           and multicasts it into both shared memories; a stage is free when both MMA warps have committed.  Halves
+//           the weight traffic out of L2 (2/3 of the operand bytes of a K = 256 tile) without the accumulator hand-off
+//           that couples the epilogues of a cta_group::2 pair.
 // CTA2 = 1: a CTA pair (cluster of 2, cta_group::2) computes a 256 x 256 tile; each CTA stages its own 128 A rows
 //           and HALF of the B tile (128 x 64) -> 32 KB stages and half the B shared-memory traffic per SM.
 // NWG   = epilogue warpgroups (1 or 2): two warps per scheduler hide each other's dependency stalls.
@@ -40,15 +45,15 @@ constexpr int STATIC_SMEM_RESERVE = 1024;            // mbarriers etc. (static _
 constexpr int EPI_SLOT_BYTES = 32 * 128;             // 32 rows x 64 bf16 columns, SWIZZLE_128B
 constexpr int BIAS_TILE_BYTES = BN * 4;              // fp32 bias of the current N tile, one copy per epilogue warpgroup
 template <int CTA2, int NWG, int SLOTS> struct Geo {
-  static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;
+  static constexpr int B_ROWS = (CTA2 == 1) ? BN / 2 : BN;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING = NWG * 4 * SLOTS * EPI_SLOT_BYTES;
   // one bias tile per warpgroup; the 1-warpgroup / 4-slot geometry also parks LayerNorm gamma and beta (fused LN)
   // (the 2-warpgroup / 2-slot geometry runs the fused LayerNorm with the row split between the warpgroups: columns
   //  0-127 / 128-255, partial row statistics exchanged through LN_XCHG bytes of shared memory, double-buffered by tile)
-  static constexpr int LN_TILES = (!CTA2 && ((NWG == 1 && SLOTS == 4) || (NWG == 2 && SLOTS == 2))) ? 2 : 0;
-  static constexpr int LN_XCHG = (!CTA2 && NWG == 2 && SLOTS == 2) ? 2 * 2 * BM * 8 : 0;
+  static constexpr int LN_TILES = (CTA2 != 1 && ((NWG == 1 && SLOTS == 4) || (NWG == 2 && SLOTS == 2))) ? 2 : 0;
+  static constexpr int LN_XCHG = (CTA2 != 1 && NWG == 2 && SLOTS == 2) ? 2 * 2 * BM * 8 : 0;
   static constexpr int BIAS = (NWG + LN_TILES) * BIAS_TILE_BYTES + LN_XCHG;
   static constexpr int STAGES_FIT = (SMEM_LIMIT - STATIC_SMEM_RESERVE - RING - BIAS) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
@@ -759,13 +764,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;       // 0 = MMA leader of the pair
-  const int ncta = CTA2 ? 2 : 1;
+  constexpr bool PAIR = (CTA2 == 1);                         // cta_group::2 pair
+  constexpr bool MCB = (CTA2 == 2);                          // independent CTAs sharing the B tile by multicast
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // 0 = MMA leader of the pair
+  const uint32_t crank = CTA2 ? cluster_ctarank() : 0u;      // rank in the cluster (pair or multicast)
+  const int ncta = PAIR ? 2 : 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), MCB ? 2 : 1);     // MCB: both CTAs' MMA warps release a shared stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full_bar[s]), 1);
@@ -779,7 +787,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
   }
   if (warp == 2) {
-    if (CTA2) tmem_alloc_2sm<TMEM_COLS>(smem_u32(&tmem_base_slot));
+    if (PAIR) tmem_alloc_2sm<TMEM_COLS>(smem_u32(&tmem_base_slot));
     else tmem_alloc<TMEM_COLS>(smem_u32(&tmem_base_slot));
   }
   // bias-gradient mode: 4 KB of bf16 ones in the (otherwise unused) epilogue ring = the B operand of the
@@ -802,7 +810,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (CTA2) cluster_sync_all();            // peer barriers are initialised before anyone signals them
+  if (CTA2) cluster_sync_all();            // peer barriers are initialised before anyone signals them (pair and MCB)
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -812,7 +820,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int cta_first = CTA2 ? static_cast<int>(blockIdx.x) / 2 : static_cast<int>(blockIdx.x);
   auto get_item = [&](int item) {
     Item it = decode_item(p, p.reverse ? num_items - 1 - item : item);
-    if (CTA2) it.m_blk = it.m_blk * 2 + static_cast<int>(rank);
+    if (CTA2) it.m_blk = it.m_blk * 2 + static_cast<int>(crank);
     return it;
   };
   const bool single_acc = (p.colsum != nullptr);       // stage 1's columns hold the row-sum accumulator
@@ -834,6 +842,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // (profiles/README.md, r1 "L2 prefetch"): the whole step got 11 % slower, K = 1024 shapes and wgrads by
         // 25-35 % -- the memory system, not the ring depth, is what these kernels wait for.
         const bool l2_pf = !CTA2 && (p.dbg & 256);
+        (void)crank;
         if (l2_pf && p.ksplit == 1 && elect_one_sync()) {
           const int nitem = item + cta_stride;
           if (nitem < num_items) {
@@ -874,8 +883,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int k0 = (p.reverse ? it.kb_end - 1 - (kb - it.kb_begin) : kb) * BK;
           if (elect_one_sync()) {
             if (p.dbg & 32) {                                   // no loads at all: raw MMA issue rate on stale smem
-              if (!CTA2 || rank == 0) mbar_arrive(fb_local);
-            } else if (CTA2) {
+              if (!PAIR || rank == 0) mbar_arrive(fb_local);
+            } else if (MCB) {
+              // own A tile (unicast) + this CTA's half of the B tile, multicast into both CTAs; each CTA's full barrier
+              // expects its A bytes and the whole B tile (two halves from two issuers)
+              const uint32_t fb = fb_local;
+              mbar_arrive_expect_tx(fb, p.a_tx + p.b_tx);
+              if (A_MN == 0) {
+                tma_load_2d(a_dst, &tmA, fb, k0, m0);
+              } else {
+                for (int c = 0; c < p.m_chunks; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + 64 * c, k0);
+              }
+              if (B_MN == 0) {                                  // K-major: rows crank*128 .. +127 of the tile (16 KB)
+                tma_load_2d_mc(b_dst + crank * (BN / 2) * BK * 2, &tmB, fb, k0, n0 + static_cast<int>(crank) * (BN / 2), 3);
+              } else {                                          // MN-major: 64-column chunks 2*crank, 2*crank + 1
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  const int cc = 2 * static_cast<int>(crank) + c;
+                  tma_load_2d_mc(b_dst + cc * CHUNK_BYTES, &tmB, fb, n0 + 64 * cc, k0, 3);
+                }
+              }
+            } else if (PAIR) {
               // all bytes of both CTAs are accounted on the LEADER's full barrier
               const uint32_t fb = mapa_shared(fb_local, 0);
               if (rank == 0) mbar_arrive_expect_tx(fb_local, 2 * STAGE_BYTES);
@@ -922,7 +950,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // (~170 cycles even when the phase is complete) would push that past the 512 cycles the tensor pipe needs, so
     // the NEXT stage's full barrier is tested before this stage's MMAs are issued and only waited on if not ready.
     if (rank == 0) {                                           // pair: only the leader CTA issues MMAs
-      const uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, CTA2 ? BN : static_cast<uint32_t>(p.n_mma), A_MN, B_MN);
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, PAIR ? BN : static_cast<uint32_t>(p.n_mma), A_MN, B_MN);
       const uint64_t a_desc0 = umma_smem_desc(0, p.a_lbo, p.a_sbo);
       const uint64_t b_desc0 = umma_smem_desc(0, p.b_lbo, p.b_sbo);
       const uint32_t a_step = p.a_kstep >> 4, b_step = p.b_kstep >> 4;
@@ -947,15 +975,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
-          const uint64_t ad = a_desc0 + (a_addr >> 4);
-          const uint64_t bd = b_desc0 + ((a_addr + A_BYTES) >> 4);
+          // 18-bit CTA-local address: in a cluster the shared::cta window of rank r starts at r << 24 (would spill into LBO)
+          const uint64_t ad = a_desc0 + ((a_addr & 0x3FFFFu) >> 4);
+          const uint64_t bd = b_desc0 + (((a_addr + A_BYTES) & 0x3FFFFu) >> 4);
           const uint32_t first = (kb > it.kb_begin) ? 1u : 0u;
-          if (!CTA2 && !rowsum && !mma_off) {
-            // common case: test of the next stage, four MMAs and the commit in one asm block (see common.cuh)
+          if (!PAIR && !rowsum && !mma_off) {
+            // common case: test of the next stage, four MMAs and the commit in one asm block (see common.cuh);
+            // MCB: the commit arrives on the stage's empty barrier in BOTH CTAs
             uint32_t r = 0;
             if (elect_one_sync())
-              r = umma_kblock4_bf16_ss(d_tmem, ad, bd, a_step, b_step, idesc, first, smem_u32(&empty_bar[stage]),
-                                       smem_u32(&full_bar[nstage]), nphase);
+              r = umma_kblock4_bf16_ss<true, true, MCB>(d_tmem, ad, bd, a_step, b_step, idesc, first,
+                                                        smem_u32(&empty_bar[stage]), smem_u32(&full_bar[nstage]), nphase);
             ready = __shfl_sync(0xffffffffu, r, 0);            // elect.sync picks lane 0 of the converged warp
           } else {
             ready = mbar_test(smem_u32(&full_bar[nstage]), nphase);
@@ -964,18 +994,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                   const uint32_t acc = (k > 0) ? 1u : first;
-                  if (CTA2) umma_bf16_ss_2sm(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
+                  if (PAIR) umma_bf16_ss_2sm(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
                   else umma_bf16_ss(d_tmem, ad + k * a_step, bd + k * b_step, idesc, acc);
                   if (rowsum) {
-                    constexpr uint32_t idesc_ones = umma_idesc_bf16(CTA2 ? 2 * BM : BM, 16, A_MN, 1);
+                    constexpr uint32_t idesc_ones = umma_idesc_bf16(PAIR ? 2 * BM : BM, 16, A_MN, 1);
                     const uint64_t od = umma_smem_desc(ones_tile, CHUNK_BYTES, 1024);
-                    if (CTA2) umma_bf16_ss_2sm(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
+                    if (PAIR) umma_bf16_ss_2sm(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
                     else umma_bf16_ss(tmem_base + BN, ad + k * a_step, od, idesc_ones, acc);
                   }
                 }
               }
               // smem slot reusable (in both CTAs of a pair) when the MMAs retire
-              if (CTA2) umma_commit_2sm(smem_u32(&empty_bar[stage])); else umma_commit(smem_u32(&empty_bar[stage]));
+              if (PAIR) umma_commit_2sm(smem_u32(&empty_bar[stage]));
+              else if (MCB) umma_commit_mc2(smem_u32(&empty_bar[stage]));
+              else umma_commit(smem_u32(&empty_bar[stage]));
             }
             __syncwarp();
           }
@@ -984,7 +1016,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         // accumulator complete (published to both CTAs of a pair)
         if (elect_one_sync()) {
-          if (CTA2) umma_commit_2sm(smem_u32(&tmem_full_bar[as])); else umma_commit(smem_u32(&tmem_full_bar[as]));
+          if (PAIR) umma_commit_2sm(smem_u32(&tmem_full_bar[as])); else umma_commit(smem_u32(&tmem_full_bar[as]));
         }
         __syncwarp();
         if (single_acc) {
@@ -1008,13 +1040,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     // split LayerNorm: the two warpgroups work on the SAME tile (columns 0-127 / 128-255) instead of alternate tiles
-    const bool ln_split = (NWG == 2 && SLOTS == 2 && !CTA2) && p.ln_split != 0;
+    const bool ln_split = (NWG == 2 && SLOTS == 2 && CTA2 != 1) && p.ln_split != 0;
     const int stride2 = ln_split ? cta_stride : NWG * cta_stride;
     const int first = ln_split ? cta_first : cta_first + wg * cta_stride;
     // pair: the leader's MMA thread waits for BOTH CTAs' epilogues -> arrive on the leader's barrier
     auto release_acc = [&](int as) {
       const uint32_t local = smem_u32(&tmem_empty_bar[as]);
-      if (CTA2) mbar_arrive_cluster(mapa_shared(local, 0)); else mbar_arrive(local);
+      if (PAIR) mbar_arrive_cluster(mapa_shared(local, 0)); else mbar_arrive(local);
     };
     if (p.epi_mode == EPI_GENERIC) {
       const int g_first = single_acc ? cta_first : first;
@@ -1171,13 +1203,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CTA2) cluster_sync_all();            // nobody tears down while the peer may still signal / read it
   if (warp == 2) {
     tc_fence_after();
-    if (CTA2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
 struct DebugOverrides {
   int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0,
-          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 0, ln_split = 1;
+          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 0, ln_split = 1, mcb = 0;
 };
 DebugOverrides g_dbg;
 
@@ -1250,6 +1282,7 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "cta2_wgrad")) g_dbg.cta2_wgrad = value;
   else if (!strcmp(key, "cta2_mink")) g_dbg.cta2_mink = value;
   else if (!strcmp(key, "ln_split")) g_dbg.ln_split = value;
+  else if (!strcmp(key, "mcb")) g_dbg.mcb = value;
   else if (!strcmp(key, "nwg")) g_dbg.nwg = value;
   else if (!strcmp(key, "gemm_dbg")) g_dbg.gemm_dbg = value;
   else if (!strcmp(key, "slots")) g_dbg.slots = value;
@@ -1291,7 +1324,13 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
                     (g_dbg.cta2_wgrad != 0 && a_mn && b_mn && ksplit > 1 && M % (2 * BM) == 0 && N % BN == 0) ||
                     (g_dbg.cta2_mink > 0 && !a_mn && K >= g_dbg.cta2_mink && ksplit <= 1 && !epi->ln_out &&
                      M % (2 * BM) == 0 && N % BN == 0);
-  p.tiles_m = cta2 ? static_cast<int>((M + 2 * BM - 1) / (2 * BM)) : static_cast<int>((M + BM - 1) / BM);
+  // activation x weight GEMMs (forward, dgrad): clusters of two independent CTAs that share the weight tile of every
+  // stage by multicast (CTA2 = 2 in the kernel).  Needs whole 256-row pairs and whole 256-column weight tiles.
+  // Opt-in (sc_debug_set("mcb", 1)): parity-green, but no shape got faster -- the weight re-loads are L2 hits that
+  // these kernels do not wait for (profiles/README.md).
+  const bool mcb = !cta2 && g_dbg.mcb != 0 && !a_mn && ksplit <= 1 && !epi->colsum && M % (2 * BM) == 0 && N % BN == 0 &&
+                   M >= 2 * BM * 2;
+  p.tiles_m = (cta2 || mcb) ? static_cast<int>((M + 2 * BM - 1) / (2 * BM)) : static_cast<int>((M + BM - 1) / BM);
   p.tiles_n = static_cast<int>((N + BN - 1) / BN);
   p.kb_total = static_cast<int>((K + BK - 1) / BK);
   int ks = ksplit < 1 ? 1 : ksplit;
@@ -1351,7 +1390,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   if (a_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM);
   else           rc = sc_encode_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK);
   if (rc != SC_OK) return rc;
-  if (b_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, cta2 ? BN / 2 : p.n_mma);
+  if (b_mn == 0) rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (cta2 || mcb) ? BN / 2 : p.n_mma);
   else           rc = sc_encode_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK);
   if (rc != SC_OK) return rc;
 
@@ -1430,6 +1469,15 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   (nwg == 2 ? (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 2, 4) : SC_LAUNCH1(AM, BMJ, 0, 2, 2))           \
             : (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 1, 4) : SC_LAUNCH1(AM, BMJ, 0, 1, 2)))
 #define SC_LAUNCH_PAIR(AM, BMJ) (nwg == 2 ? SC_LAUNCH1(AM, BMJ, 1, 2, 2) : SC_LAUNCH1(AM, BMJ, 1, 1, 2))
+#define SC_LAUNCH_MCB(AM, BMJ)                                                                      \
+  (nwg == 2 ? (slots == 4 ? SC_LAUNCH1(AM, BMJ, 2, 2, 4) : SC_LAUNCH1(AM, BMJ, 2, 2, 2))           \
+            : (slots == 4 ? SC_LAUNCH1(AM, BMJ, 2, 1, 4) : SC_LAUNCH1(AM, BMJ, 2, 1, 2)))
+  if (mcb) {
+    int pairs = grid / 2;
+    if (items < pairs) pairs = (int)items;
+    grid = 2 * pairs;
+    return b_mn ? SC_LAUNCH_MCB(0, 1) : SC_LAUNCH_MCB(0, 0);
+  }
   if (cta2) {
     int pairs = grid / 2;
     if (items < pairs) pairs = (int)items;
@@ -1445,6 +1493,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   if (a_mn == 1 && b_mn == 1) return SC_LAUNCH(1, 1);
   return SC_LAUNCH(1, 0);
 #undef SC_LAUNCH_PAIR
+#undef SC_LAUNCH_MCB
 #undef SC_LAUNCH1
 #undef SC_LAUNCH
 }
