@@ -842,7 +842,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // (profiles/README.md, r1 "L2 prefetch"): the whole step got 11 % slower, K = 1024 shapes and wgrads by
         // 25-35 % -- the memory system, not the ring depth, is what these kernels wait for.
         const bool l2_pf = !CTA2 && (p.dbg & 256);
-        (void)crank;
         if (l2_pf && p.ksplit == 1 && elect_one_sync()) {
           const int nitem = item + cta_stride;
           if (nitem < num_items) {
