@@ -127,7 +127,8 @@ struct GemmParams {
   //   256 = L2 prefetch of upcoming operand tiles (results stay correct; measured slower)
   int dbg;
   int reverse;                  // 1 = items (and the k-blocks of a split-K item) are walked in descending order
-  int ln_split;                 // fused LayerNorm with the row split between two epilogue warpgroups (NWG = 2, SLOTS = 2)
+  int ln_split;                 // column split: both epilogue warpgroups drain the SAME tile, columns 0-127 / 128-255
+                                // (NWG = 2, SLOTS = 2; fused LayerNorm and the output-only staged epilogues)
 };
 
 struct Item {
@@ -399,7 +400,9 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
                                             const CUtensorMap* tmIn, uint32_t t_addr, uint32_t ring, uint32_t in_bar0,
                                             uint32_t bias_tile, int lane, int n0, int row0, int in_row0,
                                             uint32_t row_mod, uint32_t row_grp, uint32_t tile_parity,
-                                            const NextTile& next) {
+                                            const NextTile& next, int s_lo = 0, int s_hi = 16) {
+  // [s_lo, s_hi): the 16-column steps of the tile this warp drains.  All 16, or (column split between two warpgroups
+  // that work on the SAME tile, output-only epilogues) steps 0-7 / 8-15 = chunks 0,1 / 2,3.
   constexpr bool G = (KIND == KIND_GEN);
   const bool no_tma = (p.dbg & 2) != 0;
   const bool has_in = (p.epi_mode == EPI_IN) && !no_tma;
@@ -476,15 +479,15 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
     }
   };
 
-  issue(0, v[0], bv[0]);
+  issue(s_lo, v[0], bv[0]);
 #pragma unroll 1
-  for (int s = 0; s < 16; s += 2) {
+  for (int s = s_lo; s < s_hi; s += 2) {
     if ((s & 3) == 0) chunk_begin(s >> 2);
     tmem_ld_wait();
     issue(s + 1, v[1], bv[1]);
     process(s, v[0], bv[0]);
     tmem_ld_wait();
-    if (s + 2 < 16) issue(s + 2, v[0], bv[0]);
+    if (s + 2 < s_hi) issue(s + 2, v[0], bv[0]);
     process(s + 1, v[1], bv[1]);
     if ((s & 3) == 2) chunk_end(s >> 2);
   }
@@ -1038,7 +1041,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int wg = ew >> 2;
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    // split LayerNorm: the two warpgroups work on the SAME tile (columns 0-127 / 128-255) instead of alternate tiles
+    // column split: the two warpgroups work on the SAME tile (columns 0-127 / 128-255) instead of alternate tiles.
+    // With alternate tiles a warpgroup idles while the MMAs refill ITS accumulator (epilogue -> MMA -> epilogue on one
+    // buffer); as one double-speed consumer of double-buffered accumulators the MMAs of tile i+1 run under the drain of
+    // tile i (ncu: the epilogue warps of the qkv GEMM spent 35 % of their samples waiting for accumulators).
     const bool ln_split = (NWG == 2 && SLOTS == 2 && CTA2 != 1) && p.ln_split != 0;
     const int stride2 = ln_split ? cta_stride : NWG * cta_stride;
     const int first = ln_split ? cta_first : cta_first + wg * cta_stride;
@@ -1157,7 +1163,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           named_bar_sync(1 + wg, 128);
         }
         switch (p.epi_kind) {
-#define SC_TILE(KIND) staged_tile<KIND, SLOTS>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, bias_tile, lane, n0, row0, ir0, row_mod, row_grp, tile_parity, next)
+#define SC_TILE(KIND) staged_tile<KIND, SLOTS>(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, bias_tile, lane, n0, row0, ir0, row_mod, row_grp, tile_parity, next, ln_split ? wg * 8 : 0, ln_split ? wg * 8 + 8 : 16)
           case KIND_PLAIN: SC_TILE(KIND_PLAIN); break;
           case KIND_BIAS:  SC_TILE(KIND_BIAS); break;
           case KIND_FC1:   SC_TILE(KIND_FC1); break;
@@ -1208,7 +1214,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 struct DebugOverrides {
   int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0,
-          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 0, ln_split = 1, mcb = 0;
+          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 0, ln_split = 1, mcb = 0, col_split = 0;
 };
 DebugOverrides g_dbg;
 
@@ -1282,6 +1288,7 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "cta2_mink")) g_dbg.cta2_mink = value;
   else if (!strcmp(key, "ln_split")) g_dbg.ln_split = value;
   else if (!strcmp(key, "mcb")) g_dbg.mcb = value;
+  else if (!strcmp(key, "col_split")) g_dbg.col_split = value;
   else if (!strcmp(key, "nwg")) g_dbg.nwg = value;
   else if (!strcmp(key, "gemm_dbg")) g_dbg.gemm_dbg = value;
   else if (!strcmp(key, "slots")) g_dbg.slots = value;
@@ -1463,6 +1470,13 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   p.ln_split = (fused_ln && (g_dbg.ln_split == 2 || (g_dbg.ln_split == 1 && K <= 256))) ? 1 : 0;
   const int nwg = fused_ln ? (p.ln_split ? 2 : 1) : (g_dbg.nwg ? (g_dbg.nwg == 2 ? 2 : 1) : ((short_k && !light_in) ? 2 : 1));
   const int slots = fused_ln ? (p.ln_split ? 2 : 4) : (g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2));
+  // output-only staged epilogues with two warpgroups: column split as an option (sc_debug_set("col_split", 1 | 2)); off:
+  // on the whole step it is neutral (gemm_fwd 6.708 vs 6.705 ms, dgrad 1.96 vs 2.00 ms)
+  // (measured: the one-output shapes gain 2-5 %; the two-output fc1 epilogue waits for its own stores at every chunk and
+  //  loses 16 % when a warpgroup's two chunks follow each other directly -> EPI_OUT1 only, col_split = 2 forces both)
+  if (!fused_ln && !cta2 && nwg == 2 && slots == 2 &&
+      ((g_dbg.col_split != 0 && p.epi_mode == EPI_OUT1) || (g_dbg.col_split == 2 && p.epi_mode == EPI_OUT2)))
+    p.ln_split = 1;
 #define SC_LAUNCH1(AM, BMJ, C2, W, S) launch<AM, BMJ, C2, W, S>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st)
 #define SC_LAUNCH(AM, BMJ)                                                                          \
   (nwg == 2 ? (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 2, 4) : SC_LAUNCH1(AM, BMJ, 0, 2, 2))           \

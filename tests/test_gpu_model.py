@@ -247,6 +247,8 @@ def test_forward_matches_committed_golden_vectors(cuda_lib):
     ("L2 prefetch switches", {"gemm_dbg": 256, "mlp_dbg": 3}),
     ("wgrads on a side stream", {"side_stream": 1}),
     ("weight tiles shared by CTA clusters (multicast)", {"mcb": 1}),
+    ("column-split epilogue for one-output GEMMs", {"col_split": 1}),
+    ("column-split epilogue also for two outputs", {"col_split": 2}),
 ])
 def test_schedule_switches_preserve_results(cuda_lib, name, switches):
     """Every schedule / kernel-variant switch of the library (profiles/README.md, negative-results table) computes the
@@ -257,7 +259,7 @@ def test_schedule_switches_preserve_results(cuda_lib, name, switches):
     from multimodal_sc_b200.ppo import PPOAgent
     B = 256
     mb = synthetic.minibatch(SPEC, B, seed=21, device="cuda")
-    defaults = {"cta2_wgrad": 1, "ln_split": 1, "mlp_dbg": 0, "pdl": 0, "alternate": 0, "gemm_dbg": 0, "mcb": 0}
+    defaults = {"cta2_wgrad": 1, "ln_split": 1, "mlp_dbg": 0, "pdl": 0, "alternate": 0, "gemm_dbg": 0, "mcb": 0, "col_split": 0}
 
     def run(sw):
         for k, v in {**defaults, **{k: v for k, v in sw.items() if k in defaults}}.items():
