@@ -30,6 +30,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("SC_GEMM_ACCT", "0") not in ("", "0"):       # per-role wait accounting in the GEMM kernel (debug builds)
+    NVCC_FLAGS.append("-DSC_GEMM_ACCT")
+
+
 def nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

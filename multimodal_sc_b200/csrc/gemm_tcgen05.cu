@@ -40,6 +40,13 @@ constexpr int A_BYTES = BM * BK * 2;                 // 16384
 // SLOTS = 4 KB staging slots per epilogue warp (2 or 4).  4 slots hold a whole 32 x 256 tile row block, so the
 //         bf16 input tile of the NEXT tile is prefetched a full tile ahead and two-output epilogues double-buffer.
 // The pipeline gets every stage that still fits next to the staging ring and the bias tiles.
+// wait accounting (gemm_dbg bit 512) is compiled in only with -DSC_GEMM_ACCT (SC_GEMM_ACCT=1 python -m
+// multimodal_sc_b200.build --force): its counters cost registers the 384-thread variants do not have to spare
+#ifdef SC_GEMM_ACCT
+constexpr bool kAcct = true;
+#else
+constexpr bool kAcct = false;
+#endif
 constexpr int SMEM_LIMIT = 232448;                   // 227 KB opt-in maximum per CTA
 constexpr int STATIC_SMEM_RESERVE = 1024;            // mbarriers etc. (static __shared__), rounded up
 constexpr int EPI_SLOT_BYTES = 32 * 128;             // 32 rows x 64 bf16 columns, SWIZZLE_128B
@@ -124,7 +131,9 @@ struct GemmParams {
   //   32 = no operand loads at all (MMAs run on stale shared memory),
   //   64 = producer / MMA threads hot-spin on their mbarriers (mbarrier.test_wait),
   //   128 = CTA 0 prints the MMA warp's cycles per k-block,
-  //   256 = L2 prefetch of upcoming operand tiles (results stay correct; measured slower)
+  //   256 = L2 prefetch of upcoming operand tiles (results stay correct; measured slower),
+  //   512 = wait accounting (needs a -DSC_GEMM_ACCT build): CTA 0 prints, per role, its total cycles and the cycles
+  //         spent in each of its barrier waits
   int dbg;
   int reverse;                  // 1 = items (and the k-blocks of a split-K item) are walked in descending order
   int ln_split;                 // column split: both epilogue warpgroups drain the SAME tile, columns 0-127 / 128-255
@@ -405,10 +414,16 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
   // that work on the SAME tile, output-only epilogues) steps 0-7 / 8-15 = chunks 0,1 / 2,3.
   constexpr bool G = (KIND == KIND_GEN);
   const bool no_tma = (p.dbg & 2) != 0;
-  const bool has_in = (p.epi_mode == EPI_IN) && !no_tma;
-  const bool two_out = (p.epi_mode == EPI_OUT2);
+  // The specialised kinds fix the staging mode at compile time (the host only picks a kind whose mode matches), so the
+  // hot loop carries no mode branches: the ncu source page showed 74 instructions per 16-column step, 45 of them
+  // integer / control overhead, and the epilogue warps issue-bound on them.
+  const bool has_in = G ? ((p.epi_mode == EPI_IN) && !no_tma) : ((KIND == KIND_RESID || KIND == KIND_DGELU) && !no_tma);
+  const bool two_out = G ? (p.epi_mode == EPI_OUT2) : (KIND == KIND_FC1);
   const bool has_bias = G ? (p.bias != nullptr) : (KIND == KIND_BIAS || KIND == KIND_FC1 || KIND == KIND_RESID);
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  // swizzled offset of this lane's row: piece (2h | 2h+1) ^ sw of the 128-byte row = one XOR with a constant once h is
+  // a compile-time value (the low 7 bits of swz_row are sw << 4)
+  const uint32_t swz_row = static_cast<uint32_t>(lane) * 128u | (sw << 4);
 
   auto out_slot = [&](int c) { return SLOTS == 4 ? (two_out ? 2 * (c & 1) + 1 : c) : (two_out ? 1 : (c & 1)); };
   auto aux_slot = [&](int c) { return SLOTS == 4 ? 2 * (c & 1) : 0; };
@@ -436,23 +451,22 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
     }
     __syncwarp();
   };
-  auto process = [&](int s, const uint32_t (&vv)[16], const float4 (&bb)[4]) {
-    const int c = s >> 2, h = s & 3;
-    const uint32_t row_o = ring + out_slot(c) * EPI_SLOT_BYTES + lane * 128;
-    const uint32_t row_a = ring + aux_slot(c) * EPI_SLOT_BYTES + lane * 128;      // pre-activation copy (EPI_OUT2)
-    const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+  // one 16-column step: h = its position inside the chunk (compile-time in the unrolled loop below), slot_o / slot_a =
+  // shared addresses of the chunk's output / pre-activation slots
+  auto process = [&](int s, int h, uint32_t slot_o, uint32_t slot_a, const uint32_t (&vv)[16], const float4 (&bb)[4]) {
+    const uint32_t pa = swz_row ^ (32u * h), pb = swz_row ^ (32u * h + 16u);
     uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
     if (has_in) {
-      i0 = ld_shared_v4(row_o + pa);
-      i1 = ld_shared_v4(row_o + pb);
+      i0 = ld_shared_v4(slot_o + pa);
+      i1 = ld_shared_v4(slot_o + pb);
     }
     uint32_t o[8], a[8];
     epilogue_math16<KIND>(p, vv, bb, n0 + s * 16, row_mod, row_grp, i0, i1, o, a);
-    st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
-    st_shared_v4(row_o + pb, o[4], o[5], o[6], o[7]);
+    st_shared_v4(slot_o + pa, o[0], o[1], o[2], o[3]);
+    st_shared_v4(slot_o + pb, o[4], o[5], o[6], o[7]);
     if (two_out) {
-      st_shared_v4(row_a + pa, a[0], a[1], a[2], a[3]);
-      st_shared_v4(row_a + pb, a[4], a[5], a[6], a[7]);
+      st_shared_v4(slot_a + pa, a[0], a[1], a[2], a[3]);
+      st_shared_v4(slot_a + pb, a[4], a[5], a[6], a[7]);
     }
   };
   auto chunk_end = [&](int c) {
@@ -479,17 +493,28 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
     }
   };
 
+  // one iteration per 64-column chunk, its four steps unrolled (h is a constant in every process call); the
+  // tcgen05.ld of step s + 1 is in flight while step s is computed, across the chunk boundary too
   issue(s_lo, v[0], bv[0]);
 #pragma unroll 1
-  for (int s = s_lo; s < s_hi; s += 2) {
-    if ((s & 3) == 0) chunk_begin(s >> 2);
+  for (int c = s_lo >> 2; c < (s_hi >> 2); ++c) {
+    const int s = c * 4;
+    const uint32_t slot_o = ring + out_slot(c) * EPI_SLOT_BYTES;
+    const uint32_t slot_a = ring + aux_slot(c) * EPI_SLOT_BYTES;
+    chunk_begin(c);
     tmem_ld_wait();
     issue(s + 1, v[1], bv[1]);
-    process(s, v[0], bv[0]);
+    process(s, 0, slot_o, slot_a, v[0], bv[0]);
     tmem_ld_wait();
-    if (s + 2 < s_hi) issue(s + 2, v[0], bv[0]);
-    process(s + 1, v[1], bv[1]);
-    if ((s & 3) == 2) chunk_end(s >> 2);
+    issue(s + 2, v[0], bv[0]);
+    process(s + 1, 1, slot_o, slot_a, v[1], bv[1]);
+    tmem_ld_wait();
+    issue(s + 3, v[1], bv[1]);
+    process(s + 2, 2, slot_o, slot_a, v[0], bv[0]);
+    tmem_ld_wait();
+    if (s + 4 < s_hi) issue(s + 4, v[0], bv[0]);
+    process(s + 3, 3, slot_o, slot_a, v[1], bv[1]);
+    chunk_end(c);
   }
 }
 
@@ -836,6 +861,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       uint32_t ready = mbar_test(smem_u32(&empty_bar[0]), 1u);
+      const bool acct = kAcct && (p.dbg & 512) && blockIdx.x == 0;
+      const long long acct_t0 = clock64();
+      long long acct_wait = 0;
       for (int item = cta_first; item < num_items; item += cta_stride) {
         const Item it = get_item(item);
         const int m0 = (p.dbg & 8) ? 0 : it.m_blk * BM;
@@ -876,7 +904,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           const uint32_t fb_local = smem_u32(&full_bar[stage]);
-          if (!ready) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          if (!ready) {
+            const long long tw = acct ? clock64() : 0;
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            if (acct) acct_wait += clock64() - tw;
+          }
           const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
           const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
           ready = mbar_test(smem_u32(&empty_bar[nstage]), nphase ^ 1u);
@@ -943,6 +975,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           phase = nphase;
         }
       }
+      if (acct && lane == 0)
+        printf("semcom gemm acct: producer  total %lld clk, waiting for a free stage %lld\n", clock64() - acct_t0, acct_wait);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -963,16 +997,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t aphase = 0;
       const long long t_begin = clock64();
       long long n_kb = 0;
+      const bool acct = kAcct && (p.dbg & 512) && blockIdx.x == 0;
+      long long acct_acc = 0, acct_full = 0;
       uint32_t ready = mbar_test(smem_u32(&full_bar[0]), 0u);
       for (int item = cta_first; item < num_items; item += cta_stride) {
         const Item it = get_item(item);
-        mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1u);
+        {
+          const long long tw = acct ? clock64() : 0;
+          mbar_wait(smem_u32(&tmem_empty_bar[as]), aphase ^ 1u);
+          if (acct) acct_acc += clock64() - tw;
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
         const bool rowsum = single_acc && it.n_blk == 0;
         n_kb += it.kb_end - it.kb_begin;
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
-          if (!ready) mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (!ready) {
+            const long long tw = acct ? clock64() : 0;
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            if (acct) acct_full += clock64() - tw;
+          }
           const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
           const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
           tc_fence_after();
@@ -1028,6 +1072,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (as == 0) aphase ^= 1u;
         }
       }
+      if (acct && lane == 0)
+        printf("semcom gemm acct: mma       total %lld clk, %lld k-blocks, waiting for a free accumulator %lld, for operands %lld\n",
+               clock64() - t_begin, n_kb, acct_acc, acct_full);
       if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0)       // issue-loop pace: 512 clk per k-block is the tensor pipe's floor
         printf("semcom gemm: MMA warp issued %lld k-blocks in %lld clk (%.0f clk per k-block)\n", n_kb,
                clock64() - t_begin, double(clock64() - t_begin) / double(n_kb > 0 ? n_kb : 1));
@@ -1126,6 +1173,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       int n = ln_split ? 0 : wg;
       uint32_t tile_parity = 0;
+      const bool acct = kAcct && (p.dbg & 512) && blockIdx.x == 0 && (warp & 3) == 0;
+      const long long acct_t0 = clock64();
+      long long acct_wait = 0;
+      int acct_tiles = 0;
       for (int item = first; item < num_items; item += stride2, n += (ln_split ? 1 : NWG), tile_parity ^= 1u) {
         const Item it = get_item(item);
         const int as = n & 1;
@@ -1139,7 +1190,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // this tile's 256 bias values: fetched before the accumulator wait, parked in the warpgroup's smem tile
         float2 bias2 = make_float2(0.f, 0.f);
         if (stage_bias) bias2 = __ldg(reinterpret_cast<const float2*>(p.bias + n0) + wg_tid);
-        mbar_wait(smem_u32(&tmem_full_bar[as]), static_cast<uint32_t>((n >> 1) & 1));
+        {
+          const long long tw = acct ? clock64() : 0;
+          mbar_wait(smem_u32(&tmem_full_bar[as]), static_cast<uint32_t>((n >> 1) & 1));
+          if (acct) { acct_wait += clock64() - tw; ++acct_tiles; }
+        }
         __syncwarp();
         tc_fence_after();
         const int ir0 = in_row(row0);
@@ -1200,6 +1255,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (lane == 0) tma_store_wait_all();
+      if (acct && lane == 0)
+        printf("semcom gemm acct: epilogue warpgroup %d  total %lld clk, %d tiles, waiting for accumulators %lld\n", wg,
+               clock64() - acct_t0, acct_tiles, acct_wait);
     }
   }
 
