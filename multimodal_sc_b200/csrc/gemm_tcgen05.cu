@@ -543,14 +543,14 @@ __device__ __forceinline__ void staged_tile_ln(const GemmParams& p, const CUtens
 #pragma unroll
     for (int q = 0; q < 4; ++q) bb[q] = lds4(bias_tile + s * 64 + q * 16);
   };
-  auto pass1 = [&](int s, const uint32_t (&vv)[16], const float4 (&bb)[4]) {
-    const int c = s >> 2, h = s & 3;
-    const uint32_t row_o = ring + c * EPI_SLOT_BYTES + lane * 128;
-    const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+  const uint32_t swz_row = static_cast<uint32_t>(lane) * 128u | (sw << 4);     // see staged_tile
+  auto pass1 = [&](int c, int h, const uint32_t (&vv)[16], const float4 (&bb)[4]) {      // h: compile-time in the loop below
+    const uint32_t slot = ring + c * EPI_SLOT_BYTES;
+    const uint32_t pa = swz_row ^ (32u * h), pb = swz_row ^ (32u * h + 16u);
     uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
     if (!no_tma) {
-      i0 = ld_shared_v4(row_o + pa);
-      i1 = ld_shared_v4(row_o + pb);
+      i0 = ld_shared_v4(slot + pa);
+      i1 = ld_shared_v4(slot + pb);
     }
     const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
     uint32_t o[8];
@@ -564,29 +564,32 @@ __device__ __forceinline__ void staged_tile_ln(const GemmParams& p, const CUtens
       s1 = add2(s1, xr);
       s2 = fma2(xr, xr, s2);
     }
-    st_shared_v4(row_o + pa, o[0], o[1], o[2], o[3]);
-    st_shared_v4(row_o + pb, o[4], o[5], o[6], o[7]);
+    st_shared_v4(slot + pa, o[0], o[1], o[2], o[3]);
+    st_shared_v4(slot + pb, o[4], o[5], o[6], o[7]);
   };
   issue(0, v[0], bv[0]);
 #pragma unroll 1
-  for (int s = 0; s < 16; s += 2) {
-    if ((s & 3) == 0) {
-      if (!no_tma) mbar_wait(in_bar0 + (s >> 2) * 8, tile_parity);
-      __syncwarp();
-    }
+  for (int c = 0; c < 4; ++c) {
+    const int s = c * 4;
+    if (!no_tma) mbar_wait(in_bar0 + c * 8, tile_parity);
+    __syncwarp();
     tmem_ld_wait();
     issue(s + 1, v[1], bv[1]);
-    pass1(s, v[0], bv[0]);
+    pass1(c, 0, v[0], bv[0]);
     tmem_ld_wait();
-    if (s + 2 < 16) issue(s + 2, v[0], bv[0]);
-    pass1(s + 1, v[1], bv[1]);
-    if ((s & 3) == 2) {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && !no_tma) {
-        tma_store_2d(tmOut, ring + (s >> 2) * EPI_SLOT_BYTES, (s >> 2) * 64, row0);
-        tma_store_commit();
-      }
+    issue(s + 2, v[0], bv[0]);
+    pass1(c, 1, v[1], bv[1]);
+    tmem_ld_wait();
+    issue(s + 3, v[1], bv[1]);
+    pass1(c, 2, v[0], bv[0]);
+    tmem_ld_wait();
+    if (c < 3) issue(s + 4, v[0], bv[0]);
+    pass1(c, 3, v[1], bv[1]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && !no_tma) {
+      tma_store_2d(tmOut, ring + c * EPI_SLOT_BYTES, c * 64, row0);
+      tma_store_commit();
     }
   }
   float a0, a1, q0, q1;
@@ -662,10 +665,10 @@ __device__ __forceinline__ void staged_tile_ln_split(const GemmParams& p, const 
 #pragma unroll
     for (int q = 0; q < 4; ++q) bb[q] = lds4(bias_tile + s * 64 + q * 16);
   };
-  auto pass1 = [&](int sl, const uint32_t (&vv)[16], const float4 (&bb)[4]) {
-    const int c = sl >> 2, h = sl & 3;                                   // local chunk (slot) and 16-column group in it
-    const uint32_t row_o = ring + c * EPI_SLOT_BYTES + lane * 128;
-    const uint32_t pa = ((2u * h) ^ sw) << 4, pb = ((2u * h + 1u) ^ sw) << 4;
+  const uint32_t swz_row = static_cast<uint32_t>(lane) * 128u | (sw << 4);     // see staged_tile
+  auto pass1 = [&](int c, int h, const uint32_t (&vv)[16], const float4 (&bb)[4]) {   // local chunk (slot), group in it
+    const uint32_t row_o = ring + c * EPI_SLOT_BYTES;
+    const uint32_t pa = swz_row ^ (32u * h), pb = swz_row ^ (32u * h + 16u);
     uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
     if (!no_tma) {
       i0 = ld_shared_v4(row_o + pa);
@@ -688,24 +691,27 @@ __device__ __forceinline__ void staged_tile_ln_split(const GemmParams& p, const 
   };
   issue(0, v[0], bv[0]);
 #pragma unroll 1
-  for (int sl = 0; sl < 8; sl += 2) {
-    if ((sl & 3) == 0) {
-      if (!no_tma) mbar_wait(in_bar0 + (sl >> 2) * 8, tile_parity);
-      __syncwarp();
-    }
+  for (int c = 0; c < 2; ++c) {
+    const int sl = c * 4;
+    if (!no_tma) mbar_wait(in_bar0 + c * 8, tile_parity);
+    __syncwarp();
     tmem_ld_wait();
     issue(sl + 1, v[1], bv[1]);
-    pass1(sl, v[0], bv[0]);
+    pass1(c, 0, v[0], bv[0]);
     tmem_ld_wait();
-    if (sl + 2 < 8) issue(sl + 2, v[0], bv[0]);
-    pass1(sl + 1, v[1], bv[1]);
-    if ((sl & 3) == 2) {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && !no_tma) {
-        tma_store_2d(tmOut, ring + (sl >> 2) * EPI_SLOT_BYTES, (cbase + (sl >> 2)) * 64, row0);
-        tma_store_commit();
-      }
+    issue(sl + 2, v[0], bv[0]);
+    pass1(c, 1, v[1], bv[1]);
+    tmem_ld_wait();
+    issue(sl + 3, v[1], bv[1]);
+    pass1(c, 2, v[0], bv[0]);
+    tmem_ld_wait();
+    if (c < 1) issue(sl + 4, v[0], bv[0]);
+    pass1(c, 3, v[1], bv[1]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && !no_tma) {
+      tma_store_2d(tmOut, ring + c * EPI_SLOT_BYTES, (cbase + c) * 64, row0);
+      tma_store_commit();
     }
   }
   // exchange the partial row statistics with the warp that owns the other half of these 32 rows

@@ -473,22 +473,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t v[2][16];
         float4 bv[2][4];
         uint4 iv[2][2];
-        auto issue = [&](int s, uint32_t (&vv)[16], float4 (&bb)[4], uint4 (&ii)[2]) {
+        // h4 (the 16-column group inside a 64-column half) is a compile-time value in the unrolled loop below: the
+        // swizzled piece offsets are an XOR of swz (sw << 4, the low bits of the row address) with a constant
+        const uint32_t swz_blk = hrow | (sw << 4);
+        auto issue = [&](int s, int h4, uint32_t (&vv)[16], float4 (&bb)[4], uint4 (&ii)[2]) {
           tmem_ld_32x32b_x16(t_acc1 + s * 16, vv);
-          const uint32_t blk = hrow + (s >> 2) * KB_BYTES;
-          const uint32_t h4 = static_cast<uint32_t>(s & 3);
+          const uint32_t blk = swz_blk + (s >> 2) * KB_BYTES;
           if (!BWD) {
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) bb[qd] = lds_f4(bias1 + s * 64 + qd * 16);
           } else {
-            ii[0] = ld_shared_v4(blk + (((2u * h4) ^ sw) << 4));
-            ii[1] = ld_shared_v4(blk + (((2u * h4 + 1u) ^ sw) << 4));
+            ii[0] = ld_shared_v4(blk ^ (32u * h4));
+            ii[1] = ld_shared_v4(blk ^ (32u * h4 + 16u));
           }
         };
-        auto process = [&](int s, const uint32_t (&vv)[16], const float4 (&bb)[4], const uint4 (&ii)[2]) {
-          const uint32_t blk = hrow + (s >> 2) * KB_BYTES;
-          const uint32_t h4 = static_cast<uint32_t>(s & 3);
-          const uint32_t pa = ((2u * h4) ^ sw) << 4, pb = ((2u * h4 + 1u) ^ sw) << 4;
+        auto process = [&](int s, int h4, const uint32_t (&vv)[16], const float4 (&bb)[4], const uint4 (&ii)[2]) {
+          const uint32_t blk = swz_blk + (s >> 2) * KB_BYTES;
+          const uint32_t adr_a = blk ^ (32u * h4), adr_b = blk ^ (32u * h4 + 16u);
           uint64_t x[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) x[i] = pk2u(vv[2 * i], vv[2 * i + 1]);
@@ -513,18 +514,24 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = pack2_bf16(mul2(x[i], gelu_bwd2(unpack2_bf16(iw[i]))));
           }
-          st_shared_v4(blk + pa, o[0], o[1], o[2], o[3]);
-          st_shared_v4(blk + pb, o[4], o[5], o[6], o[7]);
+          st_shared_v4(adr_a, o[0], o[1], o[2], o[3]);
+          st_shared_v4(adr_b, o[4], o[5], o[6], o[7]);
         };
-        issue(0, v[0], bv[0], iv[0]);
+        issue(0, 0, v[0], bv[0], iv[0]);
 #pragma unroll 1
-        for (int s = 0; s < HC / 16; s += 2) {
+        for (int s = 0; s < HC / 16; s += 4) {               // one 64-column half per iteration, four steps unrolled
           tmem_ld_wait();
-          issue(s + 1, v[1], bv[1], iv[1]);
-          process(s, v[0], bv[0], iv[0]);
+          issue(s + 1, 1, v[1], bv[1], iv[1]);
+          process(s, 0, v[0], bv[0], iv[0]);
           tmem_ld_wait();
-          if (s + 2 < HC / 16) issue(s + 2, v[0], bv[0], iv[0]);
-          process(s + 1, v[1], bv[1], iv[1]);
+          issue(s + 2, 2, v[0], bv[0], iv[0]);
+          process(s + 1, 1, v[1], bv[1], iv[1]);
+          tmem_ld_wait();
+          issue(s + 3, 3, v[1], bv[1], iv[1]);
+          process(s + 2, 2, v[0], bv[0], iv[0]);
+          tmem_ld_wait();
+          if (s + 4 < HC / 16) issue(s + 4, 0, v[0], bv[0], iv[0]);
+          process(s + 3, 3, v[1], bv[1], iv[1]);
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&acc1_empty[wg]));              // accumulator drained
