@@ -62,6 +62,15 @@ struct FwdParams {
   int reverse;             // 1 = items are walked in descending order
 };
 
+// 2^x for x <= 0 (scores minus their row maximum / log-sum-exp): one MUFU.EX2.  exp2f() wraps the same instruction in a
+// range check and two scalings for denormal results (FSETP + 2 FMUL per element, a third of the softmax loop); results
+// below 2^-126 are flushed to zero here, far below what a bf16 probability can hold.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -195,7 +204,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          x[j] = exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2, -m2));
+          x[j] = ex2_fast(fmaf(__uint_as_float(v[j]), p.scale_log2, -m2));
           sum += x[j];
         }
         store_row_chunk_bf16(p_buf, r, c * 32, x);
@@ -431,7 +440,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          x[j] = exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse2));
+          x[j] = ex2_fast(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse2));
           delta = fmaf(x[j], __uint_as_float(dv[j]), delta);
         }
 #pragma unroll
