@@ -194,3 +194,15 @@ def test_colsum_meanpool_mse_cast(cuda_lib):
 
     src = torch.randn(100003, generator=g)
     assert torch.equal(ops.cast_f32_bf16(src.cuda()).cpu(), src.bfloat16())
+
+
+def test_rician_channel_matches_golden_v1(cuda_lib):
+    """native fused channel kernel against the committed oracle outputs of scripts/make_golden_v1.py."""
+    import os
+    from multimodal_sc_b200 import ops
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_v1.pt"))
+    gen = torch.Generator().manual_seed(11)
+    z = torch.randn(3, 2, SPEC.k_sym, generator=gen) * 0.4
+    snr = torch.tensor([-3.0, 6.0, 15.0])
+    y, _, _ = ops.pnorm_channel_fwd(z.cuda(), "rician", snr.cuda(), seed=99, sample_offset=5, rician_k=2.5)
+    _close(y, g["rician_k2.5_seed99_off5_y"], 1e-5, 2e-5, "rician golden")

@@ -235,6 +235,11 @@ def test_forward_matches_committed_golden_vectors(cuda_lib):
             assert abs(float(aux["l_sem"]) - float(g[f"fwd_{kind}_l_sem"])) < 2e-2 * float(g[f"fwd_{kind}_l_sem"])
             assert _rel(aux["y"][:, :, :8], g[f"fwd_{kind}_y_head"]) < 2e-2
             assert _rel(aux["z"][:, :, :8], g[f"fwd_{kind}_z_head"]) < 2e-2
+        g1 = torch.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_v1.pt"))      # round-1 additions
+        l, v, aux = pol(mb["cam"].cuda(), mb["bev"].cuda(), 10.0, channel="rician", seed=1234)
+        assert _rel(l, g1["fwd_rician_logits"]) < 2e-2 and _rel(v, g1["fwd_rician_value"]) < 2e-2
+        assert abs(float(aux["l_sem"]) - float(g1["fwd_rician_l_sem"])) < 2e-2 * float(g1["fwd_rician_l_sem"])
+        assert _rel(aux["y"][:, :, :8], g1["fwd_rician_y_head"]) < 2e-2
 
 
 @pytest.mark.parametrize("name,switches", [

@@ -178,3 +178,15 @@ def test_golden_vectors():
     adv, ret = oppo.gae(r, v, d, lv, SPEC.gamma, SPEC.lam)
     assert torch.allclose(adv, g["gae_adv"], rtol=1e-6) and torch.allclose(ret, g["gae_ret"], rtol=1e-6)
     assert torch.allclose(oppo.normalize_adv(adv, SPEC.adv_eps), g["gae_adv_norm"], rtol=1e-5, atol=1e-6)
+
+
+def test_golden_vectors_v1_rician():
+    """oracle against tests/golden/oracle_v1.pt (scripts/make_golden_v1.py): pins the Rician channel added in round 1."""
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_v1.pt"))
+    gen = torch.Generator().manual_seed(11)
+    z = torch.randn(3, 2, SPEC.k_sym, generator=gen) * 0.4
+    snr = torch.tensor([-3.0, 6.0, 15.0])
+    y, _ = och.channel_forward(z, snr, "rician", seed=99, sample_offset=5, rician_k=2.5)
+    assert torch.allclose(y, g["rician_k2.5_seed99_off5_y"], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(och.rician_fading(och.make_fading(99, 3, 5), 2.5), g["rician_fading_seed99_b3_off5_k2.5"],
+                          rtol=1e-6, atol=1e-7)
