@@ -31,7 +31,7 @@ extern "C" {
 #define SC_E_LAUNCH (-4)
 #define SC_E_DRIVER (-5)
 
-#define SC_ABI_VERSION 2
+#define SC_ABI_VERSION 3
 
 /* channel kinds (SPEC v0 a4) */
 #define SC_CH_NONE 0
@@ -43,6 +43,7 @@ extern "C" {
 #define SC_ACT_NONE 0
 #define SC_ACT_GELU 1 /* tanh-form GELU */
 #define SC_ACT_TANH 2
+#define SC_ACT_GELU_ERF 3 /* exact GELU x Phi(x) (SURVEY.md 8 froze "GELU(tanh approx = False)"; SpecV0.gelu = "erf") */
 
 int sc_version(void);
 const char* sc_last_error(void);
@@ -106,6 +107,7 @@ typedef struct sc_gemm_epilogue {
   float* ln_mean;
   float* ln_rstd;
   float ln_eps;
+  int32_t aux_in_erf;      /* != 0: the GELU' applied to aux_in is the exact (erf) form instead of the tanh form */
 } sc_gemm_epilogue;
 
 int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int a_mn, int b_mn,
@@ -142,10 +144,12 @@ int sc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
 /* ---------------------------------------------------------------------------------------
  * Memory-bound fused kernels.
  * ------------------------------------------------------------------------------------- */
-/* a1/a2: img [B,C,H,W] (fp32, or bf16 when img_is_bf16 != 0) -> patch tokens bf16
- * [B*(H/P)*(W/P), C*P*P], feature order (c,py,px); the fp32 -> bf16 cast is fused here. */
+/* a1/a2: img [*,C,H,W] (fp32, or bf16 when img_is_bf16 != 0) -> patch tokens bf16
+ * [B*(H/P)*(W/P), C*P*P], feature order (c,py,px); the fp32 -> bf16 cast is fused here.
+ * row_idx (device int64 [B], optional): output sample b reads image row_idx[b] — the minibatch gather of
+ * PPOAgent.update (a10) is fused into this pass, so no gathered copy of the observations is ever made. */
 int sc_patchify_bf16(const void* img, int img_is_bf16, void* out, int64_t B, int C, int H, int W,
-                     int P, void* stream);
+                     int P, const int64_t* row_idx, void* stream);
 
 /* LayerNorm over the last dim D (D % 256 == 0, D <= 1024).  io_f32: 0 = bf16 x/y, 1 = fp32 x/y.
  * mean/rstd: fp32 [M] saved for backward (may be null in fwd for inference). */
@@ -167,20 +171,30 @@ int sc_colsum_bf16(const void* x, float* out, int64_t M, int N, int64_t ld, void
  * noise / fading: optional explicit tensors (fp32 [B,2,k] / [B,2,2]) replacing the Philox draw.
  * y_f32 / y_bf16: either may be null.  Counter layout: see oracle/philox.py.
  * rician_k: linear K-factor of SC_CH_RICIAN (>= 0; ignored by the other kinds; K = 0 is Rayleigh).  An explicit
- * `fading` tensor is the channel coefficient h itself for both fading kinds. */
+ * `fading` tensor is the channel coefficient h itself for both fading kinds.
+ * sample_idx (device int64 [B], optional): GLOBAL sample index of local sample b for the Philox counters (default
+ * sample_offset + b) — a data-parallel rank that holds an arbitrary subset of the global minibatch draws the same
+ * noise as the 1-rank run.
+ * quant_bits > 0: the normalised symbols pass a 2^bits-level mid-rise uniform quantiser on [-quant_clip, quant_clip]
+ * before the channel (oracle/channel.py: quantize_ste); backward is the clipped straight-through
+ * estimator. */
 int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f32, void* y_bf16,
                          int64_t y_sb, int64_t y_sm, float* scale, int64_t B, int k, int kind, float rician_k,
                          const float* snr_db, float snr_db_scalar, uint64_t seed,
-                         int64_t sample_offset, const float* noise, const float* fading,
-                         float eps, const uint64_t* seed_dev, void* stream);
+                         int64_t sample_offset, const int64_t* sample_idx, const float* noise, const float* fading,
+                         float eps, const uint64_t* seed_dev, int quant_bits, float quant_clip, void* stream);
 /* dz = scale * (g - zn * mean(g * zn)),  g = dy (AWGN/none) or |h|^2/(|h|^2+sigma^2) dy (Rayleigh / Rician) */
 int sc_pnorm_channel_bwd(const float* dy, int64_t y_sb, int64_t y_sm, const float* z, int64_t z_sb,
                          int64_t z_sm, const float* scale, float* dz_f32, void* dz_bf16, int64_t B,
                          int k, int kind, float rician_k, const float* snr_db, float snr_db_scalar, uint64_t seed,
-                         int64_t sample_offset, const float* fading, const uint64_t* seed_dev, void* stream);
+                         int64_t sample_offset, const int64_t* sample_idx, const float* fading,
+                         const uint64_t* seed_dev, int quant_bits, float quant_clip, void* stream);
 /* raw Philox words for parity tests: out u32 [n_quads,4], counters quad_offset.. */
 int sc_philox_words(uint32_t* out, int64_t n_quads, uint32_t stream_id, uint64_t seed,
                     int64_t quad_offset, void* stream);
+/* the in-kernel normal generator itself (stream 0, Box-Muller on the words above): out fp32 [n_quads, 4];
+ * exact != 0 selects the accurate logf / sincospif form, 0 the bounded-error SFU form the channel kernel uses */
+int sc_philox_normals(float* out, int64_t n_quads, uint64_t seed, int64_t quad_offset, int exact, void* stream);
 
 /* a5: mean over S tokens: x bf16 [B,S,D] -> out_bf16 [B,D] (and fp32 copy, optional) */
 int sc_meanpool_fwd(const void* x, void* out_bf16, float* out_f32, int64_t B, int S, int D,
@@ -218,9 +232,11 @@ int sc_adv_normalize(float* adv, const double* sums, int64_t count, int64_t n, f
 
 /* a9: PPO clipped loss, forward + backward fused.
  * head_out fp32 [M, ld] (A logits + value); writes dho fp32 [M, ld] (d total / d head_out, incl.
- * the 1/M_global factor) and accumulates stats[8] += {pi, v, ent, kl, clipfrac, 0,0,0} * inv_m */
+ * the 1/M_global factor) and accumulates stats[8] += {pi, v, ent, kl, clipfrac, 0,0,0} * inv_m
+ * idx (device int64 [M], optional): sample i reads actions / logp_old / adv / ret at idx[i] (the minibatch gather of
+ * PPOAgent.update fused into the loss; head_out and dho stay indexed by i). */
 int sc_ppo_loss(const float* head_out, int ld, const int64_t* actions, const float* logp_old,
-                const float* adv, const float* ret, float* dho, float* stats, int64_t M, int A,
+                const float* adv, const float* ret, const int64_t* idx, float* dho, float* stats, int64_t M, int A,
                 float clip_eps, float c_v, float c_ent, float inv_m, void* stream);
 
 /* a10: fused Adam over the flat parameter bucket; also refreshes the bf16 shadow copy.
@@ -233,6 +249,22 @@ int sc_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int
                  void* stream);
 
 int sc_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* a10: first kernel of an optimizer step: zero the flat gradient bucket (n floats, n % 4 == 0) and the statistics
+ * vector (n_stats floats), and advance the device-side step counter (*step_dev += 1, optional) that the channel seed
+ * and Adam's bias correction read inside a captured CUDA graph — one launch instead of two memsets and an add. */
+int sc_step_begin(float* grad, int64_t n, float* stats, int n_stats, int64_t* step_dev, void* stream);
+
+/* SURVEY.md 8f rank 3, SNR-conditioned encoders (oracle/model.py: SnrEmbed): per-sample embedding of the channel SNR
+ *   h[b, e] = tanh(s_b u[e] + v[e]),  emb[b, d] = sum_e W[d, e] h[b, e],  s_b = snr_db[b] / 20 (or the scalar)
+ * added to every token of sample b by the patch-embedding GEMM (rowgrp epilogue).  u, v fp32 [E], W fp32 [D, E],
+ * emb fp32 [B, D], h fp32 [B, E] (saved for backward).  E <= 256, D <= 1024.
+ * bwd: dW += demb^T h, du += sum_b dh s_b, dv += sum_b dh with dh = (demb W) (1 - h^2); demb is multiplied by
+ * demb_scale first (the caller passes the per-sample MEAN of the token gradients and demb_scale = tokens). */
+int sc_snr_embed_fwd(const float* snr_db, float snr_db_scalar, const float* u, const float* v, const float* W,
+                     float* emb, float* h, int64_t B, int D, int E, void* stream);
+int sc_snr_embed_bwd(const float* demb, const float* h, const float* snr_db, float snr_db_scalar, const float* W,
+                     float* dW, float* du, float* dv, float demb_scale, int64_t B, int D, int E, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,9 +12,10 @@ import torch
 
 LIB_PATH = Path(__file__).resolve().parent / "libsemcom_sm100.so"
 
-ABI_VERSION = 2          # SC_ABI_VERSION in include/semcom_sm100.h (2: rician_k argument of the channel entry points)
+ABI_VERSION = 3          # SC_ABI_VERSION in include/semcom_sm100.h (3: index arguments for the fused minibatch gather /
+                         # ragged data-parallel slices, quantised symbols, SNR embedding, erf GELU, sc_step_begin)
 SC_CH = {"none": 0, "awgn": 1, "rayleigh": 2, "rician": 3}
-SC_ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2}
+SC_ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2, "gelu_erf": 3}
 
 
 class SemcomError(RuntimeError):
@@ -46,6 +47,7 @@ class GemmEpilogue(C.Structure):
         ("ln_mean", C.c_void_p),
         ("ln_rstd", C.c_void_p),
         ("ln_eps", C.c_float),
+        ("aux_in_erf", C.c_int32),
     ]
 
 
@@ -63,14 +65,15 @@ _PROTOS = {
     "sc_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_attn_fwd": [_P, _P, _P, _I64, _I, _I, _P],
     "sc_attn_bwd": [_P, _P, _P, _P, _P, _I64, _I, _I, _P],
-    "sc_patchify_bf16": [_P, _I, _P, _I64, _I, _I, _I, _I, _P],
+    "sc_patchify_bf16": [_P, _I, _P, _I64, _I, _I, _I, _I, _P, _P],
     "sc_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _F, _I, _P],
     "sc_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_colsum_bf16": [_P, _P, _I64, _I, _I64, _P],
     "sc_pnorm_channel_fwd": [_P, _I64, _I64, _P, _P, _I64, _I64, _P, _I64, _I, _I, _F, _P, _F, _U64, _I64,
-                             _P, _P, _F, _P, _P],
+                             _P, _P, _P, _F, _P, _I, _F, _P],
     "sc_pnorm_channel_bwd": [_P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I64, _I, _I, _F, _P, _F, _U64,
-                             _I64, _P, _P, _P],
+                             _I64, _P, _P, _P, _I, _F, _P],
+    "sc_philox_normals": [_P, _I64, _U64, _I64, _I, _P],
     "sc_philox_words": [_P, _I64, _U32, _U64, _I64, _P],
     "sc_meanpool_fwd": [_P, _P, _P, _I64, _I, _I, _P],
     "sc_mse_fwd_bwd": [_P, _P, _P, _I, _I, _P, _P, _I64, _F, _F, _P],
@@ -79,9 +82,12 @@ _PROTOS = {
     "sc_sample_action": [_P, _I, _P, _P, _P, _I64, _I, _P],
     "sc_gae": [_P, _P, _P, _P, _P, _P, _P, _I, _I64, _F, _F, _P],
     "sc_adv_normalize": [_P, _P, _I64, _I64, _F, _P],
-    "sc_ppo_loss": [_P, _I, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _F, _F, _F, _P],
+    "sc_ppo_loss": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _F, _F, _F, _P],
     "sc_adam_flat": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P, _P],
     "sc_cast_f32_bf16": [_P, _P, _I64, _P],
+    "sc_step_begin": [_P, _I64, _P, _I, _P, _P],
+    "sc_snr_embed_fwd": [_P, _F, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
+    "sc_snr_embed_bwd": [_P, _P, _P, _F, _P, _P, _P, _P, _F, _I64, _I, _I, _P],
 }
 _RESTYPES = {"sc_last_error": C.c_char_p, "sc_launch_count": C.c_int64}
 
@@ -137,7 +143,10 @@ def check(rc: int, what: str = "") -> None:
         raise SemcomError(f"{what or 'libsemcom_sm100'} failed (rc={rc}): {last_error()}")
 
 
-def stream_ptr() -> int:
+def stream_ptr(ref=None) -> int:
+    """current stream of the device the operands live on (`ref`: any operand tensor), not of the current device"""
+    if ref is not None and ref.is_cuda:
+        return torch.cuda.current_stream(ref.device).cuda_stream
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -557,7 +557,10 @@ int sc_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int S, int H,
   p.num_items = (int)((M + 127) / 128) * H;
   p.scale_log2 = kLog2e * 0.125f;
   p.reverse = sc_take_direction();
-  static bool attr = false;
+  static bool attr_dev[64] = {};                             // the opt-in is a per-device attribute of the function
+  const int dev = sc_device_index();
+  SC_REQUIRE(dev >= 0, SC_E_LAUNCH, "sc_attn_fwd: cudaGetDevice failed");
+  bool& attr = attr_dev[dev];
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(1));
     if (e == cudaSuccess)
@@ -598,7 +601,10 @@ int sc_attn_bwd(const void* qkv, const void* out, const void* dout, const float*
   p.scale_log2 = kLog2e * 0.125f;
   p.scale = 0.125f;
   p.reverse = sc_take_direction();
-  static bool attr = false;
+  static bool attr_dev[64] = {};
+  const int dev = sc_device_index();
+  SC_REQUIRE(dev >= 0, SC_E_LAUNCH, "sc_attn_bwd: cudaGetDevice failed");
+  bool& attr = attr_dev[dev];
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
     SC_REQUIRE(e == cudaSuccess, SC_E_LAUNCH, "sc_attn_bwd: smem attribute: %s", cudaGetErrorString(e));

@@ -25,6 +25,7 @@ typedef __nv_bfloat162 bf162;
 void sc_set_error(const char* fmt, ...);
 int sc_check_device();                 // SC_OK or SC_E_ARCH (device is not sm_100)
 int sc_num_sms();
+int sc_device_index();               // current device (0..63), -1 on error; function attributes are per device
 void sc_count_launch(int n);           // feeds sc_launch_count()
 int sc_encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
                            uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);

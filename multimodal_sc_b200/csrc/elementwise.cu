@@ -55,7 +55,7 @@ __device__ __forceinline__ void cvt_raw(const Raw8<float>& r, float (&x)[8]) {
 template <typename TI>
 __global__ void __launch_bounds__(kThreads)
 patchify_kernel(const TI* __restrict__ img, bf16* __restrict__ out, int64_t groups, int C, int H,
-                int W, int P) {
+                int W, int P, const int64_t* __restrict__ row_idx) {
   pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   const int Wt = W / P, Ht = H / P;
   const int K = C * P * P;
@@ -78,7 +78,8 @@ patchify_kernel(const TI* __restrict__ img, bf16* __restrict__ out, int64_t grou
         const int c = kg / (P8 * P);
         const int tx = static_cast<int>(tok % Wt);
         const int ty = static_cast<int>((tok / Wt) % Ht);
-        const int64_t b = tok / (Wt * Ht);
+        int64_t b = tok / (Wt * Ht);
+        if (row_idx) b = __ldg(row_idx + b);            // fused minibatch gather: output sample -> stored image
         ld_raw(img + ((b * C + c) * H + (ty * P + py)) * static_cast<int64_t>(W) + tx * P + px0, raw[u]);
       }
     }
@@ -410,7 +411,8 @@ cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
 
 extern "C" {
 
-int sc_patchify_bf16(const void* img, int img_is_bf16, void* out, int64_t B, int C, int H, int W, int P, void* stream) {
+int sc_patchify_bf16(const void* img, int img_is_bf16, void* out, int64_t B, int C, int H, int W, int P,
+                     const int64_t* row_idx, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(img && out, SC_E_SHAPE, "sc_patchify_bf16: null pointer");
@@ -421,9 +423,9 @@ int sc_patchify_bf16(const void* img, int img_is_bf16, void* out, int64_t B, int
   const int64_t groups = B * C * H * (int64_t)W / 8;
   const int grid = persistent_blocks((groups + kThreads - 1) / kThreads, 8);
   if (img_is_bf16)
-    sc_launch_kernel(patchify_kernel<bf16>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const bf16*)img, (bf16*)out, groups, C, H, W, P);
+    sc_launch_kernel(patchify_kernel<bf16>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const bf16*)img, (bf16*)out, groups, C, H, W, P, row_idx);
   else
-    sc_launch_kernel(patchify_kernel<float>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const float*)img, (bf16*)out, groups, C, H, W, P);
+    sc_launch_kernel(patchify_kernel<float>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, (const float*)img, (bf16*)out, groups, C, H, W, P, row_idx);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_patchify_bf16");
   return SC_OK;

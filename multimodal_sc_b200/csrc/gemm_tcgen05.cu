@@ -105,6 +105,7 @@ struct GemmParams {
   float* out_f32;
   int64_t ldo;
   int act;
+  int aux_in_erf;
   int atomic;
   int vec_ok;
   int epi_mode;
@@ -155,9 +156,16 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
   return it;
 }
 
+// exact GELU x Phi(x) and its derivative Phi(x) + x phi(x) (SpecV0.gelu == "erf"; generic epilogue paths only)
+__device__ __forceinline__ float gelu_erf_fwd(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_bwd(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
 template <bool kFast>
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == SC_ACT_GELU) return gelu_fwd<kFast>(x);
+  if (act == SC_ACT_GELU_ERF) return gelu_erf_fwd(x);
   if (act == SC_ACT_TANH) return kFast ? tanh_fast(x) : tanhf(x);
   return x;
 }
@@ -203,10 +211,9 @@ __device__ __forceinline__ void epilogue_vec8(const GemmParams& p, const uint32_
   if (p.aux_in) {
     uint4 w = __ldg(reinterpret_cast<const uint4*>(p.aux_in + off));
     float2 a0 = unpack_bf16(w.x), a1 = unpack_bf16(w.y), a2 = unpack_bf16(w.z), a3 = unpack_bf16(w.w);
-    x[0] *= gelu_bwd<true>(a0.x); x[1] *= gelu_bwd<true>(a0.y);
-    x[2] *= gelu_bwd<true>(a1.x); x[3] *= gelu_bwd<true>(a1.y);
-    x[4] *= gelu_bwd<true>(a2.x); x[5] *= gelu_bwd<true>(a2.y);
-    x[6] *= gelu_bwd<true>(a3.x); x[7] *= gelu_bwd<true>(a3.y);
+    const float av[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] *= p.aux_in_erf ? gelu_erf_bwd(av[j]) : gelu_bwd<true>(av[j]);
   }
   if (p.resid) {
     uint4 w = __ldg(reinterpret_cast<const uint4*>(p.resid + off));
@@ -241,7 +248,10 @@ __device__ __noinline__ void epilogue_scalar(const GemmParams& p, float a, int64
   const int64_t off = row * p.ldo + col;
   if (p.aux_out) p.aux_out[off] = __float2bfloat16(x);
   x = apply_act<true>(x, p.act);
-  if (p.aux_in) x *= gelu_bwd<true>(__bfloat162float(p.aux_in[off]));
+  if (p.aux_in) {
+    const float av = __bfloat162float(p.aux_in[off]);
+    x *= p.aux_in_erf ? gelu_erf_bwd(av) : gelu_bwd<true>(av);
+  }
   if (p.resid) x += __bfloat162float(p.resid[off]);
   if (p.out_bf16) p.out_bf16[off] = __float2bfloat16(x);
   if (p.out_f32) {
@@ -1285,7 +1295,10 @@ DebugOverrides g_dbg;
 template <int A_MN, int B_MN, int CTA2, int NWG, int SLOTS>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAux,
            const CUtensorMap& tmIn, const GemmParams& p, int grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};                         // the opt-in is a per-device attribute of the function
+  const int dev = sc_device_index();
+  if (dev < 0) { sc_set_error("sc_gemm_bf16: cudaGetDevice failed"); return SC_E_LAUNCH; }
+  bool& attr_set = attr_set_dev[dev];
   auto kern = gemm_tcgen05_kernel<A_MN, B_MN, CTA2, NWG, SLOTS>;
   constexpr int smem = Geo<CTA2, NWG, SLOTS>::TOTAL;
   constexpr int threads = Geo<CTA2, NWG, SLOTS>::THREADS;
@@ -1332,6 +1345,8 @@ void sc_attn_debug_set_fwd_stages(int v);
 void sc_pdl_set(int v);
 void sc_mlp_debug_set(int v);
 void sc_alternate_set(int v);
+void sc_tmap_cache_set(int on);
+extern "C" int g_chan_exact;
 
 extern "C" int sc_debug_set(const char* key, int64_t value) {
   if (!key) return SC_E_SHAPE;
@@ -1339,6 +1354,8 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   if (!strcmp(key, "pdl")) { sc_pdl_set((int)value); return SC_OK; }
   if (!strcmp(key, "mlp_dbg")) { sc_mlp_debug_set((int)value); return SC_OK; }
   if (!strcmp(key, "alternate")) { sc_alternate_set((int)value); return SC_OK; }
+  if (!strcmp(key, "tmap_cache")) { sc_tmap_cache_set((int)value); return SC_OK; }
+  if (!strcmp(key, "chan_exact")) { g_chan_exact = (int)value; return SC_OK; }
   if (!strcmp(key, "a_lbo")) g_dbg.a_lbo = value;
   else if (!strcmp(key, "a_sbo")) g_dbg.a_sbo = value;
   else if (!strcmp(key, "a_kstep")) g_dbg.a_kstep = value;
@@ -1382,7 +1399,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   SC_REQUIRE(epi->ldo >= N, SC_E_SHAPE, "sc_gemm_bf16: ldo < N");
   SC_REQUIRE(!epi->rowadd || epi->rowadd_period > 0, SC_E_SHAPE, "sc_gemm_bf16: rowadd_period must be > 0");
   SC_REQUIRE(!epi->rowgrp || epi->rowgrp_size > 0, SC_E_SHAPE, "sc_gemm_bf16: rowgrp_size must be > 0");
-  SC_REQUIRE(epi->act >= SC_ACT_NONE && epi->act <= SC_ACT_TANH, SC_E_SHAPE, "sc_gemm_bf16: bad act");
+  SC_REQUIRE(epi->act >= SC_ACT_NONE && epi->act <= SC_ACT_GELU_ERF, SC_E_SHAPE, "sc_gemm_bf16: bad act");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -1426,6 +1443,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   p.out_f32 = epi->out_f32;
   p.ldo = epi->ldo;
   p.act = epi->act;
+  p.aux_in_erf = epi->aux_in_erf;
   p.atomic = epi->atomic;
   p.colsum = epi->colsum;
   p.dbg = static_cast<int>(g_dbg.gemm_dbg);
@@ -1475,7 +1493,10 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   SC_REQUIRE(!(epi->rowadd && epi->rowadd_bf16), SC_E_SHAPE, "sc_gemm_bf16: pass rowadd or rowadd_bf16, not both");
   SC_REQUIRE(!epi->rowadd_bf16 || epi->rowadd_period > 0, SC_E_SHAPE, "sc_gemm_bf16: rowadd_period must be > 0");
   bool staged_ok = false;
-  if (!g_dbg.generic_epi && p.vec_ok && sc_aligned16(epi->rowadd_bf16) && epi->out_bf16 && !epi->out_f32 && p.ksplit == 1 && (no_in || one_in) &&
+  // the exact (erf) GELU exists only in the direct-store epilogue: it is an off-by-default spec variant, and its
+  // polynomial would cost the staged kinds (one kernel, one register allocation) registers they do not have
+  const bool erf_epi = epi->act == SC_ACT_GELU_ERF || (epi->aux_in && epi->aux_in_erf);
+  if (!g_dbg.generic_epi && !erf_epi && p.vec_ok && sc_aligned16(epi->rowadd_bf16) && epi->out_bf16 && !epi->out_f32 && p.ksplit == 1 && (no_in || one_in) &&
       !(one_in && epi->aux_out) && N % BN == 0) {
     staged_ok = true;
     p.epi_mode = one_in ? EPI_IN : (epi->aux_out ? EPI_OUT2 : EPI_OUT1);
@@ -1486,7 +1507,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
       else if (b && epi->act == SC_ACT_NONE && !epi->aux_out && no_in) p.epi_kind = KIND_BIAS;
       else if (b && epi->act == SC_ACT_GELU && epi->aux_out && no_in) p.epi_kind = KIND_FC1;
       else if (b && epi->act == SC_ACT_NONE && (epi->resid || pos16)) p.epi_kind = epi->ln_out ? KIND_RESID_LN : KIND_RESID;
-      else if (!b && epi->act == SC_ACT_NONE && epi->aux_in) p.epi_kind = KIND_DGELU;
+      else if (!b && epi->act == SC_ACT_NONE && epi->aux_in && !epi->aux_in_erf) p.epi_kind = KIND_DGELU;
     }
     const uint64_t ldb_bytes = (uint64_t)epi->ldo * 2;
     if ((rc = sc_encode_tmap_2d_bf16(&tmOut, epi->out_bf16, (uint64_t)N, (uint64_t)M, ldb_bytes, 64, 32)) != SC_OK) return rc;

@@ -619,7 +619,10 @@ template <int BWD, int MC>
 int launch_mlp_impl(const CUtensorMap& tmX, const CUtensorMap& tmWa, const CUtensorMap& tmWb, const CUtensorMap& tmH,
                     const CUtensorMap& tmHin, const CUtensorMap& tmResid, const MlpParams& p, cudaStream_t st,
                     const char* name) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};                         // the opt-in is a per-device attribute of the function
+  const int dev = sc_device_index();
+  if (dev < 0) { sc_set_error("%s: cudaGetDevice failed", name); return SC_E_LAUNCH; }
+  bool& attr_set = attr_set_dev[dev];
   auto kern = mlp_fused_kernel<BWD, MC>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);

@@ -300,8 +300,8 @@ adv_normalize_kernel(float* __restrict__ adv, const double* __restrict__ sums, i
 __global__ void __launch_bounds__(kThreads)
 ppo_loss_kernel(const float* __restrict__ ho, int ld, const int64_t* __restrict__ actions,
                 const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
-                float* __restrict__ dho, float* __restrict__ stats, int64_t M, int A, float clip_eps, float c_v,
-                float c_ent, float inv_m) {
+                const int64_t* __restrict__ idx, float* __restrict__ dho, float* __restrict__ stats, int64_t M, int A,
+                float clip_eps, float c_v, float c_ent, float inv_m) {
   pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
   __shared__ float red[5][kThreads / 32];
   float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -318,8 +318,10 @@ ppo_loss_kernel(const float* __restrict__ ho, int ld, const int64_t* __restrict_
     for (int j = 0; j < kMaxA1; ++j)
       if (j < A) se += expf(lg[j] - mx);
     const float lse = mx + logf(se);
-    const int a = static_cast<int>(actions[i]);
-    float ent = 0.f, logp = 0.f;
+    const int64_t src = idx ? idx[i] : i;                      // fused minibatch gather of the rollout vectors
+    const int a = static_cast<int>(actions[src]);
+    // an action outside [0, A) poisons the statistics instead of silently contributing logp = 0
+    float ent = 0.f, logp = (a >= 0 && a < A) ? 0.f : __int_as_float(0x7fc00000);
     float p[kMaxA1], lp[kMaxA1];
 #pragma unroll
     for (int j = 0; j < kMaxA1; ++j)
@@ -329,19 +331,20 @@ ppo_loss_kernel(const float* __restrict__ ho, int ld, const int64_t* __restrict_
         ent -= p[j] * lp[j];
         if (j == a) logp = lp[j];
       }
-    const float Ad = adv[i];
-    const float ratio = expf(logp - logp_old[i]);
+    const float Ad = adv[src];
+    const float lp_old = logp_old[src];
+    const float ratio = expf(logp - lp_old);
     const float s1 = ratio * Ad;
     const float rc = fminf(fmaxf(ratio, 1.f - clip_eps), 1.f + clip_eps);
     const float s2 = rc * Ad;
     const bool inside = (ratio >= 1.f - clip_eps) && (ratio <= 1.f + clip_eps);
     const float gmin = (inside || s1 < s2) ? Ad : 0.f;          // d min(s1,s2) / d ratio
     const float v = l[A];
-    const float dv = v - ret[i];
+    const float dv = v - ret[src];
     st[0] += -fminf(s1, s2);
     st[1] += 0.5f * dv * dv;
     st[2] += ent;
-    st[3] += logp_old[i] - logp;
+    st[3] += lp_old - logp;
     st[4] += (fabsf(ratio - 1.f) > clip_eps) ? 1.f : 0.f;
     // d total / d logit_j = inv_m * [ -gmin*ratio*(1[j==a] - p_j) + c_ent * p_j (lp_j + ent) ]
     const float gp = -gmin * ratio;
@@ -362,6 +365,95 @@ ppo_loss_kernel(const float* __restrict__ ho, int ld, const int64_t* __restrict_
     for (int w = 0; w < kThreads / 32; ++w) t += red[threadIdx.x][w];
     atomicAdd(stats + threadIdx.x, t * inv_m);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// step_begin: zero the flat gradient bucket and the statistics, advance the device-side step counter
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+step_begin_kernel(float4* __restrict__ grad, int64_t n4, float* __restrict__ stats, int n_stats,
+                  int64_t* __restrict__ step_dev) {
+  pdl_sync();
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (int64_t i = t; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < n_stats) stats[t] = 0.f;
+  if (t == 0 && step_dev) *step_dev += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// SNR embedding (SNR-conditioned encoders): h = tanh(s u + v), emb = W h
+// fwd: one CTA per sample (h in shared memory, thread d owns emb[b, d]).
+// bwd: CTA per 8-sample group computes dh[b, :] = (demb[b, :] W) (1 - h^2) in shared memory and accumulates
+//      du / dv; dW[d, e] += sum_b demb[b, d] h[b, e] by a second kernel with one thread per (d, e).
+// ------------------------------------------------------------------------------------------
+constexpr int kSnrMaxE = 256;
+
+__global__ void __launch_bounds__(kThreads)
+snr_embed_fwd_kernel(const float* __restrict__ snr_db, float snr_scalar, const float* __restrict__ u,
+                     const float* __restrict__ v, const float* __restrict__ W, float* __restrict__ emb,
+                     float* __restrict__ h, int64_t B, int D, int E) {
+  pdl_sync();
+  __shared__ float hs[kSnrMaxE];
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const float s = (snr_db ? snr_db[b] : snr_scalar) * 0.05f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const float t = tanhf(fmaf(s, u[e], v[e]));
+      hs[e] = t;
+      h[b * E + e] = t;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float* w = W + static_cast<int64_t>(d) * E;
+      float acc = 0.f;
+      for (int e = 0; e < E; ++e) acc = fmaf(w[e], hs[e], acc);
+      emb[b * D + d] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// du[e] += sum_b dh[b, e] s_b, dv[e] += sum_b dh[b, e]; dh = (demb W) (1 - h^2).  One CTA per sample group.
+__global__ void __launch_bounds__(kThreads)
+snr_embed_bwd_uv_kernel(const float* __restrict__ demb, const float* __restrict__ h, const float* __restrict__ snr_db,
+                        float snr_scalar, const float* __restrict__ W, float* __restrict__ du, float* __restrict__ dv,
+                        float demb_scale, int64_t B, int D, int E) {
+  pdl_sync();
+  __shared__ float ds[1024];
+  const int e = threadIdx.x;
+  float au = 0.f, av = 0.f;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) ds[d] = demb[b * D + d] * demb_scale;
+    __syncthreads();
+    if (e < E) {
+      float acc = 0.f;
+      for (int d = 0; d < D; ++d) acc = fmaf(ds[d], W[static_cast<int64_t>(d) * E + e], acc);
+      const float t = h[b * E + e];
+      const float dh = acc * (1.0f - t * t);
+      const float s = (snr_db ? snr_db[b] : snr_scalar) * 0.05f;
+      au = fmaf(dh, s, au);
+      av += dh;
+    }
+    __syncthreads();
+  }
+  if (e < E) {
+    atomicAdd(du + e, au);
+    atomicAdd(dv + e, av);
+  }
+}
+
+// dW[d, e] += sum_b demb[b, d] h[b, e]: one thread per (d, e), the batch split over gridDim.y
+__global__ void __launch_bounds__(kThreads)
+snr_embed_bwd_w_kernel(const float* __restrict__ demb, const float* __restrict__ h, float* __restrict__ dW,
+                       float demb_scale, int64_t B, int D, int E) {
+  pdl_sync();
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= static_cast<int64_t>(D) * E) return;
+  const int d = static_cast<int>(t / E), e = static_cast<int>(t % E);
+  const int64_t per = (B + gridDim.y - 1) / gridDim.y;
+  const int64_t b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  float acc = 0.f;
+  for (int64_t b = b0; b < b1; ++b) acc = fmaf(demb[b * D + d], h[b * E + e], acc);
+  atomicAdd(dW + t, acc * demb_scale);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -502,17 +594,64 @@ int sc_adv_normalize(float* adv, const double* sums, int64_t count, int64_t n, f
 }
 
 int sc_ppo_loss(const float* head_out, int ld, const int64_t* actions, const float* logp_old, const float* adv,
-                const float* ret, float* dho, float* stats, int64_t M, int A, float clip_eps, float c_v,
-                float c_ent, float inv_m, void* stream) {
+                const float* ret, const int64_t* idx, float* dho, float* stats, int64_t M, int A, float clip_eps,
+                float c_v, float c_ent, float inv_m, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(head_out && actions && logp_old && adv && ret && dho && stats, SC_E_SHAPE, "sc_ppo_loss: null pointer");
   SC_REQUIRE(M > 0 && A >= 1 && A < kMaxA1 && ld >= A + 1, SC_E_SHAPE, "sc_ppo_loss: M=%lld A=%d ld=%d",
              (long long)M, A, ld);
   sc_launch_kernel(ppo_loss_kernel, dim3(grid_for(M, kThreads, 4)), dim3(kThreads), 0, (cudaStream_t)stream, 
-      head_out, ld, actions, logp_old, adv, ret, dho, stats, M, A, clip_eps, c_v, c_ent, inv_m);
+      head_out, ld, actions, logp_old, adv, ret, idx, dho, stats, M, A, clip_eps, c_v, c_ent, inv_m);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_ppo_loss");
+  return SC_OK;
+}
+
+int sc_step_begin(float* grad, int64_t n, float* stats, int n_stats, int64_t* step_dev, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(n >= 0 && n % 4 == 0 && n_stats >= 0 && n_stats <= kThreads && (n == 0 || grad) && (n_stats == 0 || stats),
+             SC_E_SHAPE, "sc_step_begin: n=%lld (multiple of 4) n_stats=%d (<= %d)", (long long)n, n_stats, kThreads);
+  SC_REQUIRE(sc_aligned16(grad), SC_E_ALIGN, "sc_step_begin: unaligned gradient bucket");
+  sc_launch_kernel(step_begin_kernel, dim3(grid_for(n / 4 + 1, kThreads, 8)), dim3(kThreads), 0, (cudaStream_t)stream,
+                   reinterpret_cast<float4*>(grad), n / 4, stats, n_stats, step_dev);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_step_begin");
+  return SC_OK;
+}
+
+int sc_snr_embed_fwd(const float* snr_db, float snr_db_scalar, const float* u, const float* v, const float* W,
+                     float* emb, float* h, int64_t B, int D, int E, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(u && v && W && emb && h, SC_E_SHAPE, "sc_snr_embed_fwd: null pointer");
+  SC_REQUIRE(B > 0 && D > 0 && D <= 1024 && E > 0 && E <= kSnrMaxE, SC_E_SHAPE, "sc_snr_embed_fwd: B=%lld D=%d E=%d",
+             (long long)B, D, E);
+  const int grid = (int)(B < (int64_t)sc_num_sms() * 8 ? B : (int64_t)sc_num_sms() * 8);
+  sc_launch_kernel(snr_embed_fwd_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, snr_db, snr_db_scalar, u, v,
+                   W, emb, h, B, D, E);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_snr_embed_fwd");
+  return SC_OK;
+}
+
+int sc_snr_embed_bwd(const float* demb, const float* h, const float* snr_db, float snr_db_scalar, const float* W,
+                     float* dW, float* du, float* dv, float demb_scale, int64_t B, int D, int E, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(demb && h && W && dW && du && dv, SC_E_SHAPE, "sc_snr_embed_bwd: null pointer");
+  SC_REQUIRE(B > 0 && D > 0 && D <= 1024 && E > 0 && E <= kSnrMaxE && E <= kThreads, SC_E_SHAPE,
+             "sc_snr_embed_bwd: B=%lld D=%d E=%d", (long long)B, D, E);
+  const int g1 = (int)(B < (int64_t)sc_num_sms() * 2 ? B : (int64_t)sc_num_sms() * 2);
+  sc_launch_kernel(snr_embed_bwd_uv_kernel, dim3(g1), dim3(kThreads), 0, (cudaStream_t)stream, demb, h, snr_db,
+                   snr_db_scalar, W, du, dv, demb_scale, B, D, E);
+  const int gx = (int)(((int64_t)D * E + kThreads - 1) / kThreads);
+  int gy = (int)((B + 255) / 256);
+  if (gy > 16) gy = 16;
+  sc_launch_kernel(snr_embed_bwd_w_kernel, dim3(gx, gy), dim3(kThreads), 0, (cudaStream_t)stream, demb, h, dW, demb_scale, B, D, E);
+  sc_count_launch(2);
+  SC_CHECK_LAUNCH("sc_snr_embed_bwd");
   return SC_OK;
 }
 

@@ -25,9 +25,38 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def loss_scales(local_batch: int, world: int, c_sem: float):
-    """(inv_m for per-sample PPO terms, coefficient for the rank-local mean L_sem)."""
-    return 1.0 / (local_batch * world), c_sem / world
+def loss_scales(local_batch: int, world: int, c_sem: float, global_batch: int | None = None):
+    """(inv_m for the per-sample PPO terms, gradient coefficient of the rank-local mean L_sem, this rank's weight in the
+    global-minibatch mean L_sem).  Equal shards by default (global = local * world); ragged slices pass global_batch."""
+    gb = local_batch * world if global_batch is None else int(global_batch)
+    share = local_batch / gb if gb > 0 else 0.0
+    return 1.0 / max(gb, 1), c_sem * share, share
+
+
+def env_shard(n_local_envs: int, pg=None):
+    """(first global environment index of this rank, global environment count): ranks own contiguous runs of whole
+    environments in rank order; one small all-gather of the local counts per update."""
+    world, rank = world_info(pg)
+    if world == 1:
+        return 0, n_local_envs
+    counts = [None] * world
+    dist.all_gather_object(counts, int(n_local_envs), group=pg)
+    return sum(counts[:rank]), sum(counts)
+
+
+def local_minibatch_indices(global_idx: torch.Tensor, n_envs_global: int, env_lo: int, n_envs_local: int):
+    """The rank-local part of one GLOBAL minibatch ("sliced by rank so the union equals the 1-rank
+    permutation").  global_idx: int64 slice of the global permutation over the flattened [T, N_global] rollout
+    (flat index = t * N_global + env).  This rank owns environments [env_lo, env_lo + n_envs_local).
+    Returns (rows, pos): rows = local flat indices (t * N_local + env - env_lo) of the owned samples, pos = their
+    positions inside the global minibatch (the global sample index of the channel's noise counters).  Order follows
+    the permutation, so one rank with every environment gets rows == global_idx, pos == arange."""
+    env = global_idx % n_envs_global
+    mine = (env >= env_lo) & (env < env_lo + n_envs_local)
+    pos = torch.nonzero(mine).flatten()
+    g = global_idx[pos]
+    rows = (g // n_envs_global) * n_envs_local + (g % n_envs_global - env_lo)
+    return rows.contiguous(), pos.contiguous()
 
 
 def allreduce_flat_grads(g32: torch.Tensor, pg=None) -> torch.Tensor:

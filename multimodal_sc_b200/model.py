@@ -54,6 +54,9 @@ def param_shapes(spec: SpecV0) -> "OrderedDict[str, tuple]":
             out += _block_shapes(f"{enc}.blocks.{l}", spec)
         out += [(f"{enc}.norm.weight", (D,)), (f"{enc}.norm.bias", (D,)),
                 (f"{enc}.sym.weight", (spec.c_sym, D)), (f"{enc}.sym.bias", (spec.c_sym,))]
+        if spec.snr_cond:                                    # SNR-conditioned encoders (oracle/model.py: SnrEmbed)
+            E = spec.snr_embed_dim
+            out += [(f"{enc}.snr.u", (E,)), (f"{enc}.snr.v", (E,)), (f"{enc}.snr.w", (D, E))]
     out += [("dec.pos", (spec.dec_tokens, D)), ("dec.in_proj.weight", (D, spec.c_sym)), ("dec.in_proj.bias", (D,))]
     for l in range(spec.dec_layers):
         out += _block_shapes(f"dec.blocks.{l}", spec)
@@ -118,17 +121,38 @@ def _init_flat(flat: FlatParams, spec: SpecV0, std: float, seed: int):
 # engine: explicit forward / backward schedules over a per-batch-size activation arena
 # ----------------------------------------------------------------------------------------------
 class _Arena(dict):
-    """named activation buffers for one batch size"""
+    """named activation buffers for one batch size.
 
-    def __init__(self, device):
+    `cap` > 0 makes it a CAPACITY arena: every per-sample buffer is allocated for `cap` samples once and handed out as a
+    view of the first B rows, so the ragged local slices of a data-parallel update (each rank processes the
+    samples of the global minibatch it owns, a different count every step) reuse one set of buffers.
+    `generation` counts Engine.forward calls on this arena: an autograd node that saved activations here checks it in
+    backward (a later forward with the same batch size would otherwise silently corrupt the gradients)."""
+
+    def __init__(self, device, cap: int = 0):
         super().__init__()
         self.device = device
+        self.cap = cap
+        self.B = 0                      # batch size of the current forward (capacity arenas)
+        self.generation = 0
+        self._store = {}
 
     def buf(self, name, shape, dtype=BF16):
-        t = self.get(name)
-        if t is None:
-            t = torch.empty(shape, device=self.device, dtype=dtype)
-            self[name] = t
+        if not self.cap:
+            t = self.get(name)
+            if t is None:
+                t = torch.empty(shape, device=self.device, dtype=dtype)
+                self[name] = t
+            return t
+        n = 1
+        for d in shape:
+            n *= d
+        full = n // self.B * self.cap if (self.B and n % self.B == 0) else n
+        st = self._store.get(name)
+        if st is None or st.numel() < max(full, n) or st.dtype != dtype:
+            st = self._store[name] = torch.empty(max(full, n), device=self.device, dtype=dtype)
+        t = st[:n].view(shape)
+        self[name] = t
         return t
 
 
@@ -153,12 +177,30 @@ class Engine:
         # one GEMM-class kernel overlaps the ramp-up of the next.  Block-parity scratch sets + events keep it race-free.
         self.wgrad_stream = torch.cuda.Stream(device) if os.environ.get("SC_WGRAD_STREAM", "0") != "0" else None
         self._side_done = []          # per block of the current backward: event after its last side-stream wgrad
+        self._free_arenas = {}        # batch size -> arenas returned by finished autograd nodes
+        # exact (erf) GELU: the fused MLP kernels implement the tanh form only -> two-GEMM schedule, direct-store epilogue
+        self.gelu_act = "gelu" if spec.gelu == "tanh" else "gelu_erf"
+        if spec.gelu != "tanh":
+            assert spec.gelu == "erf", f"unknown GELU form {spec.gelu!r}"
+            self.fused_mlp = False
+        # deterministic=True: weight gradients without split-K (one red.add per element, in stream order) — a debug /
+        # test mode; the default split-K wgrads add their K-slices in arbitrary order (fp32 rounding-level run-to-run noise)
+        self.deterministic = os.environ.get("SC_DETERMINISTIC", "0") != "0"
 
-    def arena(self, B: int) -> _Arena:
-        a = self.arenas.get(B)
+    def arena(self, B: int, cap: int = 0) -> _Arena:
+        """the shared arena of batch size B, or (cap >= B) the capacity arena for up to `cap` samples"""
+        key = ("cap", cap) if cap else B
+        a = self.arenas.get(key)
         if a is None:
-            a = self.arenas[B] = _Arena(self.device)
+            a = self.arenas[key] = _Arena(self.device, cap)
         return a
+
+    def lease_arena(self, B: int) -> "_ArenaLease":
+        """a private arena for one outstanding autograd node (two grad-mode forwards followed by one backward each own
+        their activations); returned to the pool when the node is freed"""
+        pool = self._free_arenas.setdefault(B, [])
+        a = pool.pop() if pool else _Arena(self.device)
+        return _ArenaLease(a, pool)
 
     # ---- helpers ------------------------------------------------------------------------
     def _linear_bwd(self, dy, x, wname, dx=None, bias_colsum=True, side=False, **dgrad_epi):
@@ -179,7 +221,7 @@ class Engine:
 
         def run():
             ops.gemm(dy, x, a_mn=True, b_mn=True, out_f32=f.g(f"{wname}.weight"), atomic=True,
-                     ksplit=_wgrad_ksplit(N, K, dy.shape[0], self.sms),
+                     ksplit=1 if self.deterministic else _wgrad_ksplit(N, K, dy.shape[0], self.sms),
                      colsum=f.g(f"{wname}.bias") if bias_colsum else None)
 
         if not (side and self._side_on()):
@@ -244,7 +286,7 @@ class Engine:
         # keeps the two-GEMM form (profiles/README.md, r1 fused-MLP table)
         h = k("h", (M, sp.d_mlp))
         hpre = k("hpre", (M, sp.d_mlp)) if train else None
-        ops.gemm(xn2, f.w16(f"{pfx}.fc1.weight"), bias=f.w32(f"{pfx}.fc1.bias"), act="gelu", aux_out=hpre, out=h)
+        ops.gemm(xn2, f.w16(f"{pfx}.fc1.weight"), bias=f.w32(f"{pfx}.fc1.bias"), act=self.gelu_act, aux_out=hpre, out=h)
         ops.gemm(h, f.w16(f"{pfx}.fc2.weight"), bias=f.w32(f"{pfx}.fc2.bias"), resid=x1, out=x_out,
                  ln=next_ln if fuse_ln else None)
         if next_ln is not None and not fuse_ln:
@@ -256,7 +298,7 @@ class Engine:
         sp, f = self.spec, self.flat
         M, D, H = x_in.shape[0], sp.d_model, sp.n_heads
         k = lambda n: A[f"{pfx}.{n}"]
-        s = lambda n, shape, dt=BF16: A.buf(f"scratch.{n}.{shape[0]}", shape, dt)   # shared across blocks
+        s = lambda n, shape, dt=BF16: A.buf(f"scratch.{n}.S{shape[0] // B}", shape, dt)   # shared across blocks of one width
         side = self._side_on()
         # With the wgrads on the side stream, the buffers they read (dhpre, dx1, dqkv) alternate between two scratch
         # sets by block parity, and the side stream never lags by more than one block: LN1-backward of block j (the
@@ -273,7 +315,8 @@ class Engine:
             self._linear_bwd(dx_out, k("h"), f"{pfx}.fc2", bias_colsum=False, side=True)
             self._linear_bwd(dhpre, k("xn2"), f"{pfx}.fc1", side=True)
         else:
-            self._linear_bwd(dx_out, k("h"), f"{pfx}.fc2", dx=dhpre, bias_colsum=False, aux_in=k("hpre"), side=True)
+            self._linear_bwd(dx_out, k("h"), f"{pfx}.fc2", dx=dhpre, bias_colsum=False, aux_in=k("hpre"), side=True,
+                             aux_in_erf=self.gelu_act == "gelu_erf")
             self._linear_bwd(dhpre, k("xn2"), f"{pfx}.fc1", dx=dxn2, side=True)
         dx1 = s2("dx1", (M, D))
         ops.layernorm_bwd(dxn2, k("x1"), k("mean2"), k("rstd2"), f.w32(f"{pfx}.ln2.weight"),
@@ -298,23 +341,41 @@ class Engine:
 
     # ---- forward --------------------------------------------------------------------------
     def forward(self, cam, bev, snr_db, channel, seed, noise, fading, sample_offset, train, want_aux=False,
-                seed_dev=None):
+                seed_dev=None, row_idx=None, sample_idx=None, arena=None):
+        """row_idx (int64 [B], optional): the step's samples are rows row_idx of cam / bev (the minibatch gather is fused
+        into the patchify pass).  sample_idx (int64 [B], optional): global sample index of every local sample for the
+        channel's noise counters (default sample_offset + b).  arena: the activation arena to use (default: the shared
+        arena of this batch size)."""
         sp, f = self.spec, self.flat
-        B = cam.shape[0]
-        A = self.arena(B)
+        B = cam.shape[0] if row_idx is None else row_idx.numel()
+        A = arena if arena is not None else self.arena(B)
+        A.B = B
+        A.generation += 1
         D, S, C = sp.d_model, sp.cam_tokens, sp.c_sym
         k_sym = sp.k_sym
         z_mm = A.buf("z_mm", (2, B, k_sym), F32)                       # modality-major symbols
         for mi, (enc, img, patch) in enumerate((("cam_enc", cam, sp.cam_patch), ("bev_enc", bev, sp.bev_patch))):
             M = B * S
-            tok = ops.patchify(img, patch, out=A.buf(f"{enc}.tok", (M, img.shape[1] * patch * patch)))
+            tok = ops.patchify(img, patch, out=A.buf(f"{enc}.tok", (M, img.shape[1] * patch * patch)), row_idx=row_idx)
             xs = [A.buf(f"{enc}.x{l}", (M, D)) for l in range(sp.enc_layers + 1)]
             fuse_ln = self.fused_ln and D == 256
             # every LayerNorm rides on the epilogue of the GEMM that produces its input: the patch embedding feeds
             # block 0's LN1, each block's fc2 feeds the next block's LN1 / the final norm
-            ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
-                     rowadd=f.w16(f"{enc}.pos"), out=xs[0],
-                     ln=self._block_ln1(A, f"{enc}.blocks.0", M) if fuse_ln else None)
+            if sp.snr_cond:
+                # SNR-conditioned encoder: the per-sample embedding rides on the row-group add of the epilogue (the same
+                # path the mean-pool backward uses); that epilogue kind has no fused LayerNorm, so block 0's LN1 runs
+                # as its own kernel
+                emb, _ = ops.snr_embed_fwd(snr_db, f.w32(f"{enc}.snr.u"), f.w32(f"{enc}.snr.v"), f.w32(f"{enc}.snr.w"), B,
+                                           emb=A.buf(f"{enc}.snr_emb", (B, D), F32),
+                                           h=A.buf(f"{enc}.snr_h", (B, sp.snr_embed_dim), F32))
+                ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
+                         rowadd=f.w16(f"{enc}.pos"), rowgrp=emb, rowgrp_size=S, rowgrp_scale=1.0, out=xs[0])
+                if fuse_ln:
+                    self._run_ln(xs[0], self._block_ln1(A, f"{enc}.blocks.0", M))
+            else:
+                ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
+                         rowadd=f.w16(f"{enc}.pos"), out=xs[0],
+                         ln=self._block_ln1(A, f"{enc}.blocks.0", M) if fuse_ln else None)
             final_ln = self._ln_spec(A, f"{enc}.norm", M, f"{enc}.t", f"{enc}.mean", f"{enc}.rstd")
             for l in range(sp.enc_layers):
                 nxt = self._block_ln1(A, f"{enc}.blocks.{l + 1}", M) if l + 1 < sp.enc_layers else final_ln
@@ -327,7 +388,8 @@ class Engine:
         scale = A.buf("scale", (B, 2), F32)
         ops.pnorm_channel_fwd(z_mm, channel, snr_db, rician_k=self.rician_k, seed=seed or 0, sample_offset=sample_offset, noise=noise,
                               fading=fading, eps=sp.pnorm_eps, y_f32=y32, y_bf16=y16, scale=scale,
-                              z_strides=(k_sym, B * k_sym, B, k_sym), seed_dev=seed_dev)
+                              z_strides=(k_sym, B * k_sym, B, k_sym), seed_dev=seed_dev, sample_idx=sample_idx,
+                              quant_bits=sp.quant_bits, quant_clip=sp.quant_clip)
         # ---- decoder ----
         Sd = sp.dec_tokens
         Md = B * Sd
@@ -362,7 +424,7 @@ class Engine:
 
     # ---- backward -------------------------------------------------------------------------
     def backward(self, A, B, dho, cam_unused, channel, snr_db, seed, fading, sample_offset, seed_dev=None,
-                 grad_ready=None):
+                 grad_ready=None, sample_idx=None):
         """dho: fp32 [B, A+1] = d loss / d head_out.  `dec.drecon` must hold d loss / d recon (l_sem()).
         Accumulates into flat.g32.  `grad_ready(name)` is called on the compute stream as soon as the gradient
         region `name` of dp.grad_buckets() ("dec", "cam_enc", "bev_enc") is final (data-parallel overlap)."""
@@ -376,12 +438,12 @@ class Engine:
         df = A.buf("dec.df", (B, D), F32)
         self._linear_bwd(dtrunk, A["dec.f"], "ac.trunk", out_f32=df)
         # recon head; d tn = d recon W_rec + (1/Sd) d f   (mean-pool backward fused as a row-group add)
-        dtn = A.buf("scratch.dxn.%d" % Md, (Md, D))
+        dtn = A.buf("scratch.dxn.S%d" % Sd, (Md, D))
         self._linear_bwd(A["dec.drecon"], A["dec.tn"], "dec.recon", dx=dtn, rowgrp=df, rowgrp_size=Sd,
                          rowgrp_scale=1.0 / Sd)
         L = sp.dec_layers
-        dxa = A.buf("scratch.dxa.%d" % Md, (Md, D))
-        dxb = A.buf("scratch.dxb.%d" % Md, (Md, D))
+        dxa = A.buf("scratch.dxa.S%d" % Sd, (Md, D))
+        dxb = A.buf("scratch.dxb.S%d" % Sd, (Md, D))
         ops.layernorm_bwd(dtn, A[f"dec.x{L}"], A["dec.mean"], A["dec.rstd"], f.w32("dec.norm.weight"),
                           f.g("dec.norm.weight"), f.g("dec.norm.bias"), dx=dxa,
                           colsum=f.g(f"dec.blocks.{L - 1}.fc2.bias"))
@@ -401,16 +463,17 @@ class Engine:
         dz_mm = A.buf("dz_mm", (2, B, sp.k_sym))
         ops.pnorm_channel_bwd(dy, A["z_mm"], A["scale"], channel, snr_db, rician_k=self.rician_k, seed=seed or 0,
                               sample_offset=sample_offset, fading=fading, dz_bf16=dz_mm,
-                              z_strides=(sp.k_sym, B * sp.k_sym, B, sp.k_sym), seed_dev=seed_dev)
+                              z_strides=(sp.k_sym, B * sp.k_sym, B, sp.k_sym), seed_dev=seed_dev, sample_idx=sample_idx,
+                              quant_bits=sp.quant_bits, quant_clip=sp.quant_clip)
         # encoders
         M = B * S
         for mi, enc in enumerate(("cam_enc", "bev_enc")):
             dz = dz_mm[mi].view(M, C)
-            dt = A.buf("scratch.dxn.%d" % M, (M, D))
+            dt = A.buf("scratch.dxn.S%d" % S, (M, D))
             self._linear_bwd(dz, A[f"{enc}.t"], f"{enc}.sym", dx=dt)
             Le = sp.enc_layers
-            dxa = A.buf("scratch.dxa.%d" % M, (M, D))
-            dxb = A.buf("scratch.dxb.%d" % M, (M, D))
+            dxa = A.buf("scratch.dxa.S%d" % S, (M, D))
+            dxb = A.buf("scratch.dxb.S%d" % S, (M, D))
             ops.layernorm_bwd(dt, A[f"{enc}.x{Le}"], A[f"{enc}.mean"], A[f"{enc}.rstd"], f.w32(f"{enc}.norm.weight"),
                               f.g(f"{enc}.norm.weight"), f.g(f"{enc}.norm.bias"), dx=dxa,
                               colsum=f.g(f"{enc}.blocks.{Le - 1}.fc2.bias"))
@@ -420,6 +483,10 @@ class Engine:
                 self._block_bwd(A, f"{enc}.blocks.{l}", A[f"{enc}.x{l}"], cur, nxt, prev_bias, B, S)
                 cur, nxt = nxt, cur
             ops.colsum(cur.view(B, S * D), f.g(f"{enc}.pos").view(-1))
+            if sp.snr_cond:               # d emb[b] = sum over the sample's tokens of d x0 (mean-pool x S), then the tiny MLP
+                demb = ops.meanpool_fwd(cur.view(B, S, D), out_f32=A.buf(f"{enc}.snr_demb", (B, D), F32))
+                ops.snr_embed_bwd(demb, A[f"{enc}.snr_h"], snr_db, f.w32(f"{enc}.snr.w"), f.g(f"{enc}.snr.w"),
+                                  f.g(f"{enc}.snr.u"), f.g(f"{enc}.snr.v"), demb_scale=float(S))
             self._linear_bwd(cur, A[f"{enc}.tok"], f"{enc}.patch_embed", bias_colsum=False)
             if grad_ready is not None:
                 self._join_side()
@@ -434,24 +501,43 @@ class Engine:
 # ----------------------------------------------------------------------------------------------
 # nn.Module facade
 # ----------------------------------------------------------------------------------------------
+class _ArenaLease:
+    """ownership of one activation arena by one autograd node; the arena returns to the engine's pool when the node
+    (and every other holder of the lease) is gone"""
+
+    def __init__(self, arena: _Arena, pool: list):
+        self.arena, self._pool = arena, pool
+
+    def __del__(self):
+        try:
+            self._pool.append(self.arena)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
 class _PolicyFn(torch.autograd.Function):
-    """one autograd node around the whole engine (generic API path; PPOAgent bypasses it)."""
+    """one autograd node around the whole engine (generic API path; PPOAgent bypasses it).  Each node owns a private
+    activation arena (lease), so several grad-mode forwards may be outstanding before their backwards run."""
 
     @staticmethod
-    def forward(ctx, policy, cam, bev, kw, *params):
+    def forward(ctx, policy, cam, bev, kw, lease, *params):
         eng = policy.engine
         B = cam.shape[0]
         eng.rician_k = kw["rician_k"]
         ho, A = eng.forward(cam, bev, kw["snr_db"], kw["channel"], kw["seed"], kw["noise"], kw["fading"],
-                            kw["sample_offset"], train=True, want_aux=True)
+                            kw["sample_offset"], train=True, want_aux=True, arena=lease.arena)
         lsem = torch.zeros(1, device=cam.device)
         eng.l_sem(A, B, lsem)
-        ctx.policy, ctx.kw, ctx.B, ctx.A = policy, kw, B, A
+        ctx.policy, ctx.kw, ctx.B, ctx.A, ctx.lease, ctx.generation = policy, kw, B, A, lease, A.generation
         return ho.clone(), lsem
 
     @staticmethod
     def backward(ctx, dho, dlsem):
         policy, kw, B, A = ctx.policy, ctx.kw, ctx.B, ctx.A
+        if A.generation != ctx.generation:
+            raise RuntimeError("SemComPolicy: the activation arena of this autograd node was overwritten by a later "
+                               "Engine.forward (generation %d -> %d); its gradients would be wrong" %
+                               (ctx.generation, A.generation))
         eng, flat = policy.engine, policy.flat
         saved = flat.g32
         flat.g32 = torch.zeros_like(saved)                  # scratch bucket for this backward
@@ -463,7 +549,7 @@ class _PolicyFn(torch.autograd.Function):
             grads = [flat.g(n).clone() for n in flat.shapes]
         finally:
             flat.g32 = saved
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 class SemComPolicy(nn.Module):
@@ -518,8 +604,9 @@ class SemComPolicy(nn.Module):
         bev = bev.to(self.device, bev.dtype if bev.dtype == BF16 else F32).contiguous()
         B, A_ = cam.shape[0], self.spec.n_actions
         if torch.is_grad_enabled():
-            ho, lsem = _PolicyFn.apply(self, cam, bev, kw, *self.parameters())
-            arena = self.engine.arena(B)
+            lease = self.engine.lease_arena(B)
+            ho, lsem = _PolicyFn.apply(self, cam, bev, kw, lease, *self.parameters())
+            arena = lease.arena
         else:
             self.engine.rician_k = kw["rician_k"]
             ho, arena = self.engine.forward(cam, bev, kw["snr_db"], channel, seed, kw["noise"], kw["fading"],

@@ -85,12 +85,42 @@ def _profiled(name):
                 items = (Bn * S + 127) // 128 * H
                 fl = items * (2 if name == "attn_fwd" else 5) * 2.0 * 128 * Sk * 64
                 by = qkv.numel() * 2.0 * (4.0 / 3.0 if name == "attn_fwd" else 7.0 / 3.0)
+            else:
+                by = float(_ALGO_BYTES.get(name, lambda a, k, r: 0.0)(a, k, r))
             _PROF.pending.append((nm, e0, e1, fl, by))
             return r
         wrapper.__name__ = fn.__name__
         wrapper.__doc__ = fn.__doc__
         return wrapper
     return deco
+
+
+def _nbytes(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
+# algorithmic bytes of the memory-bound kernels (each operand read once, each result written once) for the roofline
+# pass of bench.py: name -> f(args, kwargs, result)
+_ALGO_BYTES = {
+    "patchify": lambda a, k, r: (r.numel() * (2 if a[0].dtype == BF16 else 4)) + _nbytes(r),
+    "layernorm_fwd": lambda a, k, r: _nbytes(a[0]) * 2 + a[0].numel() // a[0].shape[-1] * 8,
+    "layernorm_bwd": lambda a, k, r: _nbytes(a[0], a[1], k.get("dres"), r) + a[0].numel() // a[0].shape[-1] * 8,
+    "colsum": lambda a, k, r: _nbytes(a[0]),
+    "pnorm_channel_fwd": lambda a, k, r: (k["z_strides"][2] * 2 * k["z_strides"][3] * 4 if k.get("z_strides") else _nbytes(a[0]))
+    + _nbytes(k.get("y_f32"), k.get("y_bf16"), k.get("noise")),
+    "pnorm_channel_bwd": lambda a, k, r: _nbytes(a[0]) * 2 + _nbytes(k.get("dz_f32"), k.get("dz_bf16")),
+    "meanpool_fwd": lambda a, k, r: _nbytes(a[0]),
+    "mse_fwd_bwd": lambda a, k, r: _nbytes(a[0]) * 2 + _nbytes(k.get("dr")),
+    "cast_f32_bf16": lambda a, k, r: _nbytes(a[0]) * 3 // 2,
+    "heads_fwd": lambda a, k, r: _nbytes(a[0], a[1], r),
+    "heads_bwd": lambda a, k, r: _nbytes(a[0], a[1], a[2]) + _nbytes(a[1]),
+    "sample_action": lambda a, k, r: _nbytes(a[0], a[1]) + a[1].numel() * 12,
+    "gae": lambda a, k, r: a[0].numel() * 20 + _nbytes(a[3]),
+    "adv_normalize": lambda a, k, r: _nbytes(a[0]) * 2,
+    "ppo_loss": lambda a, k, r: _nbytes(a[0]) * 2 + a[0].shape[0] * 20,
+    "adam_flat": lambda a, k, r: a[0].numel() * 30,
+    "step_begin": lambda a, k, r: _nbytes(a[0]),
+}
 
 
 def _cuda(*ts):
@@ -102,7 +132,7 @@ def _cuda(*ts):
 @_profiled("gemm")
 def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, rowgrp_size=0,
          rowgrp_scale=1.0, alpha=1.0, resid=None, aux_in=None, aux_out=None, out=None,
-         out_f32=None, act=None, atomic=False, ksplit=1, colsum=None, ln=None):
+         out_f32=None, act=None, atomic=False, ksplit=1, colsum=None, ln=None, aux_in_erf=False):
     """acc[m,n] = sum_k A(m,k) B(n,k) with the fused epilogue of sc_gemm_bf16.
 
     a_mn=False: A is [M,K]; a_mn=True: A is [K,M].  b_mn=False: B is [N,K]; b_mn=True: B is [K,N].
@@ -138,14 +168,15 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, r
         rowadd_period=(rowadd.shape[0] if rowadd is not None else 0),
         rowgrp=ptr(rowgrp), rowgrp_size=rowgrp_size, rowgrp_scale=rowgrp_scale, alpha=alpha,
         resid=ptr(resid), aux_in=ptr(aux_in), aux_out=ptr(aux_out), out_bf16=ptr(out),
-        out_f32=ptr(out_f32), ldo=ldo, act=SC_ACT[act], atomic=int(atomic), colsum=ptr(colsum))
+        out_f32=ptr(out_f32), ldo=ldo, act=SC_ACT[act], atomic=int(atomic), colsum=ptr(colsum),
+        aux_in_erf=int(bool(aux_in_erf)))
     if ln is not None:
         y = ln["y"]
         assert y.dtype == BF16 and y.shape == (M, N) and y.stride(1) == 1 and y.stride(0) == ldo
         epi.ln_out, epi.ln_gamma, epi.ln_beta = ptr(y), ptr(ln["gamma"]), ptr(ln["beta"])
         epi.ln_mean, epi.ln_rstd, epi.ln_eps = ptr(ln.get("mean")), ptr(ln.get("rstd")), float(ln["eps"])
     rc = _lib.load().sc_gemm_bf16(ptr(A), ptr(B), M, N, K, int(a_mn), int(b_mn), A.stride(0),
-                                  B.stride(0), C.byref(epi), ksplit, stream_ptr())
+                                  B.stride(0), C.byref(epi), ksplit, stream_ptr(A))
     check(rc, "sc_gemm_bf16")
     return o
 
@@ -165,7 +196,7 @@ def mlp_fwd(x, w1, b1, w2, b2, *, resid=None, hpre=None, h=None, out=None):
         if t is not None:
             assert t.dtype == BF16 and t.shape == shp and t.is_contiguous()
     rc = _lib.load().sc_mlp_fwd(ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(resid), ptr(hpre), ptr(h), ptr(out),
-                                M, D, R, stream_ptr())
+                                M, D, R, stream_ptr(x))
     check(rc, "sc_mlp_fwd")
     return out
 
@@ -178,7 +209,7 @@ def mlp_bwd_dgrad(dy, w1, w2, hpre, *, dhpre, dx):
     R = w1.shape[0]
     for t, shp in ((dy, (M, D)), (dx, (M, D)), (hpre, (M, R)), (dhpre, (M, R)), (w1, (R, D)), (w2, (D, R))):
         assert t.dtype == BF16 and t.shape == shp and t.is_contiguous()
-    rc = _lib.load().sc_mlp_bwd_dgrad(ptr(dy), ptr(w1), ptr(w2), ptr(hpre), ptr(dhpre), ptr(dx), M, D, R, stream_ptr())
+    rc = _lib.load().sc_mlp_bwd_dgrad(ptr(dy), ptr(w1), ptr(w2), ptr(hpre), ptr(dhpre), ptr(dx), M, D, R, stream_ptr(dy))
     check(rc, "sc_mlp_bwd_dgrad")
     return dx
 
@@ -188,15 +219,21 @@ def debug_set(key: str, value: int):
 
 
 @_profiled("patchify")
-def patchify(img, patch: int, out=None):
-    """img fp32 or bf16 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P]"""
-    _cuda(img)
+def patchify(img, patch: int, out=None, row_idx=None):
+    """img fp32 or bf16 [*,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P].  row_idx (int64 [B], optional): output sample b is
+    image row_idx[b] (fused minibatch gather); B = len(row_idx)."""
+    _cuda(img, row_idx)
     assert img.dtype in (F32, BF16) and img.is_contiguous()
     B, Cc, H, W = img.shape
+    if row_idx is not None:
+        assert row_idx.dtype == torch.int64 and row_idx.is_contiguous() and row_idx.dim() == 1
+        B = row_idx.numel()
     T = (H // patch) * (W // patch)
     if out is None:
         out = torch.empty(B * T, Cc * patch * patch, device=img.device, dtype=BF16)
-    check(_lib.load().sc_patchify_bf16(ptr(img), int(img.dtype == BF16), ptr(out), B, Cc, H, W, patch, stream_ptr()), "sc_patchify_bf16")
+    assert out.numel() == B * T * Cc * patch * patch
+    check(_lib.load().sc_patchify_bf16(ptr(img), int(img.dtype == BF16), ptr(out), B, Cc, H, W, patch, ptr(row_idx),
+                                       stream_ptr(img)), "sc_patchify_bf16")
     return out
 
 
@@ -209,7 +246,7 @@ def layernorm_fwd(x, gamma, beta, eps, y=None, mean=None, rstd=None):
     if y is None:
         y = torch.empty_like(x)
     check(_lib.load().sc_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), M, D, eps,
-                                       int(x.dtype == F32), stream_ptr()), "sc_layernorm_fwd")
+                                       int(x.dtype == F32), stream_ptr(x)), "sc_layernorm_fwd")
     return y
 
 
@@ -223,7 +260,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, dx=None, c
         dx = torch.empty_like(x)
     check(_lib.load().sc_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx),
                                        ptr(dgamma), ptr(dbeta), ptr(colsum), M, D, int(x.dtype == F32),
-                                       stream_ptr()), "sc_layernorm_bwd")
+                                       stream_ptr(x)), "sc_layernorm_bwd")
     return dx
 
 
@@ -233,14 +270,14 @@ def colsum(x, out):
     _cuda(x, out)
     assert x.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32
     M, N = x.shape
-    check(_lib.load().sc_colsum_bf16(ptr(x), ptr(out), M, N, x.stride(0), stream_ptr()), "sc_colsum_bf16")
+    check(_lib.load().sc_colsum_bf16(ptr(x), ptr(out), M, N, x.stride(0), stream_ptr(x)), "sc_colsum_bf16")
     return out
 
 
 @_profiled("pnorm_channel_fwd")
 def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, fading=None, eps=1e-12,
                       y_f32=None, y_bf16=None, scale=None, z_strides=None, y_strides=None, seed_dev=None,
-                      rician_k=0.0):
+                      rician_k=0.0, sample_idx=None, quant_bits=0, quant_clip=4.0):
     """z fp32 logical [B,2,k] addressed with z_strides=(sb, sm) (default: contiguous [B,2,k]).
     `seed_dev` (device int64 [1], optional) is added to `seed` inside the kernel (CUDA-graph replays).
     Returns (y_f32, y_bf16, scale)."""
@@ -264,14 +301,16 @@ def pnorm_channel_fwd(z, kind, snr_db, *, seed=0, sample_offset=0, noise=None, f
     check(_lib.load().sc_pnorm_channel_fwd(ptr(z), z_strides[0], z_strides[1], ptr(y_f32), ptr(y_bf16),
                                            y_strides[0], y_strides[1], ptr(scale), B, k, SC_CH[kind],
                                            float(rician_k), ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1), sample_offset,
-                                           ptr(noise), ptr(fading), eps, ptr(seed_dev), stream_ptr()),
+                                           ptr(_idx(sample_idx, B)), ptr(noise), ptr(fading), eps, ptr(seed_dev),
+                                           int(quant_bits), float(quant_clip), stream_ptr(z)),
           "sc_pnorm_channel_fwd")
     return y_f32, y_bf16, scale
 
 
 @_profiled("pnorm_channel_bwd")
 def pnorm_channel_bwd(dy, z, scale, kind, snr_db, *, seed=0, sample_offset=0, fading=None, dz_f32=None,
-                      dz_bf16=None, z_strides=None, y_strides=None, seed_dev=None, rician_k=0.0):
+                      dz_bf16=None, z_strides=None, y_strides=None, seed_dev=None, rician_k=0.0, sample_idx=None,
+                      quant_bits=0, quant_clip=4.0):
     _cuda(dy, z, scale)
     assert dy.dtype == F32 and z.dtype == F32
     if z_strides is None:
@@ -288,15 +327,30 @@ def pnorm_channel_bwd(dy, z, scale, kind, snr_db, *, seed=0, sample_offset=0, fa
     check(_lib.load().sc_pnorm_channel_bwd(ptr(dy), y_strides[0], y_strides[1], ptr(z), z_strides[0],
                                            z_strides[1], ptr(scale), ptr(dz_f32), ptr(dz_bf16), B, k,
                                            SC_CH[kind], float(rician_k), ptr(snr_t), snr_s, int(seed) & (2 ** 64 - 1),
-                                           sample_offset, ptr(fading), ptr(seed_dev), stream_ptr()),
+                                           sample_offset, ptr(_idx(sample_idx, B)), ptr(fading), ptr(seed_dev),
+                                           int(quant_bits), float(quant_clip), stream_ptr(z)),
           "sc_pnorm_channel_bwd")
     return dz_f32, dz_bf16
+
+
+def _idx(t, n):
+    if t is not None:
+        assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == n, "index vector: cuda int64 [n]"
+    return t
+
+
+def philox_normals(n_quads, seed, quad_offset=0, exact=False, device="cuda"):
+    """normals of the in-kernel generator (stream 0): fp32 [n_quads, 4]"""
+    out = torch.empty(n_quads, 4, device=device, dtype=F32)
+    check(_lib.load().sc_philox_normals(ptr(out), n_quads, int(seed) & (2 ** 64 - 1), quad_offset, int(exact),
+                                        stream_ptr(out)), "sc_philox_normals")
+    return out
 
 
 def philox_words(n_quads, stream_id, seed, quad_offset=0, device="cuda"):
     out = torch.empty(n_quads, 4, device=device, dtype=torch.int32)
     check(_lib.load().sc_philox_words(ptr(out), n_quads, stream_id, int(seed) & (2 ** 64 - 1), quad_offset,
-                                      stream_ptr()), "sc_philox_words")
+                                      stream_ptr(out)), "sc_philox_words")
     return out
 
 
@@ -307,7 +361,7 @@ def meanpool_fwd(x, out_bf16=None, out_f32=None):
     B, S, D = x.shape
     if out_bf16 is None and out_f32 is None:
         out_bf16 = torch.empty(B, D, device=x.device, dtype=BF16)
-    check(_lib.load().sc_meanpool_fwd(ptr(x), ptr(out_bf16), ptr(out_f32), B, S, D, stream_ptr()),
+    check(_lib.load().sc_meanpool_fwd(ptr(x), ptr(out_bf16), ptr(out_f32), B, S, D, stream_ptr(x)),
           "sc_meanpool_fwd")
     return out_bf16 if out_bf16 is not None else out_f32
 
@@ -321,7 +375,7 @@ def mse_fwd_bwd(r, t, loss_accum, dr=None, grad_scale=1.0, t1=None, seg_rows=0):
     n = r.numel()
     D = r.shape[-1]
     check(_lib.load().sc_mse_fwd_bwd(ptr(r), ptr(t), ptr(t1), seg_rows, D, ptr(loss_accum), ptr(dr), n, 1.0 / n,
-                                     grad_scale, stream_ptr()), "sc_mse_fwd_bwd")
+                                     grad_scale, stream_ptr(r)), "sc_mse_fwd_bwd")
     return dr
 
 
@@ -331,7 +385,7 @@ def cast_f32_bf16(src, dst=None):
     assert src.dtype == F32 and src.is_contiguous()
     if dst is None:
         dst = torch.empty_like(src, dtype=BF16)
-    check(_lib.load().sc_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "sc_cast_f32_bf16")
+    check(_lib.load().sc_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr(src)), "sc_cast_f32_bf16")
     return dst
 
 
@@ -344,7 +398,7 @@ def attn_fwd(qkv, B, S, H, out=None, lse=None):
         out = torch.empty(B * S, H * 64, device=qkv.device, dtype=BF16)
     if lse is None:
         lse = torch.empty(B * S, H, device=qkv.device, dtype=F32)
-    check(_lib.load().sc_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, S, H, stream_ptr()), "sc_attn_fwd")
+    check(_lib.load().sc_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, S, H, stream_ptr(qkv)), "sc_attn_fwd")
     return out, lse
 
 
@@ -354,7 +408,7 @@ def attn_bwd(qkv, out, dout, lse, B, S, H, dqkv=None):
     assert qkv.dtype == BF16 and dout.dtype == BF16 and qkv.is_contiguous() and dout.is_contiguous()
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
-    check(_lib.load().sc_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, S, H, stream_ptr()),
+    check(_lib.load().sc_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, S, H, stream_ptr(qkv)),
           "sc_attn_bwd")
     return dqkv
 
@@ -368,7 +422,7 @@ def heads_fwd(trunk, W, bias, out=None):
     assert trunk.dtype == BF16 and W.dtype == F32 and W.is_contiguous() and trunk.is_contiguous()
     if out is None:
         out = torch.empty(B, A1, device=trunk.device, dtype=F32)
-    check(_lib.load().sc_heads_fwd(ptr(trunk), ptr(W), ptr(bias), ptr(out), B, D, A1, stream_ptr()), "sc_heads_fwd")
+    check(_lib.load().sc_heads_fwd(ptr(trunk), ptr(W), ptr(bias), ptr(out), B, D, A1, stream_ptr(trunk)), "sc_heads_fwd")
     return out
 
 
@@ -381,7 +435,7 @@ def heads_bwd(dho, trunk, W, dW, dbias, dtrunk_pre=None):
     if dtrunk_pre is None:
         dtrunk_pre = torch.empty_like(trunk)
     check(_lib.load().sc_heads_bwd(ptr(dho), ptr(trunk), ptr(W), ptr(dtrunk_pre), ptr(dW), ptr(dbias), B, D, A1,
-                                   stream_ptr()), "sc_heads_bwd")
+                                   stream_ptr(dho)), "sc_heads_bwd")
     return dtrunk_pre
 
 
@@ -395,7 +449,7 @@ def sample_action(head_out, u, n_actions, action=None, logp=None):
     if logp is None:
         logp = torch.empty(B, device=u.device, dtype=F32)
     check(_lib.load().sc_sample_action(ptr(head_out), ld, ptr(u), ptr(action), ptr(logp), B, n_actions,
-                                       stream_ptr()), "sc_sample_action")
+                                       stream_ptr(head_out)), "sc_sample_action")
     return action, logp
 
 
@@ -412,7 +466,7 @@ def gae(rewards, values, dones, last_value, gamma, lam, adv=None, ret=None, sums
     if sums is not None:
         assert sums.dtype == torch.float64 and sums.numel() == 2
     check(_lib.load().sc_gae(ptr(rewards), ptr(values), ptr(dones), ptr(last_value), ptr(adv), ptr(ret), ptr(sums),
-                             T, N, gamma, lam, stream_ptr()), "sc_gae")
+                             T, N, gamma, lam, stream_ptr(rewards)), "sc_gae")
     return adv, ret
 
 
@@ -420,23 +474,31 @@ def gae(rewards, values, dones, last_value, gamma, lam, adv=None, ret=None, sums
 def adv_normalize(adv, sums, count, eps):
     _cuda(adv, sums)
     assert adv.dtype == F32 and adv.is_contiguous() and sums.dtype == torch.float64
-    check(_lib.load().sc_adv_normalize(ptr(adv), ptr(sums), count, adv.numel(), eps, stream_ptr()),
+    check(_lib.load().sc_adv_normalize(ptr(adv), ptr(sums), count, adv.numel(), eps, stream_ptr(adv)),
           "sc_adv_normalize")
     return adv
 
 
 @_profiled("ppo_loss")
-def ppo_loss(head_out, actions, logp_old, adv, ret, n_actions, clip_eps, c_v, c_ent, inv_m, dho=None, stats=None):
-    """fused PPO loss fwd+bwd. stats[0:5] += (pi, v, ent, kl, clipfrac) * inv_m"""
-    _cuda(head_out, actions, logp_old, adv, ret)
+def ppo_loss(head_out, actions, logp_old, adv, ret, n_actions, clip_eps, c_v, c_ent, inv_m, dho=None, stats=None,
+             idx=None):
+    """fused PPO loss fwd+bwd. stats[0:5] += (pi, v, ent, kl, clipfrac) * inv_m.  idx (int64 [M], optional): sample i
+    reads actions / logp_old / adv / ret at idx[i] (fused minibatch gather).  An action outside [0, n_actions) turns
+    the statistics into NaN (the kernel does not trap)."""
+    _cuda(head_out, actions, logp_old, adv, ret, idx)
     M, ld = head_out.shape
-    assert head_out.dtype == F32 and head_out.is_contiguous() and actions.dtype == torch.int64
+    assert head_out.dtype == F32 and head_out.is_contiguous() and actions.dtype == torch.int64 and actions.is_contiguous()
+    for t in (logp_old, adv, ret):
+        assert t.dtype == F32 and t.is_contiguous(), "logp_old / adv / ret must be contiguous fp32"
+    n_src = actions.numel()
+    assert logp_old.numel() == n_src and adv.numel() == n_src and ret.numel() == n_src
+    assert idx is not None or n_src == M, "without idx the per-sample vectors must have M entries"
     if dho is None:
         dho = torch.empty_like(head_out)
     if stats is None:
         stats = torch.zeros(8, device=head_out.device, dtype=F32)
-    check(_lib.load().sc_ppo_loss(ptr(head_out), ld, ptr(actions), ptr(logp_old), ptr(adv), ptr(ret), ptr(dho),
-                                  ptr(stats), M, n_actions, clip_eps, c_v, c_ent, inv_m, stream_ptr()),
+    check(_lib.load().sc_ppo_loss(ptr(head_out), ld, ptr(actions), ptr(logp_old), ptr(adv), ptr(ret), ptr(_idx(idx, M)),
+                                  ptr(dho), ptr(stats), M, n_actions, clip_eps, c_v, c_ent, inv_m, stream_ptr(head_out)),
           "sc_ppo_loss")
     return dho, stats
 
@@ -447,4 +509,43 @@ def adam_flat(p, g, m, v, p_bf16, lr, beta1, beta2, eps, step, grad_scale=1.0, s
     _cuda(p, g, m, v)
     n = p.numel()
     check(_lib.load().sc_adam_flat(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), n, lr, beta1, beta2, eps, step,
-                                   grad_scale, ptr(step_dev), stream_ptr()), "sc_adam_flat")
+                                   grad_scale, ptr(step_dev), stream_ptr(p)), "sc_adam_flat")
+
+
+@_profiled("step_begin")
+def step_begin(grad, stats, step_dev=None):
+    """zero the flat gradient bucket and the statistics vector, advance the device-side step counter (one launch)"""
+    _cuda(grad, stats)
+    assert grad.dtype == F32 and grad.is_contiguous() and stats.dtype == F32 and stats.is_contiguous()
+    if step_dev is not None:
+        assert step_dev.dtype == torch.int64 and step_dev.is_cuda
+    check(_lib.load().sc_step_begin(ptr(grad), grad.numel(), ptr(stats), stats.numel(), ptr(step_dev), stream_ptr(grad)),
+          "sc_step_begin")
+
+
+@_profiled("snr_embed_fwd")
+def snr_embed_fwd(snr_db, u, v, W, B, emb=None, h=None):
+    """emb[b] = W tanh(s_b u + v), s_b = snr_db[b] / 20 (tensor [B] or float).  Returns (emb fp32 [B,D], h fp32 [B,E])."""
+    _cuda(u, v, W)
+    D, E = W.shape
+    snr_t, snr_s = (snr_db, 0.0) if torch.is_tensor(snr_db) else (None, float(snr_db))
+    if snr_t is not None:
+        assert snr_t.is_cuda and snr_t.dtype == F32 and snr_t.numel() == B
+    if emb is None:
+        emb = torch.empty(B, D, device=W.device, dtype=F32)
+    if h is None:
+        h = torch.empty(B, E, device=W.device, dtype=F32)
+    check(_lib.load().sc_snr_embed_fwd(ptr(snr_t), snr_s, ptr(u), ptr(v), ptr(W), ptr(emb), ptr(h), B, D, E,
+                                       stream_ptr(W)), "sc_snr_embed_fwd")
+    return emb, h
+
+
+@_profiled("snr_embed_bwd")
+def snr_embed_bwd(demb, h, snr_db, W, dW, du, dv, demb_scale=1.0):
+    _cuda(demb, h, W, dW, du, dv)
+    B, D = demb.shape
+    E = h.shape[1]
+    assert demb.dtype == F32 and demb.is_contiguous() and h.is_contiguous() and W.shape == (D, E)
+    snr_t, snr_s = (snr_db, 0.0) if torch.is_tensor(snr_db) else (None, float(snr_db))
+    check(_lib.load().sc_snr_embed_bwd(ptr(demb), ptr(h), ptr(snr_t), snr_s, ptr(W), ptr(dW), ptr(du), ptr(dv),
+                                       float(demb_scale), B, D, E, stream_ptr(W)), "sc_snr_embed_bwd")

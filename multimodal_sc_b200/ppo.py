@@ -4,7 +4,7 @@ Drop-in for `oracle/ppo.py: PPOAgent` (same constructor arguments, `update(rollo
 `minibatch_step(...)`; upstream /root/reference/README.md:1-2 has no
 trainer).  One optimizer step is a fixed kernel schedule on the current stream:
 
-    memset(flat grad, stats) -> Engine.forward -> sc_mse_fwd_bwd -> sc_ppo_loss -> Engine.backward
+    sc_step_begin (zero flat grad + stats, step counter) -> Engine.forward -> sc_mse_fwd_bwd -> sc_ppo_loss -> Engine.backward
       -> [NCCL all-reduce of the flat fp32 bucket, data-parallel only; SC_DP_OVERLAP=1 launches it in three regions,
           each as soon as backward has finished writing it] -> sc_adam_flat
 
@@ -74,70 +74,100 @@ class PPOAgent:
         self.stats = torch.zeros(8, device=dev, dtype=F32)      # pi, v, ent, kl, clipfrac, l_sem, -, -
         self.sums = torch.zeros(2, device=dev, dtype=torch.float64)
         # device-side mirror of step_count: the channel seed and Adam's bias correction read it inside the kernels,
-        # so a captured CUDA graph of the step advances both on every replay
+        # so a captured CUDA graph of the step advances both on every replay.  sc_step_begin (the first kernel of a
+        # step) increments it, so it equals step_count between steps and step_count + 1 inside one.
         self.dev_step = torch.zeros(1, device=dev, dtype=torch.int64)
-        self._graphs = {}                                        # (B, sample_offset) -> (CUDAGraph, static inputs)
+        self._graphs = {}                                        # key (shapes + every baked-in scalar) -> (CUDAGraph, static inputs)
         self._overlap = None                                     # dp.OverlappedGradAllReduce, built on first use
         # opt-in: measured 2 % SLOWER at 2 GPUs (21.6 -> 22.0-22.3 ms): the NCCL kernels take SMs away from the
         # persistent one-CTA-per-SM GEMMs, whose displaced CTAs then run as a second wave (profiles/README.md)
         self.overlap_allreduce = os.environ.get("SC_DP_OVERLAP", "0") != "0"
+        self._lsem_weight = 1.0 / self.world                     # this rank's share of the global-minibatch mean L_sem
+        self.last_perms = []                                     # permutations / per-minibatch statistics of the last
+        self.last_step_stats = []                                #   update() (parity tests)
+        self.allreduce_events = None                             # (start, end) CUDA events around the last gradient all-reduce
 
     # ---- one optimizer step on one (local) minibatch ---------------------------------------------
     def minibatch_step(self, cam, bev, actions, logp_old, adv, values_unused, ret, sample_offset: int = 0,
-                       sync_stats: bool = True, graph: bool = False):
+                       sync_stats: bool = True, graph: bool = False, *, row_idx=None, sample_idx=None,
+                       global_batch: int | None = None, arena_cap: int = 0):
         """cam/bev fp32 or bf16, actions int64, logp_old/adv/ret fp32 — all on the policy's device.
         With world_size > 1 the arguments are this rank's shard of the global minibatch and
         `sample_offset` is its first global sample index (noise counters are global).
         graph=True (single GPU): the step's ~130 launches are captured once per batch size in a CUDA graph and
-        replayed; the arguments are copied into the graph's static input buffers."""
-        if graph and self.world == 1:
+        replayed; the arguments are copied into the graph's static input buffers.
+        row_idx (int64 [B], device): the minibatch is rows row_idx of the given tensors (whole-rollout storage) — the
+        gather is fused into the first kernels (sc_patchify_bf16, sc_ppo_loss), no gathered copy is made.
+        sample_idx (int64 [B], device) + global_batch: this rank's samples sit at positions sample_idx of a global
+        minibatch of `global_batch` samples (ragged data-parallel slices of update())."""
+        if graph and self.world == 1 and row_idx is None and sample_idx is None:
             return self._graphed_step(cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats)
-        self._step_body(cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters=False)
+        self._step_body(cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters=False, row_idx=row_idx,
+                        sample_idx=sample_idx, global_batch=global_batch, arena_cap=arena_cap)
         if not sync_stats:
             return None
         return self.read_stats()
 
-    def _step_body(self, cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters: bool):
+    def _step_body(self, cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters: bool, row_idx=None,
+                   sample_idx=None, global_batch=None, arena_cap: int = 0):
         """the kernel schedule of one optimizer step.  device_counters=True: seed and Adam step come from
         self.dev_step inside the kernels (graph capture / replay), otherwise from the host's step_count."""
         sp, pol = self.spec, self.policy
         eng, flat = pol.engine, pol.flat
-        Bl = cam.shape[0]
-        flat.g32.zero_()
-        self.stats.zero_()
-        seed = self.seed if device_counters else self.seed + self.step_count
+        Bl = cam.shape[0] if row_idx is None else row_idx.numel()
+        gb = Bl * self.world if global_batch is None else int(global_batch)
+        # zero the gradient bucket and the statistics, dev_step += 1 (one launch)
+        ops.step_begin(flat.g32, self.stats, self.dev_step)
+        # dev_step already counts this step: seed + step_count = (seed - 1) + dev_step, Adam step = 0 + dev_step
+        seed = self.seed - 1 if device_counters else self.seed + self.step_count
         sdev = self.dev_step if device_counters else None
-        ho, A = eng.forward(cam, bev, self.snr_db, self.channel, seed, None, None, sample_offset, train=True,
-                            seed_dev=sdev)
-        # l_sem is a mean over the GLOBAL minibatch: each rank contributes its share
-        inv_m, sem_coef = dp.loss_scales(Bl, self.world, sp.c_sem)
-        eng.l_sem(A, Bl, self.stats[5:6], grad_coef=sem_coef)
-        dho = A.buf("ac.dho", tuple(ho.shape), F32)
-        ops.ppo_loss(ho, actions, logp_old, adv, ret, sp.n_actions, sp.clip_eps, sp.c_v, sp.c_ent, inv_m,
-                     dho=dho, stats=self.stats)
-        # data parallel, overlap mode: the decoder's gradients are all-reduced while the encoders' backward still runs,
-        # the camera encoder's while the BEV encoder's runs (three contiguous regions of the flat bucket, dp.grad_buckets)
+        # per-sample loss terms are means over the GLOBAL minibatch; l_sem is a local mean weighted by this rank's share
+        inv_m, sem_coef, self._lsem_weight = dp.loss_scales(Bl, self.world, sp.c_sem, global_batch=gb)
         if self.world > 1 and self._overlap is None:
             self._overlap = dp.OverlappedGradAllReduce(flat.g32, flat.offsets, self.pg)
         ov = self._overlap if (self.world > 1 and self.overlap_allreduce) else None
-        eng.backward(A, Bl, dho, None, self.channel, self.snr_db, seed, None, sample_offset, seed_dev=sdev,
-                     grad_ready=ov.ready if ov is not None else None)
+        if Bl > 0:
+            arena = eng.arena(Bl, cap=arena_cap) if arena_cap else None
+            ho, A = eng.forward(cam, bev, self.snr_db, self.channel, seed, None, None, sample_offset, train=True,
+                                seed_dev=sdev, row_idx=row_idx, sample_idx=sample_idx, arena=arena)
+            eng.l_sem(A, Bl, self.stats[5:6], grad_coef=sem_coef)
+            dho = A.buf("ac.dho", tuple(ho.shape), F32)
+            ops.ppo_loss(ho, actions, logp_old, adv, ret, sp.n_actions, sp.clip_eps, sp.c_v, sp.c_ent, inv_m,
+                         dho=dho, stats=self.stats, idx=row_idx)
+            # data parallel, overlap mode: the decoder's gradients are all-reduced while the encoders' backward still
+            # runs, the camera encoder's while the BEV encoder's runs (three contiguous regions, dp.grad_buckets)
+            eng.backward(A, Bl, dho, None, self.channel, self.snr_db, seed, None, sample_offset, seed_dev=sdev,
+                         grad_ready=ov.ready if ov is not None else None, sample_idx=sample_idx)
+        elif ov is not None:                                     # a rank without samples still joins every collective
+            for name in ("dec", "cam_enc", "bev_enc"):
+                ov.ready(name)
+        if self.world > 1:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if ov is not None:
             ov.finish()
         else:
             dp.allreduce_flat_grads(flat.g32, self.pg)
+        if self.world > 1:
+            ev1.record()
+            self.allreduce_events = (ev0, ev1)
         if device_counters:
             ops.adam_flat(flat.p32, flat.g32, flat.m, flat.v, flat.p16, sp.lr, sp.beta1, sp.beta2, sp.adam_eps,
-                          1, grad_scale=1.0, step_dev=self.dev_step)
+                          0, grad_scale=1.0, step_dev=self.dev_step)
         else:
             ops.adam_flat(flat.p32, flat.g32, flat.m, flat.v, flat.p16, sp.lr, sp.beta1, sp.beta2, sp.adam_eps,
                           self.step_count + 1, grad_scale=1.0)
-        self.dev_step.add_(1)
-        if not device_counters:
             self.step_count += 1
 
+    def _graph_key(self, cam, bev, sample_offset):
+        """everything a captured step bakes in: shapes / dtypes, the noise offset, and every scalar the kernels receive
+        by value (channel, SNR, Rician K, the whole spec incl. lr and the loss coefficients, seed)"""
+        snr = ("ptr", self.snr_db.data_ptr()) if torch.is_tensor(self.snr_db) else float(self.snr_db)
+        return (tuple(cam.shape), cam.dtype, tuple(bev.shape), bev.dtype, int(sample_offset), snr, self.channel,
+                float(self.policy.engine.rician_k), self.spec, int(self.seed))
+
     def _graphed_step(self, cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats):
-        key = (tuple(cam.shape), cam.dtype, tuple(bev.shape), bev.dtype, int(sample_offset))
+        key = self._graph_key(cam, bev, sample_offset)
         entry = self._graphs.get(key)
         if entry is None:
             # the first step of this shape runs eagerly (allocates the activation arena, sets kernel attributes);
@@ -163,13 +193,21 @@ class PPOAgent:
     def read_stats(self) -> dict:
         st = self.stats.clone()
         if self.world > 1:
-            st[5] /= self.world
+            st[5] *= self._lsem_weight
             torch.distributed.all_reduce(st, group=self.pg)
         s = st.cpu().tolist()                                     # the step's device->host read
         out = {"pi": s[0], "v": s[1], "ent": s[2], "kl": s[3], "clipfrac": s[4], "l_sem": s[5]}
         sp = self.spec
         out["total"] = out["pi"] + sp.c_v * out["v"] - sp.c_ent * out["ent"] + sp.c_sem * out["l_sem"]
         return out
+
+    def allreduce_ms(self):
+        """device time of the last gradient all-reduce (None on one rank); synchronises"""
+        if self.allreduce_events is None:
+            return None
+        ev0, ev1 = self.allreduce_events
+        ev1.synchronize()
+        return ev0.elapsed_time(ev1)
 
     # ---- advantages ----------------------------------------------------------------------------------
     def compute_advantages(self, rewards, values, dones, last_value):
@@ -182,30 +220,45 @@ class PPOAgent:
 
     # ---- full update over a rollout ----------------------------------------------------------------
     def update(self, rollout: dict) -> dict:
+        """rollout: this rank's trajectories (whole environments; dict of [T, N_local, ...] tensors, host or device).
+
+        Matches `oracle/ppo.py: PPOAgent.update` step for step: the permutation of every epoch is the oracle's
+        `torch.randperm(T * N_global, generator=cpu_gen(seed))` (bit-exact, host RNG).  With world_size > 1 every rank
+        draws the SAME global permutation and processes, of each global minibatch, the samples whose environment it
+        owns, at their global positions for the noise counters — so the N-rank update equals the 1-rank update on the
+        concatenated rollout (tests/test_dp_gloo.py, scripts/gpu_dp_check.py).
+        The observations go to the device once; minibatches are never materialised: the gather by `perm` is fused into
+        sc_patchify_bf16 / sc_ppo_loss (row-index argument)."""
         dev = self.policy.device
         to = lambda x, dt=F32: x.to(dev, dt, non_blocking=True).contiguous()
         rewards, values, dones = to(rollout["rewards"]), to(rollout["values"]), to(rollout["dones"])
         T, N = rewards.shape
         adv, ret = self.compute_advantages(rewards, values, dones, to(rollout["last_value"]))
         n = T * N
-        # observations go to the device once (pinned or pageable host tensors both work); minibatches are
-        # gathered on the device — a host-side gather of 870 MB per step would dominate the update
         obs_dt = lambda x: x.dtype if x.dtype == torch.bfloat16 else F32
         cam_h = to(rollout["cam"], obs_dt(rollout["cam"])).reshape(n, *rollout["cam"].shape[2:])
         bev_h = to(rollout["bev"], obs_dt(rollout["bev"])).reshape(n, *rollout["bev"].shape[2:])
         act = to(rollout["actions"], torch.int64).reshape(n)
         lp = to(rollout["logp"]).reshape(n)
         adv, ret = adv.reshape(n), ret.reshape(n)
-        mb = min(self.minibatch, n)
+        env_lo, n_envs_global = dp.env_shard(N, self.pg)
+        n_global = T * n_envs_global
+        mb = min(self.minibatch, n_global)                         # `minibatch` is the GLOBAL minibatch on any world size
         tot, cnt = {}, 0
+        self.last_perms, self.last_step_stats = [], []
         for _ in range(self.epochs):
-            perm = torch.randperm(n, generator=self.gen)            # host, seeded: bit-exact with the oracle
-            for i in range(0, n - mb + 1, mb):
-                idx = perm[i:i + mb]
-                idx_d = idx.to(dev)
-                cam, bev = cam_h[idx_d], bev_h[idx_d]
-                s = self.minibatch_step(cam, bev, act[idx_d], lp[idx_d], adv[idx_d], None,
-                                        ret[idx_d], sample_offset=self.rank * mb)
+            perm = torch.randperm(n_global, generator=self.gen)    # host, seeded: bit-exact with the oracle
+            self.last_perms.append(perm)
+            slices = [dp.local_minibatch_indices(perm[i:i + mb], n_envs_global, env_lo, N)
+                      for i in range(0, n_global - mb + 1, mb)]
+            # one capacity arena for the ragged local slices of this epoch (exact-size arena on one rank)
+            cap = 0 if self.world == 1 else (max(int(r.numel()) for r, _ in slices) + 255) // 256 * 256
+            for rows, pos in slices:
+                rows_d = rows.to(dev, non_blocking=True)
+                pos_d = None if self.world == 1 else pos.to(dev, non_blocking=True)
+                s = self.minibatch_step(cam_h, bev_h, act, lp, adv, None, ret, sample_offset=0, row_idx=rows_d,
+                                        sample_idx=pos_d, global_batch=mb, arena_cap=cap)
+                self.last_step_stats.append(s)
                 for k, v in s.items():
                     tot[k] = tot.get(k, 0.0) + v
                 cnt += 1

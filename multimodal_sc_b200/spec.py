@@ -15,6 +15,14 @@ Revisions relative to SURVEY.md §8 (allowed "once in PR1, then frozen"):
     issue slots per output element before the epilogue, not the tensor pipe, bounds them).
   * every encoder and the decoder end with a LayerNorm (pre-LN stacks need one);
     the semantic target of L_sem is that final-LN encoder feature.
+
+Round-2 OPTIONS (every default reproduces the frozen SPEC v0 bit for bit):
+  * gelu = "erf": the exact GELU x Phi(x) that SURVEY.md §8 originally froze, for interchange with an upstream
+    `nn.GELU()` model should one ever be published (direct-store GEMM epilogue; measured cost in profiles/);
+  * snr_cond: SNR-conditioned encoders, a per-sample embedding W tanh(s u + v), s = snr_db / 20, added to every
+    token next to the positional embedding (parameters {cam,bev}_enc.snr.{u,v,w});
+  * quant_bits > 0: the normalised symbols pass a 2^bits-level uniform quantiser on [-quant_clip, quant_clip]
+    before the channel, clipped straight-through gradient.
 """
 from __future__ import annotations
 
@@ -42,6 +50,12 @@ class SpecV0:
     # channel
     pnorm_eps: float = 1e-12
     rician_k: float = 4.0          # linear K-factor (6 dB) of the "rician" channel kind
+    # round-2 options (defaults = frozen SPEC v0)
+    gelu: str = "tanh"             # "tanh" | "erf"
+    snr_cond: bool = False         # SNR-conditioned encoders
+    snr_embed_dim: int = 64
+    quant_bits: int = 0            # 0 = continuous symbols
+    quant_clip: float = 4.0        # a power of two keeps the quantiser step exact in fp32
     # PPO
     gamma: float = 0.99
     lam: float = 0.95

@@ -18,6 +18,18 @@ def power_normalize(z: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     return z * torch.rsqrt(p + eps)
 
 
+def quantize_ste(zn: torch.Tensor, bits: int, clip: float) -> torch.Tensor:
+    """b-bit quantised symbols (no upstream code, /root/reference/README.md:1-2): mid-rise uniform
+    quantiser with L = 2^bits levels on [-clip, clip], q = (clamp(floor(zn / delta), -L/2, L/2 - 1) + 0.5) delta,
+    delta = 2 clip / L.  Gradient: clipped straight-through estimator (1 inside [-clip, clip], 0 outside)."""
+    L = 2 ** int(bits)
+    delta = 2.0 * clip / L
+    q = (torch.clamp(torch.floor(zn * (L / (2.0 * clip))), -L / 2, L / 2 - 1) + 0.5) * delta
+    inside = (zn.abs() <= clip).to(zn.dtype)
+    passed = zn * inside
+    return passed + (q - passed).detach()
+
+
 def snr_to_sigma(snr_db, batch: int, device, dtype) -> torch.Tensor:
     """sigma[B,1,1] with sigma^2 = 10^(-snr_db/10) per real dimension."""
     s = torch.as_tensor(snr_db, dtype=torch.float32, device=device)
@@ -72,32 +84,44 @@ def rician_fading(h0: torch.Tensor, k_factor: float) -> torch.Tensor:
 
 
 def channel_forward(z: torch.Tensor, snr_db, kind: str, *, seed=None, noise=None, fading=None,
-                    sample_offset: int = 0, eps: float = 1e-12, rician_k: float = 4.0):
+                    sample_offset: int = 0, eps: float = 1e-12, rician_k: float = 4.0, quant_bits: int = 0,
+                    quant_clip: float = 4.0, sample_idx=None):
     """z[B,2,k] -> (y[B,2,k], zn).  kind in {"awgn", "rayleigh", "rician", "none"}.  An explicit `fading` tensor is the
-    channel coefficient h itself for both fading kinds."""
+    channel coefficient h itself for both fading kinds.  quant_bits > 0: the channel input is quantize_ste(zn).
+    sample_idx (int64 [B], optional): global sample index of every row for the noise counters (ragged data-parallel
+    slices); default sample_offset + b."""
     B, M, k = z.shape
     zn = power_normalize(z, eps)
+    tx = quantize_ste(zn, quant_bits, quant_clip) if quant_bits > 0 else zn
     if kind == "none":
-        return zn, zn
+        return tx, zn
+    if sample_idx is not None and noise is None:
+        ids = [int(i) for i in sample_idx]
+        noise = torch.cat([make_noise(seed, 1, k, i) for i in ids]).to(z.device)
+        if kind in ("rayleigh", "rician") and fading is None:
+            fading = torch.cat([make_fading(seed, 1, i) for i in ids])
+            if kind == "rician":
+                fading = rician_fading(fading, rician_k)
+            fading = fading.to(z.device)
     sigma = snr_to_sigma(snr_db, B, z.device, z.dtype)
     if noise is None:
         if seed is None:
             raise ValueError("channel needs seed= or noise=")
         noise = make_noise(seed, B, k, sample_offset).to(z.device)
     if kind == "awgn":
-        return awgn(zn, sigma, noise), zn
+        return awgn(tx, sigma, noise), zn
     if kind == "rayleigh":
         if fading is None:
             if seed is None:
                 raise ValueError("rayleigh channel needs seed= or fading=")
             fading = make_fading(seed, B, sample_offset).to(z.device)
-        return rayleigh(zn, sigma, noise, fading), zn
+        return rayleigh(tx, sigma, noise, fading), zn
     if kind == "rician":                                      # same receiver, line-of-sight component added to h
         if fading is None:
             if seed is None:
                 raise ValueError("rician channel needs seed= or fading=")
             fading = rician_fading(make_fading(seed, B, sample_offset), rician_k).to(z.device)
-        return rayleigh(zn, sigma, noise, fading), zn
+        return rayleigh(tx, sigma, noise, fading), zn
     raise ValueError(f"unknown channel kind {kind!r}")
 
 

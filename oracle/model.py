@@ -27,12 +27,14 @@ def patchify(img: torch.Tensor, p: int) -> torch.Tensor:
 
 
 class Block(nn.Module):
-    """pre-LN transformer block: x += proj(attn(ln1 x)); x += fc2(gelu_tanh(fc1(ln2 x)))."""
+    """pre-LN transformer block: x += proj(attn(ln1 x)); x += fc2(gelu(fc1(ln2 x))); GELU in the tanh form (SPEC v0) or
+    exact (spec.gelu == "erf")."""
 
     def __init__(self, spec: SpecV0):
         super().__init__()
         D = spec.d_model
         self.h = spec.n_heads
+        self.gelu_approx = "tanh" if spec.gelu == "tanh" else "none"
         self.ln1 = nn.LayerNorm(D, eps=spec.ln_eps)
         self.qkv = nn.Linear(D, 3 * D)
         self.proj = nn.Linear(D, D)
@@ -50,8 +52,26 @@ class Block(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = x + self.proj(self.attention(self.ln1(x)))
-        x = x + self.fc2(F.gelu(self.fc1(self.ln2(x)), approximate="tanh"))
+        x = x + self.fc2(F.gelu(self.fc1(self.ln2(x)), approximate=self.gelu_approx))
         return x
+
+
+class SnrEmbed(nn.Module):
+    """SNR conditioning (no upstream code): emb[b] = w tanh(s_b u + v), s_b = snr_db[b] / 20."""
+
+    def __init__(self, spec: SpecV0):
+        super().__init__()
+        E, D = spec.snr_embed_dim, spec.d_model
+        self.u = nn.Parameter(torch.zeros(E))
+        self.v = nn.Parameter(torch.zeros(E))
+        self.w = nn.Parameter(torch.zeros(D, E))
+
+    def forward(self, snr_db, batch: int, device) -> torch.Tensor:
+        s = torch.as_tensor(snr_db, dtype=torch.float32, device=device)
+        if s.dim() == 0:
+            s = s.expand(batch)
+        s = s * 0.05
+        return torch.tanh(s[:, None] * self.u + self.v) @ self.w.t()          # [B, D]
 
 
 class Encoder(nn.Module):
@@ -66,9 +86,12 @@ class Encoder(nn.Module):
         self.blocks = nn.ModuleList([Block(spec) for _ in range(spec.enc_layers)])
         self.norm = nn.LayerNorm(spec.d_model, eps=spec.ln_eps)
         self.sym = nn.Linear(spec.d_model, spec.c_sym)
+        self.snr = SnrEmbed(spec) if spec.snr_cond else None
 
-    def forward(self, img: torch.Tensor):
+    def forward(self, img: torch.Tensor, snr_db=None):
         x = self.patch_embed(patchify(img, self.patch)) + self.pos
+        if self.snr is not None:
+            x = x + self.snr(snr_db, img.shape[0], img.device)[:, None, :]
         for b in self.blocks:
             x = b(x)
         t = self.norm(x)                                   # [B,S,D]  semantic feature
@@ -165,13 +188,15 @@ class SemComPolicy(nn.Module):
                     p.copy_(w * std)
 
     def forward(self, cam, bev, snr_db, *, channel: str = "awgn", seed=None, noise=None,
-                fading=None, sample_offset: int = 0, rician_k=None):
-        z_c, t_c = self.cam_enc(cam)
-        z_b, t_b = self.bev_enc(bev)
+                fading=None, sample_offset: int = 0, rician_k=None, sample_idx=None):
+        z_c, t_c = self.cam_enc(cam, snr_db)
+        z_b, t_b = self.bev_enc(bev, snr_db)
         z = torch.stack([z_c, z_b], dim=1)                  # [B,2,k]
         y, zn = ch.channel_forward(z, snr_db, channel, seed=seed, noise=noise, fading=fading,
                                    sample_offset=sample_offset, eps=self.spec.pnorm_eps,
-                                   rician_k=self.spec.rician_k if rician_k is None else rician_k)
+                                   rician_k=self.spec.rician_k if rician_k is None else rician_k,
+                                   quant_bits=self.spec.quant_bits, quant_clip=self.spec.quant_clip,
+                                   sample_idx=sample_idx)
         f, recon = self.dec(y)
         logits, value = self.ac(f)
         l_sem = semantic_distortion(recon, torch.cat([t_c, t_b], dim=1))

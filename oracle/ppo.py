@@ -76,6 +76,8 @@ class PPOAgent:
         self.gen = torch.Generator().manual_seed(seed)
         self.opt = torch.optim.Adam(policy.parameters(), lr=spec.lr,
                                     betas=(spec.beta1, spec.beta2), eps=spec.adam_eps)
+        self.last_perms = []          # permutations / per-minibatch statistics of the last update() (parity tests)
+        self.last_step_stats = []
 
     def minibatch_step(self, cam, bev, actions, logp_old, adv, values_unused, ret,
                        sample_offset: int = 0):
@@ -104,12 +106,15 @@ class PPOAgent:
         adv, ret = adv.reshape(n), ret.reshape(n)
         mb = min(self.minibatch, n)
         stats, cnt = {}, 0
+        self.last_perms, self.last_step_stats = [], []
         for _ in range(self.epochs):
             perm = minibatch_permutation(n, self.gen)
+            self.last_perms.append(perm)
             for i in range(0, n - mb + 1, mb):
-                idx = perm[i:i + mb]
+                idx = perm[i:i + mb].to(cam.device)
                 s = self.minibatch_step(cam[idx], bev[idx], act[idx], lp[idx], adv[idx],
                                         val[idx], ret[idx])
+                self.last_step_stats.append(s)
                 for k, v in s.items():
                     stats[k] = stats.get(k, 0.0) + v
                 cnt += 1

@@ -130,10 +130,13 @@ def test_ppo_loss_fwd_bwd(cuda_lib, M):
     out["total"].backward()
     dho, stats = ops.ppo_loss(ho.cuda(), act.cuda(), lp_old.cuda(), adv.cuda(), ret.cuda(), A, SPEC.clip_eps,
                               SPEC.c_v, SPEC.c_ent, 1.0 / M)
-    _close(dho, hr.grad, 1e-4, 1e-7, "dho")
+    # fp32 rtol 1e-5 (north_star).  The logit gradient inv_m (gp (1[j=a] - p_j) + c_ent p_j (lp_j + H)) cancels O(1)
+    # terms, so the element-wise floor is ulp(1) * inv_m, not ulp(result): the absolute term is 1e-5 of the tensor's scale
+    scale = float(hr.grad.abs().max())
+    _close(dho, hr.grad, 1e-5, 1e-5 * scale, "dho")
     s = stats.cpu()
     for i, k in enumerate(["pi", "v", "ent", "kl", "clipfrac"]):
-        assert abs(float(s[i]) - float(out[k])) <= 1e-5 + 1e-4 * abs(float(out[k])), (k, float(s[i]), float(out[k]))
+        assert abs(float(s[i]) - float(out[k])) <= 1e-6 + 1e-5 * abs(float(out[k])), (k, float(s[i]), float(out[k]))
 
 
 def test_adam_matches_torch(cuda_lib):

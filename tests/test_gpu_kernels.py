@@ -206,3 +206,157 @@ def test_rician_channel_matches_golden_v1(cuda_lib):
     snr = torch.tensor([-3.0, 6.0, 15.0])
     y, _, _ = ops.pnorm_channel_fwd(z.cuda(), "rician", snr.cuda(), seed=99, sample_offset=5, rician_k=2.5)
     _close(y, g["rician_k2.5_seed99_off5_y"], 1e-5, 2e-5, "rician golden")
+
+
+# ---- round 2: ABI v3 additions ------------------------------------------------------------------------------------
+def test_box_muller_fast_error_bound(cuda_lib):
+    """the channel kernel's SFU Box-Muller against the float64 oracle over 2^26 normals (and dense coverage of the
+    dangerous u -> 1 region is part of any such sample: 2^26 / 2^23 = 8 draws per representable u on average):
+    max abs error <= 8e-6 (bound derived in csrc/channel.cu), so y = zn + sigma n stays inside fp32 rtol 1e-5 +
+    atol 2e-5 for sigma <= 1.78 (-5 dB); the accurate variant stays the yardstick."""
+    from multimodal_sc_b200 import ops
+    n_quads = 1 << 22
+    worst = {False: 0.0, True: 0.0}
+    for chunk in range(4):
+        off = chunk * n_quads + (7 << 30) * chunk
+        w = oph.philox_words(99, n_quads, 0, off)
+        u = oph.u32_to_uniform(w)
+        n0, n1 = oph.box_muller(u[:, 0], u[:, 1])
+        n2, n3 = oph.box_muller(u[:, 2], u[:, 3])
+        ref = torch.from_numpy(np.stack([n0, n1, n2, n3], axis=-1))
+        for exact in (False, True):
+            got = ops.philox_normals(n_quads, 99, off, exact=exact).cpu().double()
+            worst[exact] = max(worst[exact], float((got - ref).abs().max()))
+    assert worst[True] <= 2e-6, worst
+    assert worst[False] <= 8e-6, worst
+
+
+def test_box_muller_fast_near_one(cuda_lib):
+    """u -> 1 (r -> 0), where lg2.approx's absolute error would dominate: the series branch keeps the error bounded.
+    Draws are filtered from a large sample by u_a > 1 - 2^-6 (1.6 % of them)."""
+    from multimodal_sc_b200 import ops
+    n_quads = 1 << 21
+    w = oph.philox_words(5, n_quads, 0, 0)
+    u = oph.u32_to_uniform(w)
+    n0, n1 = oph.box_muller(u[:, 0], u[:, 1])
+    got = ops.philox_normals(n_quads, 5, 0, exact=False).cpu().double().numpy()
+    near = u[:, 0] > 1.0 - 2.0 ** -6
+    assert near.sum() > 10000
+    err = np.maximum(np.abs(got[near, 0] - n0[near]), np.abs(got[near, 1] - n1[near]))
+    assert err.max() <= 2e-6, float(err.max())
+
+
+def test_channel_sample_idx_matches_offsets(cuda_lib):
+    """sample_idx (global position of every local sample) draws the noise / fading of exactly those samples: a ragged
+    subset of a batch equals the same rows of the full-batch output, bit for bit"""
+    from multimodal_sc_b200 import ops
+    k, B = SPEC.k_sym, 24
+    g = torch.Generator().manual_seed(0)
+    z = (torch.randn(B, 2, k, generator=g) * 0.3).cuda()
+    snr = torch.linspace(-5, 20, B).cuda()
+    pos = torch.tensor([0, 3, 4, 9, 17, 23])
+    for kind in ("awgn", "rayleigh", "rician"):
+        y_full, _, sc = ops.pnorm_channel_fwd(z, kind, snr, seed=77, sample_offset=100, rician_k=2.0)
+        zs, ss = z[pos.cuda()].contiguous(), snr[pos.cuda()].contiguous()
+        y_sub, _, sc_sub = ops.pnorm_channel_fwd(zs, kind, ss, seed=77, sample_idx=(pos + 100).cuda(), rician_k=2.0)
+        assert torch.equal(y_sub, y_full[pos.cuda()]), kind
+        dy = torch.randn(B, 2, k, generator=g).cuda()
+        dz_full, _ = ops.pnorm_channel_bwd(dy, z, sc, kind, snr, seed=77, sample_offset=100, rician_k=2.0)
+        dz_sub, _ = ops.pnorm_channel_bwd(dy[pos.cuda()].contiguous(), zs, sc_sub, kind, ss, seed=77,
+                                          sample_idx=(pos + 100).cuda(), rician_k=2.0)
+        assert torch.equal(dz_sub, dz_full[pos.cuda()]), kind
+
+
+@pytest.mark.parametrize("bits", [1, 4, 8])
+@pytest.mark.parametrize("kind", ["none", "awgn", "rayleigh"])
+def test_quantised_symbols_fwd_bwd(cuda_lib, kind, bits):
+    """b-bit quantised symbols with the clipped straight-through gradient vs oracle/channel.py: quantize_ste"""
+    from multimodal_sc_b200 import ops
+    k, B, clip = SPEC.k_sym, 16, 2.0
+    g = torch.Generator().manual_seed(bits)
+    z = torch.randn(B, 2, k, generator=g) * 0.3
+    z[0, 0, :8] *= 40.0                                       # a few symbols beyond the clip level after normalisation
+    snr = torch.linspace(0, 20, B)
+    dy = torch.randn(B, 2, k, generator=g)
+    zr = z.clone().requires_grad_(True)
+    y_ref, _ = och.channel_forward(zr, snr, kind, seed=3, quant_bits=bits, quant_clip=clip)
+    (y_ref * dy).sum().backward()
+    y, _, scale = ops.pnorm_channel_fwd(z.cuda(), kind, snr.cuda(), seed=3, quant_bits=bits, quant_clip=clip)
+    dz, _ = ops.pnorm_channel_bwd(dy.cuda(), z.cuda(), scale, kind, snr.cuda(), seed=3, quant_bits=bits, quant_clip=clip)
+    # a symbol within one ulp of a decision boundary may fall into the neighbouring cell
+    step = 2 * clip / 2 ** bits
+    d = (y.cpu() - y_ref.detach()).abs()
+    flipped = d > 0.25 * step
+    assert float(flipped.float().mean()) < 1e-4, float(flipped.float().mean())
+    _close(y.cpu()[~flipped], y_ref.detach()[~flipped], 1e-5, 2e-5, "y quantised")
+    ok = (~flipped).reshape(B * 2, k).all(dim=1).reshape(B, 2)  # rows without a flipped cell
+    _close(dz.cpu()[ok], zr.grad[ok], 1e-4, 2e-5, "dz quantised")
+    if kind == "none":                                         # noiseless output lies on the quantiser grid
+        lv = (y.cpu() / step - 0.5)
+        assert float((lv - lv.round()).abs().max()) < 1e-4
+        assert int(torch.unique(lv.round()).numel()) <= 2 ** bits
+
+
+def test_patchify_row_index_gather(cuda_lib):
+    from multimodal_sc_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for shape, P, dt in [((10, 3, 128, 128), 16, torch.float32), ((12, 1, 64, 64), 8, torch.bfloat16)]:
+        img = torch.rand(*shape, generator=g).to(dt).cuda()
+        idx = torch.tensor([9, 0, 3, 3, 7], dtype=torch.int64).cuda()
+        got = ops.patchify(img, P, row_idx=idx)
+        ref = ops.patchify(img[idx].contiguous(), P)
+        assert torch.equal(got, ref)
+
+
+def test_ppo_loss_index_gather_and_bad_action(cuda_lib):
+    from multimodal_sc_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    n, M, A = 100, 37, SPEC.n_actions
+    ho = torch.randn(M, A + 1, generator=g).cuda()
+    act = torch.randint(0, A, (n,), generator=g).cuda()
+    lp, adv, ret = (torch.randn(n, generator=g).cuda() for _ in range(3))
+    idx = torch.randperm(n, generator=g)[:M].cuda()
+    d0, s0 = ops.ppo_loss(ho, act[idx].contiguous(), lp[idx].contiguous(), adv[idx].contiguous(), ret[idx].contiguous(),
+                          A, SPEC.clip_eps, SPEC.c_v, SPEC.c_ent, 1.0 / M)
+    d1, s1 = ops.ppo_loss(ho, act, lp, adv, ret, A, SPEC.clip_eps, SPEC.c_v, SPEC.c_ent, 1.0 / M, idx=idx)
+    assert torch.equal(d0, d1) and torch.allclose(s0, s1, rtol=1e-6, atol=1e-7)
+    bad = act[idx].contiguous()
+    bad[5] = A                                               # out of range: the statistics turn NaN (loud), no trap
+    _, sb = ops.ppo_loss(ho, bad, lp[idx].contiguous(), adv[idx].contiguous(), ret[idx].contiguous(), A, SPEC.clip_eps,
+                         SPEC.c_v, SPEC.c_ent, 1.0 / M)
+    assert torch.isnan(sb[0]) or torch.isnan(sb[3])
+
+
+def test_step_begin(cuda_lib):
+    from multimodal_sc_b200 import ops
+    g32 = torch.randn(5165888, device="cuda")
+    stats = torch.randn(8, device="cuda")
+    step = torch.full((1,), 41, device="cuda", dtype=torch.int64)
+    ops.step_begin(g32, stats, step)
+    assert float(g32.abs().max()) == 0.0 and float(stats.abs().max()) == 0.0 and int(step) == 42
+    ops.step_begin(g32[:4], stats, None)
+    assert int(step) == 42
+
+
+def test_snr_embed_fwd_bwd(cuda_lib):
+    from multimodal_sc_b200 import ops
+    B, D, E = 70, 256, 64
+    g = torch.Generator().manual_seed(2)
+    u, v, W = torch.randn(E, generator=g), torch.randn(E, generator=g) * 0.3, torch.randn(D, E, generator=g) * 0.1
+    snr = torch.linspace(-5, 20, B)
+    demb = torch.randn(B, D, generator=g)
+    ur, vr, Wr = (t.clone().requires_grad_(True) for t in (u, v, W))
+    emb_ref = torch.tanh((snr * 0.05)[:, None] * ur + vr) @ Wr.t()
+    (emb_ref * demb * 3.0).sum().backward()
+    for s_arg, s_ref in ((snr.cuda(), None), (7.5, 7.5)):
+        if s_ref is not None:
+            ur, vr, Wr = (t.clone().requires_grad_(True) for t in (u, v, W))
+            emb_ref = torch.tanh(torch.full((B,), s_ref * 0.05)[:, None] * ur + vr) @ Wr.t()
+            (emb_ref * demb * 3.0).sum().backward()
+        emb, h = ops.snr_embed_fwd(s_arg, u.cuda(), v.cuda(), W.cuda(), B)
+        _close(emb, emb_ref, 1e-5, 1e-6, "emb")
+        dW, du, dv = torch.zeros(D, E, device="cuda"), torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
+        ops.snr_embed_bwd(demb.cuda(), h, s_arg, W.cuda(), dW, du, dv, demb_scale=3.0)
+        _close(dW, Wr.grad, 1e-4, 1e-5, "dW")
+        _close(du, ur.grad, 1e-4, 1e-5, "du")
+        _close(dv, vr.grad, 1e-4, 1e-5, "dv")

@@ -171,7 +171,7 @@ def test_dp_shards_equal_full_batch_on_gpu(cuda_lib):
 
     def run(lo, hi, world):
         n = hi - lo
-        inv_m, sem_coef = dp.loss_scales(n, world, SPEC.c_sem)
+        inv_m, sem_coef, _ = dp.loss_scales(n, world, SPEC.c_sem)
         stats = torch.zeros(8, device="cuda")
         ho, A = eng.forward(cam[lo:hi].contiguous(), bev[lo:hi].contiguous(), 8.0, "rayleigh", 99, None, None, lo,
                             train=True)

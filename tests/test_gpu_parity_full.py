@@ -1,0 +1,303 @@
+"""Parity at BASELINE.json's REAL sizes: the fp32 oracle runs on the GPU (eager PyTorch, TF32 off) next to the native
+bf16 tensor-core path on identical weights, inputs and noise seeds.
+
+  cfg2  B = 256   forward, AWGN 10 dB
+  cfg4  B = 1024  Rayleigh, per-sample SNR cycling through {-5, 0, 5, 10, 15, 20} dB, forward + L_sem + backward
+  cfg3  B = 4096  one PPO minibatch step (forward, fused loss, backward, Adam)
+  a10   update(rollout) native vs oracle: identical permutations (torch.equal), per-minibatch statistics
+
+Tolerances (north_star: bf16 rtol 2e-2): every activation / statistic within 2e-2 of the reference tensor's scale
+(max |ref|); EVERY gradient tensor with max-abs error <= 2e-2 of its scale; after the Adam step every weight whose
+gradient is resolved (|g_ref| > 10 x the tensor's max gradient error — the first Adam step is lr * sign(g), which is
+discontinuous at 0) moved by the reference amount within 2e-2 * lr."""
+import pytest
+import torch
+
+from multimodal_sc_b200.spec import SpecV0
+from oracle.model import SemComPolicy as OraclePolicy
+from oracle.ppo import PPOAgent as OracleAgent
+
+pytestmark = pytest.mark.gpu
+SPEC = SpecV0()
+
+
+@pytest.fixture(autouse=True)
+def _fp32_oracle():
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _pair(spec=SPEC, std=0.05, seed=3):
+    """oracle on the GPU (fp32) and the native policy with the same weights; non-trivial LayerNorm affine and biases"""
+    from multimodal_sc_b200.model import SemComPolicy
+    o = OraclePolicy(spec)
+    o.reset_parameters(std=std, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in o.named_parameters():
+            if n.endswith("bias") or n.endswith(".v"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+            elif ".ln" in n or "norm" in n:
+                p.copy_(1.0 + torch.randn(p.shape, generator=g) * 0.1)
+            elif n.endswith(".u"):
+                p.copy_(torch.randn(p.shape, generator=g))
+    n = SemComPolicy(spec)
+    n.load_state_dict(o.state_dict())
+    return o.cuda(), n
+
+
+def _inputs(B, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    cam = torch.rand(B, 3, 128, 128, generator=g)
+    bev = (torch.rand(B, 1, 64, 64, generator=g) < 0.1).float() * torch.rand(B, 1, 64, 64, generator=g)
+    return cam.cuda(), bev.cuda()
+
+
+def _rel(got, ref):
+    got, ref = got.detach().float(), ref.detach().float().to(got.device)
+    return float((got - ref).abs().max() / (ref.abs().max() + 1e-30))
+
+
+def _grad_table(named_ref, named_got):
+    """[(max-abs error / scale, name, scale)] per parameter tensor, worst first"""
+    rows = []
+    for (name, gr), (_, gg) in zip(named_ref, named_got):
+        gr, gg = gr.detach().double(), gg.detach().double().to(gr.device)
+        scale = float(gr.abs().max())
+        rows.append((float((gr - gg).abs().max()) / (scale + 1e-30), name, scale))
+    rows.sort(reverse=True)
+    return rows
+
+
+def test_cfg2_forward_b256_awgn10(cuda_lib):
+    o, n = _pair()
+    cam, bev = _inputs(256)
+    with torch.no_grad():
+        lo, vo, ao = o(cam, bev, 10.0, channel="awgn", seed=1234)
+        ln, vn, an = n(cam, bev, 10.0, channel="awgn", seed=1234)
+    errs = {"z": _rel(an["z"], ao["z"]), "y": _rel(an["y"], ao["y"]), "logits": _rel(ln, lo), "value": _rel(vn, vo),
+            "l_sem": abs(float(an["l_sem"]) - float(ao["l_sem"])) / float(ao["l_sem"])}
+    assert all(e < 2e-2 for e in errs.values()), errs
+
+
+def test_cfg4_rayleigh_sweep_b1024_fwd_bwd(cuda_lib):
+    o, n = _pair()
+    B = 1024
+    cam, bev = _inputs(B, seed=1)
+    snr = torch.tensor([-5.0, 0.0, 5.0, 10.0, 15.0, 20.0]).repeat(B // 6 + 1)[:B].cuda()
+    g = torch.Generator().manual_seed(9)
+    gl, gv = torch.randn(B, SPEC.n_actions, generator=g).cuda() / B, torch.randn(B, generator=g).cuda() / B
+
+    def run(model):
+        l, v, aux = model(cam, bev, snr, channel="rayleigh", seed=77)
+        loss = (l * gl).sum() + (v * gv).sum() + aux["l_sem"]
+        loss.backward()
+        return l.detach(), v.detach(), {k: a.detach() for k, a in aux.items()}
+
+    lo, vo, ao = run(o)
+    ln, vn, an = run(n)
+    errs = {"z": _rel(an["z"], ao["z"]), "y": _rel(an["y"], ao["y"]), "logits": _rel(ln, lo), "value": _rel(vn, vo),
+            "l_sem": abs(float(an["l_sem"]) - float(ao["l_sem"])) / float(ao["l_sem"])}
+    assert all(e < 2e-2 for e in errs.values()), errs
+    table = _grad_table([(k, p.grad) for k, p in o.named_parameters()], [(k, p.grad) for k, p in n.named_parameters()])
+    bad = [r for r in table if r[0] > 2e-2]
+    assert not bad, f"gradient tensors beyond 2e-2 of their scale (err/scale, name, scale): {bad[:10]}"
+
+
+def test_cfg3_minibatch_step_b4096(cuda_lib):
+    from multimodal_sc_b200 import ops, synthetic
+    from multimodal_sc_b200.ppo import PPOAgent
+    o, n = _pair()
+    B = 4096
+    mb = synthetic.minibatch(SPEC, B, seed=2, device="cuda")
+    ao = OracleAgent(o, SPEC, minibatch=B, seed=1234)
+    an = PPOAgent(n, SPEC, minibatch=B, seed=1234)
+    p_before = {k: v.detach().clone() for k, v in o.named_parameters()}
+    so = ao.minibatch_step(mb["cam"], mb["bev"], mb["actions"], mb["logp_old"], mb["adv"], None, mb["ret"])
+    grads = {}
+    orig = ops.adam_flat
+
+    def spy(p32, g32, *a, **k):
+        grads["g"] = g32.clone()
+        return orig(p32, g32, *a, **k)
+
+    ops.adam_flat = spy
+    try:
+        sn = an.minibatch_step(mb["cam"], mb["bev"], mb["actions"], mb["logp_old"], mb["adv"], None, mb["ret"])
+    finally:
+        ops.adam_flat = orig
+    for k in ("pi", "v", "ent", "kl", "l_sem", "total"):
+        assert abs(sn[k] - so[k]) <= 2e-2 * max(abs(so[k]), 0.05), (k, sn[k], so[k])
+    assert abs(sn["clipfrac"] - so["clipfrac"]) <= 2e-2, (sn["clipfrac"], so["clipfrac"])
+    flat = n.flat
+    g_native = [(name, grads["g"][off:off + cnt].view(flat.shapes[name])) for name, (off, cnt) in flat.offsets.items()]
+    g_oracle = [(name, p.grad) for name, p in o.named_parameters()]
+    table = _grad_table(g_oracle, g_native)
+    bad = [r for r in table if r[0] > 2e-2]
+    assert not bad, f"gradient tensors beyond 2e-2 of their scale (err/scale, name, scale): {bad[:10]}"
+    # Adam-updated weights: where the gradient is resolved, the update matches within 2e-2 of lr
+    sd_n = dict(n.named_parameters())
+    worst = 0.0
+    for (name, go), (_, gn) in zip(g_oracle, g_native):
+        err = float((go - gn.to(go.device)).abs().max())
+        resolved = go.abs() > 10.0 * err
+        do = (dict(o.named_parameters())[name].detach() - p_before[name])
+        dn = (sd_n[name].detach() - p_before[name])
+        if resolved.any():
+            worst = max(worst, float((do - dn)[resolved].abs().max()))
+    assert worst <= 2e-2 * SPEC.lr, (worst, SPEC.lr)
+
+
+def test_update_matches_oracle_update(cuda_lib):
+    """a10 at update() level: same rollout, same seed -> identical permutations (bit-exact, torch.equal) and
+    per-minibatch statistics within the bf16 tolerance; T = 8, N = 8, 2 epochs, minibatches of 16 (8 optimizer steps)."""
+    from multimodal_sc_b200 import synthetic
+    from multimodal_sc_b200.ppo import PPOAgent
+    o, n = _pair()
+    T, N = 8, 8
+    ro = synthetic.rollout(SPEC, T, N, seed=11)
+    ao = OracleAgent(o, SPEC, minibatch=16, epochs=2, seed=99, channel="awgn")
+    an = PPOAgent(n, SPEC, minibatch=16, epochs=2, seed=99, channel="awgn")
+    so = ao.update({k: v.cuda() for k, v in ro.items()})
+    sn = an.update(ro)
+    assert len(ao.last_perms) == len(an.last_perms) == 2
+    for po, pn in zip(ao.last_perms, an.last_perms):
+        assert po.dtype == torch.int64 and torch.equal(po.cpu(), pn.cpu())
+    assert len(ao.last_step_stats) == len(an.last_step_stats) == 8
+    for i, (a, b) in enumerate(zip(ao.last_step_stats, an.last_step_stats)):
+        for k in ("pi", "v", "ent", "l_sem", "total"):
+            # later steps compare two trajectories that already differ by bf16-level weight updates
+            tol = 2e-2 * max(abs(a[k]), 0.05)
+            assert abs(a[k] - b[k]) <= tol, (i, k, a[k], b[k])
+    for k in ("pi", "v", "ent", "l_sem", "total"):
+        assert abs(so[k] - sn[k]) <= 2e-2 * max(abs(so[k]), 0.05), (k, so[k], sn[k])
+    assert an.step_count == ao.step_count == 8 and int(an.dev_step) == 8
+
+
+def test_ragged_rank_slices_equal_full_minibatch(cuda_lib):
+    """SURVEY.md §8e on the native path: two 'ranks' that own 3 and 5 of 8 environments process the ragged parts of one
+    global minibatch (capacity arena, fused gather, global noise positions); the SUM of their flat gradients equals the
+    gradient of the 1-rank step on the whole minibatch, and so do the combined statistics."""
+    from multimodal_sc_b200 import dp, ops, synthetic
+    from multimodal_sc_b200.model import SemComPolicy
+    pol = SemComPolicy(SPEC, init_std=0.05, seed=2)
+    eng, flat = pol.engine, pol.flat
+    T, N, MB = 4, 8, 24
+    ro = synthetic.rollout(SPEC, T, N, seed=4)
+    perm = torch.randperm(T * N, generator=torch.Generator().manual_seed(0))[:MB]
+    g = torch.Generator().manual_seed(1)
+    adv_all, ret_all = torch.randn(T, N, generator=g), torch.randn(T, N, generator=g)
+    lp_all = torch.full((T, N), -2.2) + 0.1 * torch.randn(T, N, generator=g)
+
+    def run(env_lo, n_loc, world):
+        sl = slice(env_lo, env_lo + n_loc)
+        fl = lambda x: x[:, sl].reshape(T * n_loc, *x.shape[2:]).contiguous().cuda()
+        rows, pos = dp.local_minibatch_indices(perm, N, env_lo, n_loc)
+        rows_d, pos_d = rows.cuda(), pos.cuda()
+        inv_m, sem_coef, share = dp.loss_scales(rows.numel(), world, SPEC.c_sem, global_batch=MB)
+        stats = torch.zeros(8, device="cuda")
+        arena = eng.arena(rows.numel(), cap=32) if world > 1 else None
+        ho, A = eng.forward(fl(ro["cam"]), fl(ro["bev"]), 8.0, "rayleigh", 99, None, None, 0, train=True,
+                            row_idx=rows_d, sample_idx=pos_d, arena=arena)
+        eng.l_sem(A, rows.numel(), stats[5:6], grad_coef=sem_coef)
+        dho = torch.empty_like(ho)
+        ops.ppo_loss(ho, fl(ro["actions"]), fl(lp_all), fl(adv_all), fl(ret_all), SPEC.n_actions, SPEC.clip_eps,
+                     SPEC.c_v, SPEC.c_ent, inv_m, dho=dho, stats=stats, idx=rows_d)
+        eng.backward(A, rows.numel(), dho, None, "rayleigh", 8.0, 99, None, 0, sample_idx=pos_d)
+        stats[5] *= share
+        return stats, rows.numel()
+
+    flat.g32.zero_()
+    s_full, n_full = run(0, N, 1)
+    g_full = flat.g32.clone()
+    flat.g32.zero_()
+    s_a, n_a = run(0, 3, 2)
+    s_b, n_b = run(3, 5, 2)
+    g_dp = flat.g32.clone()
+    assert n_a + n_b == n_full == MB and n_a != n_b
+    scale = float(g_full.abs().max())
+    assert float((g_full - g_dp).abs().max()) <= 2e-2 * scale
+    cos = float((g_full.double() @ g_dp.double()) / (g_full.double().norm() * g_dp.double().norm()))
+    assert cos > 0.9999, cos
+    assert torch.allclose((s_a + s_b)[:6].cpu(), s_full[:6].cpu(), rtol=2e-3, atol=1e-5), (s_a + s_b, s_full)
+
+
+def test_two_forwards_then_backward_matches_oracle(cuda_lib):
+    """two grad-mode forwards (two SNRs) summed into one loss, with a no_grad forward of the same batch size in between:
+    every autograd node owns its activation arena, so the gradients equal the oracle's"""
+    o, n = _pair()
+    B = 4
+    cam, bev = _inputs(B, seed=5)
+    g = torch.Generator().manual_seed(3)
+    gl = torch.randn(B, SPEC.n_actions, generator=g).cuda()
+
+    def loss_of(model):
+        l1, v1, a1 = model(cam, bev, 0.0, channel="awgn", seed=5)
+        with torch.no_grad():
+            model(cam, bev, 3.0, channel="awgn", seed=6)
+        l2, v2, a2 = model(cam, bev, 15.0, channel="awgn", seed=7)
+        return (l1 * gl).sum() + 0.5 * (l2 * gl).sum() + v1.sum() - v2.sum() + a1["l_sem"] + 2.0 * a2["l_sem"]
+
+    loss_of(o).backward()
+    loss_of(n).backward()
+    table = _grad_table([(k, p.grad) for k, p in o.named_parameters()], [(k, p.grad) for k, p in n.named_parameters()])
+    bad = [r for r in table if r[0] > 3e-2]
+    assert not bad, bad[:8]
+
+
+def test_stale_arena_is_detected(cuda_lib):
+    """the generation guard: a node whose arena was overwritten raises instead of returning wrong gradients"""
+    from multimodal_sc_b200.model import SemComPolicy
+    n = SemComPolicy(SPEC, seed=1)
+    cam, bev = _inputs(2, seed=6)
+    l, v, aux = n(cam, bev, 10.0, channel="awgn", seed=1)
+    assert all(not pool for pool in n.engine._free_arenas.values())        # the arena is leased to the node
+    fn = l.grad_fn
+    while fn is not None and not hasattr(fn, "A"):
+        fn = fn.next_functions[0][0] if fn.next_functions else None
+    assert fn is not None
+    with torch.no_grad():
+        n.engine.forward(cam, bev, 10.0, "awgn", 2, None, None, 0, train=False, arena=fn.A)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        l.sum().backward()
+
+
+@pytest.mark.parametrize("spec_kw", [{"snr_cond": True}, {"gelu": "erf"}, {"quant_bits": 4},
+                                     {"snr_cond": True, "gelu": "erf", "quant_bits": 6}])
+def test_round2_options_match_oracle(cuda_lib, spec_kw):
+    """SNR-conditioned encoders, exact (erf) GELU, b-bit quantised symbols — forward and every
+    gradient tensor against the oracle at B = 64, per-sample SNRs, Rayleigh channel."""
+    import dataclasses
+    spec = dataclasses.replace(SPEC, **spec_kw)
+    o, n = _pair(spec)
+    B = 64
+    cam, bev = _inputs(B, seed=8)
+    snr = torch.linspace(-5, 20, B).cuda()
+    g = torch.Generator().manual_seed(2)
+    gl, gv = torch.randn(B, spec.n_actions, generator=g).cuda() / B, torch.randn(B, generator=g).cuda() / B
+
+    def run(model):
+        l, v, aux = model(cam, bev, snr, channel="rayleigh", seed=21)
+        ((l * gl).sum() + (v * gv).sum() + aux["l_sem"]).backward()
+        return l.detach(), v.detach(), {k: a.detach() for k, a in aux.items()}
+
+    lo, vo, ao = run(o)
+    ln, vn, an = run(n)
+    assert _rel(ln, lo) < 2e-2 and _rel(vn, vo) < 2e-2, (_rel(ln, lo), _rel(vn, vo))
+    assert abs(float(an["l_sem"]) - float(ao["l_sem"])) < 2e-2 * float(ao["l_sem"])
+    if spec.quant_bits:
+        # quantised symbols: a symbol within bf16 rounding of a decision boundary may land in the neighbouring cell
+        step = 2 * spec.quant_clip / 2 ** spec.quant_bits
+        d = (an["y"] - ao["y"]).abs()
+        assert float((d > 0.5 * step).float().mean()) < 2e-3
+    else:
+        assert _rel(an["y"], ao["y"]) < 2e-2
+    table = _grad_table([(k, p.grad) for k, p in o.named_parameters()], [(k, p.grad) for k, p in n.named_parameters()])
+    tol = 5e-2 if spec.quant_bits else 2e-2           # a flipped quantiser cell moves the gradient of its symbol
+    bad = [r for r in table if r[0] > tol]
+    assert not bad, bad[:8]
+    if spec.snr_cond:
+        for enc in ("cam_enc", "bev_enc"):
+            assert float(dict(n.named_parameters())[f"{enc}.snr.w"].grad.abs().max()) > 0

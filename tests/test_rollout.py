@@ -123,3 +123,45 @@ def test_collect_then_update_end_to_end(cuda_lib):
     st = ag.update(ro)
     assert all(torch.isfinite(torch.tensor(v)) for v in st.values()), st
     assert 0.0 <= st["clipfrac"] <= 1.0 and st["ent"] > 0.0
+
+
+@pytest.mark.gpu
+def test_graphed_step_counters_noise_and_key(cuda_lib):
+    """graph=True: (1) replays advance the device-side counter, so the SAME minibatch sees fresh channel noise every
+    step (statistics differ between replays) and Adam's moments / bias correction follow the eager run on identical
+    inputs within the summation-order yardstick; (2) everything a capture bakes in is part of the graph key: changing
+    agent.snr_db / agent.channel records a new graph instead of replaying the old scalars."""
+    from multimodal_sc_b200 import synthetic
+    from multimodal_sc_b200.model import SemComPolicy
+    from multimodal_sc_b200.ppo import PPOAgent
+    B = 32
+    m = synthetic.minibatch(SPEC, B, seed=3, device="cuda")
+    args = (m["cam"], m["bev"], m["actions"], m["logp_old"], m["adv"], None, m["ret"])
+
+    def run(graph, steps=4):
+        pol = SemComPolicy(SPEC, seed=0)
+        pol.engine.deterministic = True                      # ordered (split-free) weight gradients
+        ag = PPOAgent(pol, SPEC, minibatch=B, seed=5, snr_db=0.0)
+        st = [ag.minibatch_step(*args, graph=graph) for _ in range(steps)]
+        return ag, pol, st
+
+    ag_e, pol_e, st_e = run(False)
+    ag_g, pol_g, st_g = run(True)
+    assert ag_g.step_count == 4 and int(ag_g.dev_step) == 4 and len(ag_g._graphs) == 1
+    # fresh noise per replay: at 0 dB the semantic distortion of the same minibatch moves from step to step
+    assert len({round(s["l_sem"], 7) for s in st_g}) == 4
+    for k in ("pi", "v", "ent", "l_sem"):
+        for i in range(4):
+            assert abs(st_e[i][k] - st_g[i][k]) <= 2e-2 * max(abs(st_e[i][k]), 0.05), (i, k, st_e[i][k], st_g[i][k])
+    # Adam state after 4 steps: second moments are sums of squares (insensitive to sign flips)
+    ve, vg = pol_e.flat.v, pol_g.flat.v
+    assert float((ve - vg).abs().max()) <= 2e-2 * float(ve.abs().max())
+    assert float((pol_e.flat.p32 - pol_g.flat.p32).abs().max()) <= 2 * 4 * SPEC.lr + 1e-6
+    # the key: another SNR / channel kind is another graph, and its first use is an eager step with the new value
+    ag_g.snr_db = 20.0
+    s20 = ag_g.minibatch_step(*args, graph=True)
+    assert len(ag_g._graphs) == 2
+    ag_g.channel = "rayleigh"
+    ag_g.minibatch_step(*args, graph=True)
+    assert len(ag_g._graphs) == 3 and ag_g.step_count == 6 and int(ag_g.dev_step) == 6
+    assert s20["l_sem"] < min(s["l_sem"] for s in st_g[1:])   # 20 dB distorts less than 0 dB on the same weights' trajectory
