@@ -13,6 +13,14 @@ all-reduce of the flat fp32 gradient bucket per step: weak scaling.
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM, `e2e` = the same
 step driven through the public API (PPOAgent.minibatch_step) from pinned HOST buffers with the
 H2D copy of every step's inputs and the D2H read of its statistics inside the timed region.
+
+Beside the contract keys the line carries: `roofline` (dominant kernel family, both views, per-kernel
+table with algorithmic GB/s for every kernel of the step), `cpu_baseline`, `update_e2e` (the WHOLE
+PPOAgent.update() from a pinned host rollout: H2D of the rollout, fused GAE scan + advantage
+normalisation, host permutation, minibatch gather fused into the first kernels, every minibatch step,
+D2H of the statistics), `allreduce_ms` (N > 1: device time of the gradient all-reduce, the scaling
+limiter) and `secondary` (BASELINE.json's other configs measured in the same run: cfg2 forward eager +
+CUDA graph, cfg4 Rayleigh sweep per SNR, cfg1 the oracle's own 1-env CPU update).
 """
 from __future__ import annotations
 
@@ -84,6 +92,25 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle on the host cores
 # --------------------------------------------------------------------------------------------------
+def cpu_oracle_cfg1():
+    """cfg1 (BASELINE.json configs[0]): the oracle's CPU entry point at its smallest config — 1 environment, T = 128,
+    one update() (GAE + 1 epoch over one minibatch of 128), fp32.  -> dict"""
+    import torch
+    from multimodal_sc_b200.spec import SpecV0
+    from multimodal_sc_b200 import synthetic
+    from oracle.model import SemComPolicy
+    from oracle.ppo import PPOAgent
+    torch.set_num_threads(os.cpu_count() or 1)
+    sp = SpecV0()
+    ag = PPOAgent(SemComPolicy(sp), sp, minibatch=128, epochs=1, snr_db=SNR_DB, channel="awgn", seed=1234)
+    ro = synthetic.rollout(sp, sp.rollout_t, 1, seed=0)
+    t0 = time.perf_counter()
+    st = ag.update(ro)
+    dt = time.perf_counter() - t0
+    return {"workload": "cfg1: oracle update(), 1 env x T=128, minibatch 128, fp32, host CPU", "ms": dt * 1e3,
+            "samples_per_s": sp.rollout_t / dt, "cores": torch.get_num_threads(), "total_loss": st["total"]}
+
+
 def cpu_oracle_rate(steps: int, warmup: int, batch: int):
     """oracle PPO minibatch steps (fwd + loss + bwd + Adam), fp32, all host threads. -> (samples/s, ms/step, cores)"""
     import torch
@@ -111,8 +138,8 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 64
-    steps = max(1, min(a.steps, 8))
+    batch = 256
+    steps = max(1, min(a.steps, 20))
     val, ms, cores = cpu_oracle_rate(steps, max(1, min(a.warmup, 2)), batch)
     sample = f"{steps} oracle PPO minibatch steps of {batch} samples (same shapes/seeds as the workload, fp32 eager PyTorch)"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
@@ -123,6 +150,72 @@ def run_reference(a):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# secondary configs (BASELINE.json configs[0], [1], [3]) — measured in the same run, for the record
+# --------------------------------------------------------------------------------------------------
+def secondary_configs(pol, sp, torch, synthetic, _lib, ops, cpu_leg=True):
+    eng = pol.engine
+    out = {}
+
+    def timeit(fn, n=30, warm=5):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    fwd_flops = None
+    from multimodal_sc_b200.spec import fwd_flops_per_sample
+    fwd_flops = fwd_flops_per_sample(sp)
+    peaks = _peaks()
+    # cfg2: forward only, B = 256, AWGN 10 dB — eager and as one CUDA-graph replay (device-side seed counter)
+    B = 256
+    mb = synthetic.minibatch(sp, B, seed=5, device=pol.device, obs_dtype=torch.bfloat16)
+    l0 = _lib.launch_count()
+    ms = timeit(lambda: eng.forward(mb["cam"], mb["bev"], SNR_DB, "awgn", 77, None, None, 0, train=False))
+    c2 = {"workload": "cfg2: camera + LiDAR-BEV encoders -> AWGN 10 dB -> fusion decoder + heads forward, batch 256, bf16",
+          "eager_ms": ms, "eager_samples_per_s": B / ms * 1e3, "launches_per_forward": (_lib.launch_count() - l0) // 35}
+    ctr = torch.zeros(1, device=pol.device, dtype=torch.int64)
+
+    def body():
+        eng.forward(mb["cam"], mb["bev"], SNR_DB, "awgn", 77, None, None, 0, train=False, seed_dev=ctr)
+        ctr.add_(1)
+
+    body()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        body()
+    ms = timeit(g.replay)
+    c2.update({"graph_ms": ms, "graph_samples_per_s": B / ms * 1e3,
+               "graph_frac_of_fwd_roofline": (B / ms * 1e3) * fwd_flops / (peaks["tf_sustained"] * 1e12)})
+    out["cfg2"] = c2
+    # cfg4: Rayleigh block fading, B = 1024, SNR sweep, forward + L_sem + backward of the semantic loss
+    B = 1024
+    mb = synthetic.minibatch(sp, B, seed=6, device=pol.device, obs_dtype=torch.bfloat16)
+    lsem = torch.zeros(1, device=pol.device)
+    dho = torch.zeros(B, sp.n_actions + 1, device=pol.device)
+    per = {}
+    for snr in (-5.0, 0.0, 5.0, 10.0, 15.0, 20.0):
+        def step():
+            ops.step_begin(pol.flat.g32, lsem, None)
+            ho, A = eng.forward(mb["cam"], mb["bev"], snr, "rayleigh", 1234, None, None, 0, train=True)
+            eng.l_sem(A, B, lsem, grad_coef=1.0)
+            eng.backward(A, B, dho, None, "rayleigh", snr, 1234, None, 0)
+        ms = timeit(step, n=10, warm=3)
+        per[str(snr)] = {"ms": ms, "samples_per_s": B / ms * 1e3, "l_sem": float(lsem)}
+    out["cfg4"] = {"workload": "cfg4: Rayleigh fading, SNR sweep -5..20 dB, semantic-distortion loss forward + backward, "
+                               "batch 1024, bf16 (random-init weights: l_sem is not a trained value)", "per_snr_db": per}
+    if cpu_leg:
+        out["cfg1"] = cpu_oracle_cfg1()
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -189,17 +282,24 @@ def run_native(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, with_last=False):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step = {}
+
+    def timed(fn, steps, with_last=False, tag=None):
+        """EXACTLY `steps` steps between barrier + synchronize on both sides, CUDA events, max over ranks; an event after
+        every step additionally gives the per-step median."""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         barrier()
-        e0.record()
+        evs[0].record()
         for i in range(steps):
             fn(i, i == steps - 1) if with_last else fn(i)
-        e1.record()
+            evs[i + 1].record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        ms = torch.tensor([evs[0].elapsed_time(evs[-1])], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if tag:
+            d = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+            per_step[tag] = {"median": d[len(d) // 2], "min": d[0], "max": d[-1]}
         return float(ms)
 
     for i in range(max(a.warmup, 3)):
@@ -208,15 +308,16 @@ def run_native(a):
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    ms_total = timed(step_dev, a.steps)
+    ms_total = timed(step_dev, a.steps, tag="value")
     launches = _lib.launch_count() - l0
+    ar_ms = ag.allreduce_ms() if world > 1 else None          # device time of the last step's gradient all-reduce
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * a.steps / (ms_total * 1e-3)
 
     # end-to-end: host buffers, H2D + D2H inside the timed region
     for i in range(2):
         step_host(i, i == 1)
-    ms_e2e = timed(step_host, a.steps, with_last=True)
+    ms_e2e = timed(step_host, a.steps, with_last=True, tag="e2e")
     e2e_val = world * B * a.steps / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
@@ -225,6 +326,28 @@ def run_native(a):
     with ops.profile() as prof:
         step_dev(0)
     summ = prof.summary()
+
+    # whole update() from a pinned host rollout (GAE, permutation, fused gather, every minibatch step); at N > 1 each rank
+    # owns N_ENVS whole environments and update() slices the global permutation by rank (ragged local minibatches)
+    upd = None
+    if not a.no_update:
+        T_ro, n_env = sp.rollout_t, max(2 * B // sp.rollout_t, 1)
+        ro = synthetic.rollout(sp, T_ro, n_env, seed=300 + rank)
+        ro["cam"], ro["bev"] = ro["cam"].bfloat16(), ro["bev"].bfloat16()
+        ro = {k: v.pin_memory() for k, v in ro.items()}
+        agu = PPOAgent(pol, sp, minibatch=B * world, epochs=1, snr_db=SNR_DB, channel="awgn", seed=4321,
+                       process_group=None)
+        agu.update(ro)                                          # warm-up (allocates the capacity arena on N > 1)
+        reps = 3
+        ms_u = timed(lambda i: agu.update(ro), reps)
+        n_samples = T_ro * n_env * world
+        upd = {"value": n_samples * reps / (ms_u * 1e-3), "unit": UNIT, "ms_per_update": ms_u / reps,
+               "rollout": f"T={T_ro} x N={n_env} envs per GPU (bf16 observations, pinned host)",
+               "minibatch_steps_per_update": (n_samples // (B * world)),
+               "h2d_bytes_per_update": sum(v.numel() * v.element_size() for v in ro.values()),
+               "includes": "H2D of the rollout, sc_gae + sc_adv_normalize, host randperm, gather fused into sc_patchify_bf16 / "
+                           "sc_ppo_loss, all minibatch steps, D2H of the statistics"}
+        del ro
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -239,10 +362,16 @@ def run_native(a):
     step_ms_prof = sum(v["ms"] for v in summ.values())
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     g_by = sum(v["bytes"] for v in gemm.values())
-    traffic = None                  # DRAM bytes per launch from the committed ncu capture of this same command
-    tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
-    if os.path.exists(tpath) and B == MB_PER_GPU:
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
+    # DRAM bytes per launch: NOT measured by this run (it needs ncu replay); taken from the committed `ncu --set full`
+    # capture of this same command, whose file records the commit it was taken at (`traffic_source`)
+    traffic, traffic_src = None, None
+    for name in ("r2_gemm_dram_traffic.json", "r1_gemm_dram_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath) and B == MB_PER_GPU:
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch_avg")
+            traffic_src = f"profiles/{name} (ncu capture at commit {tj.get('commit', 'unrecorded')})"
+            break
     # which roof binds: arithmetic intensity of the launches (algorithmic FLOP / algorithmic bytes, each operand read
     # once, each result written once) against the ridge point of the measured peaks.  The D = 256 GEMMs of this model
     # sit below the ridge (AI ~150 < ~214 FLOP/B), so the attainable rate is AI x HBM bandwidth, not the tensor peak;
@@ -257,7 +386,7 @@ def run_native(a):
     main = hbm_view if bound == "hbm" else tensor_view
     roof = {"bound": bound, "kernel": "gemm_tcgen05_kernel (all operand-major variants)",
             "achieved": main["achieved"], "peak": main["peak"], "unit": main["unit"], "frac": main["frac"],
-            "traffic": traffic, "algorithmic_bytes_per_launch": g_by / max(g_n, 1),
+            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": g_by / max(g_n, 1),
             "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
             "tensor_view": tensor_view, "hbm_view": hbm_view,
             "peak_source": peaks["source"] + "; tensor view uses the sustained bf16 figure (kernels timed inside a long step)",
@@ -268,15 +397,20 @@ def run_native(a):
                               "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in sorted(summ.items())}}
     flops_step = 3.0 * fwd_flops_per_sample(sp) * B
     cpu = None
+    secondary = None
     if world == 1 and not a.no_cpu:
-        v, ms, cores = cpu_oracle_rate(2, 1, 32)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "2 oracle PPO minibatch steps of 32 samples (fp32 eager PyTorch, all host threads)"}
+        v, ms, cores = cpu_oracle_rate(8, 2, 256)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+               "sample": "8 timed (+2 warm-up) oracle PPO minibatch steps of 256 samples (fp32 eager PyTorch, all host threads)"}
+    if world == 1 and not a.no_secondary:
+        secondary = secondary_configs(pol, sp, torch, synthetic, _lib, ops, cpu_leg=not a.no_cpu)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "cfg3/cfg5: PPO minibatch step (fwd + fused loss + bwd + Adam), 4096 samples per GPU, "
-                                   "AWGN 10 dB; global batch = 4096 x n_gpus, DP all-reduce of the flat fp32 grads",
+            "ms_per_step_median": per_step["value"]["median"], "ms_per_step_minmax": [per_step["value"]["min"], per_step["value"]["max"]],
+            "config": {"workload": f"cfg3/cfg5: PPO minibatch step (fwd + fused loss + bwd + Adam), {B} samples per GPU, "
+                                   f"AWGN 10 dB; global batch = {B} x {world} GPUs (weak scaling; 8 GPUs x 4096 = cfg5's 32768), "
+                                   "DP all-reduce of the flat fp32 grads",
                        "minibatch_per_gpu": B, "global_batch": B * world, "snr_db": SNR_DB, "channel": "awgn",
                        "params": pol.flat.n_params(), "parallelism": f"dp{world}",
                        "observations": "bf16 (fp32 U[0,1) cast once on the host before timing)",
@@ -287,6 +421,16 @@ def run_native(a):
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 32},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+    line["e2e"]["ms_per_step_median"] = per_step["e2e"]["median"]
+    if ar_ms is not None:
+        line["allreduce_ms"] = ar_ms
+        line["allreduce"] = {"ms": ar_ms, "bytes": pol.flat.numel * 4, "share_of_step": ar_ms / (ms_total / a.steps),
+                             "what": "CUDA events around the NCCL all-reduce of the flat fp32 gradient bucket in the last timed "
+                                     "step on rank 0 (includes waiting for the slowest rank's backward)"}
+    if upd:
+        line["update_e2e"] = upd
+    if secondary:
+        line["secondary"] = secondary
     if cpu:
         line["cpu_baseline"] = cpu
     if a.debug_set:
@@ -301,11 +445,13 @@ def run_native(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)      # >= 20 warm-up, >= 100 timed iterations
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--minibatch", type=int, default=MB_PER_GPU)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg1 / cfg2 / cfg4 measurements")
+    ap.add_argument("--no-update", action="store_true", help="skip the update_e2e measurement")
     ap.add_argument("--debug-set", action="append", default=[], metavar="KEY=INT",
                     help="A/B switch forwarded to sc_debug_set (e.g. nwg=1 slots=2); recorded in config.debug")
     a = ap.parse_args()

@@ -375,6 +375,104 @@ pnorm_channel_fwd_warp_kernel(const ChanArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// The production shape (k = 1024 reals per row, in-kernel noise, continuous symbols) as a compile-time specialisation:
+// the channel kind is a template parameter (no branches in the symbol loop), all 8 float4 of a lane are live (no
+// predicates), the ten Philox round keys are hoisted out of the row loop, and the fading channel is applied in the
+// folded form  y = (|h|^2 s + sigma conj(h) n) / (|h|^2 + sigma^2)  (three operations per real symbol).
+// ncu (round 1) had the generic kernel issue-bound at 64 thread-instructions per symbol; this one needs ~26.
+// ------------------------------------------------------------------------------------------
+struct PhiloxKeys {
+  uint32_t k0[10], k1[10];
+};
+__device__ __forceinline__ PhiloxKeys philox_keys(uint32_t k0, uint32_t k1) {
+  PhiloxKeys ks;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    ks.k0[r] = k0 + static_cast<uint32_t>(r) * PHILOX_W0;
+    ks.k1[r] = k1 + static_cast<uint32_t>(r) * PHILOX_W1;
+  }
+  return ks;
+}
+__device__ __forceinline__ uint4 philox4x32_10_keys(uint4 c, const PhiloxKeys& ks) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(PHILOX_M0) * c.x;
+    const uint64_t p1 = static_cast<uint64_t>(PHILOX_M1) * c.z;
+    c = make_uint4(static_cast<uint32_t>(p1 >> 32) ^ c.y ^ ks.k0[r], static_cast<uint32_t>(p1),
+                   static_cast<uint32_t>(p0 >> 32) ^ c.w ^ ks.k1[r], static_cast<uint32_t>(p0));
+  }
+  return c;
+}
+
+template <int KIND, bool kExact>
+__global__ void __launch_bounds__(kThreads)
+pnorm_channel_fwd_k1024_kernel(const ChanArgs a) {
+  pdl_sync();                                   // first statement: no global-memory access before it (common.cuh)
+  constexpr int NV = 8;                                      // 8 float4 per lane = 1024 reals per warp
+  const uint2 key = chan_key(a);
+  const PhiloxKeys ks = philox_keys(key.x, key.y);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < a.B * 2; row += nwarps) {
+    const int64_t b = row >> 1;
+    const int m = static_cast<int>(row & 1);
+    const float4* zr = reinterpret_cast<const float4*>(a.z + b * a.z_sb + m * a.z_sm) + lane;
+    float4 v[NV];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = zr[i * 32];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    ss = warp_sum(ss);
+    const float scale = rsqrtf(ss * (1.0f / 1024.0f) + a.eps);
+    if (lane == 0 && a.scale) a.scale[row] = scale;
+    const int64_t gb = global_sample(a, b);
+    // symbol gain and noise coefficients: AWGN y = s + sigma n; fading y = g s + (ar n_r + ai n_i, ar n_i - ai n_r)
+    float g = scale, ar = 0.f, ai = 0.f;
+    if (KIND != SC_CH_NONE) {
+      const float sigma = sigma_of(a.snr_db, a.snr_db_scalar, b);
+      ar = sigma;
+      if (KIND >= SC_CH_RAYLEIGH) {
+        const float2 h = fading_of(a.fading, b, m, gb, key.x, key.y, KIND, a.rician_k);
+        const float h2 = h.x * h.x + h.y * h.y;
+        const float inv_den = 1.0f / (h2 + sigma * sigma);
+        g = scale * h2 * inv_den;
+        ar = sigma * h.x * inv_den;
+        ai = sigma * h.y * inv_den;
+      }
+    }
+    const uint64_t quad0 = (static_cast<uint64_t>(gb) * 2 + m) * 256u + static_cast<uint32_t>(lane);
+    float4* yf = a.y_f32 ? reinterpret_cast<float4*>(a.y_f32 + b * a.y_sb + m * a.y_sm) + lane : nullptr;
+    uint2* yb = a.y_bf16 ? reinterpret_cast<uint2*>(a.y_bf16 + b * a.y_sb + m * a.y_sm) + lane : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 o = make_float4(v[i].x * g, v[i].y * g, v[i].z * g, v[i].w * g);
+      if (KIND != SC_CH_NONE) {
+        const uint64_t quad = quad0 + static_cast<uint32_t>(i * 32);
+        const uint4 w = philox4x32_10_keys(make_uint4(static_cast<uint32_t>(quad), 0u, static_cast<uint32_t>(quad >> 32), 0u), ks);
+        float4 n;
+        if (kExact) {
+          box_muller(w.x, w.y, n.x, n.y);
+          box_muller(w.z, w.w, n.z, n.w);
+        } else {
+          box_muller_fast(w.x, w.y, n.x, n.y);
+          box_muller_fast(w.z, w.w, n.z, n.w);
+        }
+        if (KIND == SC_CH_AWGN) {
+          o = make_float4(fmaf(ar, n.x, o.x), fmaf(ar, n.y, o.y), fmaf(ar, n.z, o.z), fmaf(ar, n.w, o.w));
+        } else {
+          o = make_float4(fmaf(ai, n.y, fmaf(ar, n.x, o.x)), fmaf(-ai, n.x, fmaf(ar, n.y, o.y)),
+                          fmaf(ai, n.w, fmaf(ar, n.z, o.z)), fmaf(-ai, n.z, fmaf(ar, n.w, o.w)));
+        }
+      }
+      if (yf) yf[i * 32] = o;
+      if (yb) yb[i * 32] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(kThreads)
 pnorm_channel_bwd_warp_kernel(const ChanBwdArgs a) {
@@ -440,6 +538,7 @@ int check_common(const char* nm, int64_t B, int k, int kind, int64_t sb, int64_t
 extern "C" {
 
 int g_chan_exact = 0;          // sc_debug_set("chan_exact", 1): accurate logf / sincospif Box-Muller (A/B yardstick)
+int g_chan_generic = 0;        // sc_debug_set("chan_generic", 1): the run-time-kind kernel also for the production shape
 
 int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f32, void* y_bf16, int64_t y_sb,
                          int64_t y_sm, float* scale, int64_t B, int k, int kind, float rician_k,
@@ -469,7 +568,22 @@ int sc_pnorm_channel_fwd(const float* z, int64_t z_sb, int64_t z_sm, float* y_f3
   const int64_t rows = B * 2;
   const bool exact = g_chan_exact != 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (k <= 1024) {                               // warp per row, 8 rows per CTA
+  if (k == 1024 && !noise && !a.qlevels && g_chan_generic == 0) {        // the production shape: specialised kernels
+    const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 8;
+    const dim3 grid((int)(blocks < cap ? blocks : cap));
+#define SC_CHAN_LAUNCH(KIND)                                                                                         \
+  do {                                                                                                               \
+    if (exact) sc_launch_kernel(pnorm_channel_fwd_k1024_kernel<KIND, true>, grid, dim3(kThreads), 0, st, a);         \
+    else sc_launch_kernel(pnorm_channel_fwd_k1024_kernel<KIND, false>, grid, dim3(kThreads), 0, st, a);              \
+  } while (0)
+    switch (kind) {
+      case SC_CH_NONE: SC_CHAN_LAUNCH(SC_CH_NONE); break;
+      case SC_CH_AWGN: SC_CHAN_LAUNCH(SC_CH_AWGN); break;
+      case SC_CH_RAYLEIGH: SC_CHAN_LAUNCH(SC_CH_RAYLEIGH); break;
+      default: SC_CHAN_LAUNCH(SC_CH_RICIAN); break;
+    }
+#undef SC_CHAN_LAUNCH
+  } else if (k <= 1024) {                        // warp per row, 8 rows per CTA
     const int64_t blocks = (rows + 7) / 8, cap = (int64_t)sc_num_sms() * 8;
     const dim3 grid((int)(blocks < cap ? blocks : cap));
     if (exact) sc_launch_kernel(pnorm_channel_fwd_warp_kernel<8, true>, grid, dim3(kThreads), 0, st, a);

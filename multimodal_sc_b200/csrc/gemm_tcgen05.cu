@@ -1347,6 +1347,7 @@ void sc_mlp_debug_set(int v);
 void sc_alternate_set(int v);
 void sc_tmap_cache_set(int on);
 extern "C" int g_chan_exact;
+extern "C" int g_chan_generic;
 
 extern "C" int sc_debug_set(const char* key, int64_t value) {
   if (!key) return SC_E_SHAPE;
@@ -1356,6 +1357,7 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   if (!strcmp(key, "alternate")) { sc_alternate_set((int)value); return SC_OK; }
   if (!strcmp(key, "tmap_cache")) { sc_tmap_cache_set((int)value); return SC_OK; }
   if (!strcmp(key, "chan_exact")) { g_chan_exact = (int)value; return SC_OK; }
+  if (!strcmp(key, "chan_generic")) { g_chan_generic = (int)value; return SC_OK; }
   if (!strcmp(key, "a_lbo")) g_dbg.a_lbo = value;
   else if (!strcmp(key, "a_sbo")) g_dbg.a_sbo = value;
   else if (!strcmp(key, "a_kstep")) g_dbg.a_kstep = value;

@@ -81,6 +81,7 @@ class FlatParams:
             self.offsets[name] = (off, n)
             off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = off
+        self._views = {}
         self.p32 = torch.zeros(off, device=device, dtype=F32)
         self.p16 = torch.zeros(off, device=device, dtype=BF16)
         self.g32 = torch.zeros(off, device=device, dtype=F32)
@@ -91,9 +92,21 @@ class FlatParams:
         off, n = self.offsets[name]
         return buf[off:off + n].view(self.shapes[name])
 
-    def w32(self, name): return self._view(self.p32, name)
-    def w16(self, name): return self._view(self.p16, name)
-    def g(self, name): return self._view(self.g32, name)
+    # The views are built once per (bucket, name): an eager small-batch forward makes ~150 of these lookups, and two
+    # tensor ops per lookup cost more host time than the kernels take on the device (cfg2, B = 256).  The cache is
+    # keyed by the bucket's storage, so swapping a bucket (the autograd facade's scratch gradient bucket) is safe.
+    def _cached(self, key, buf, name):
+        c = self._views.get(key)
+        if c is None or c[0] != buf.data_ptr():
+            c = self._views[key] = (buf.data_ptr(), {})
+        v = c[1].get(name)
+        if v is None:
+            v = c[1][name] = self._view(buf, name)
+        return v
+
+    def w32(self, name): return self._cached("p32", self.p32, name)
+    def w16(self, name): return self._cached("p16", self.p16, name)
+    def g(self, name): return self._cached("g32", self.g32, name)
 
     def sync_shadow(self):
         ops.cast_f32_bf16(self.p32, self.p16)

@@ -38,6 +38,38 @@ with torch.cuda.graph(g):
 ms = timeit(g.replay)
 out["cfg2_fwd_b256_awgn10_cuda_graph"] = {"ms": ms, "samples_per_s": B / ms * 1e3}
 
+# the same two measurements with programmatic dependent launch (kernel prologues overlap the predecessor's tail)
+from multimodal_sc_b200 import ops
+ops.debug_set("pdl", 1)
+B = 256
+ms = timeit(lambda: eng.forward(mb["cam"], mb["bev"], 10.0, "awgn", 77, None, None, 0, train=False))
+out["cfg2_fwd_b256_awgn10_pdl"] = {"ms": ms, "samples_per_s": B / ms * 1e3}
+g2 = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g2):
+    body()
+ms = timeit(g2.replay)
+out["cfg2_fwd_b256_awgn10_cuda_graph_pdl"] = {"ms": ms, "samples_per_s": B / ms * 1e3}
+for cs in (1, 2):
+    ops.debug_set("col_split", cs)
+    gg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gg):
+        body()
+    ms = timeit(gg.replay)
+    out[f"cfg2_fwd_b256_awgn10_cuda_graph_pdl_colsplit{cs}"] = {"ms": ms, "samples_per_s": B / ms * 1e3}
+ops.debug_set("col_split", 0)
+pol.engine.fused_mlp = False
+gg = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gg):
+    body()
+ms = timeit(gg.replay)
+out["cfg2_fwd_b256_awgn10_cuda_graph_pdl_two_gemm_mlp"] = {"ms": ms, "samples_per_s": B / ms * 1e3}
+pol.engine.fused_mlp = True
+ops.debug_set("pdl", 0)
+ops.debug_set("tmap_cache", 0)
+ms = timeit(lambda: eng.forward(mb["cam"], mb["bev"], 10.0, "awgn", 77, None, None, 0, train=False))
+out["cfg2_fwd_b256_awgn10_no_tmap_cache"] = {"ms": ms, "samples_per_s": B / ms * 1e3}
+ops.debug_set("tmap_cache", 1)
+
 # cfg4: Rayleigh sweep, B = 1024, fwd + L_sem + bwd of the semantic loss only
 B = 1024
 mb = synthetic.minibatch(sp, B, seed=6, device="cuda", obs_dtype=torch.bfloat16)
