@@ -257,8 +257,10 @@ def run_native(a):
     def step_dev(i, sync_stats=False):
         m = devb[i & 1]
         return ag.minibatch_step(m["cam"], m["bev"], m["actions"], m["logp_old"], m["adv"], None, m["ret"],
-                                 sample_offset=rank * B, sync_stats=sync_stats)
+                                 sample_offset=rank * B, sync_stats=sync_stats, graph=GRAPH)
 
+    # --graph: the step as CUDA-graph replays (one graph per persistent input buffer set, no copies); single GPU only
+    GRAPH = "inplace" if (a.graph and world == 1) else False
     feeder = HostMinibatchFeeder(dev)
     pending = {}
 
@@ -273,7 +275,7 @@ def run_native(a):
             pending[i + 1] = feeder.submit(host[(i + 1) & 1])
         torch.cuda.current_stream().wait_event(ready)
         st = ag.minibatch_step(m["cam"], m["bev"], m["actions"], m["logp_old"], m["adv"], None, m["ret"],
-                               sample_offset=rank * B, sync_stats=True)          # D2H read of the step's stats
+                               sample_offset=rank * B, sync_stats=True, graph=GRAPH)   # D2H read of the step's stats
         feeder.release(slot)
         return st
 
@@ -323,6 +325,7 @@ def run_native(a):
 
     # roofline pass: one extra step with every launch bracketed by CUDA events on the launching stream
     barrier()
+    GRAPH = False                                   # per-launch events need the eager schedule
     with ops.profile() as prof:
         step_dev(0)
     summ = prof.summary()
@@ -452,6 +455,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg1 / cfg2 / cfg4 measurements")
     ap.add_argument("--no-update", action="store_true", help="skip the update_e2e measurement")
+    ap.add_argument("--graph", action="store_true", help="A/B: replay the step as a CUDA graph (single GPU)")
     ap.add_argument("--debug-set", action="append", default=[], metavar="KEY=INT",
                     help="A/B switch forwarded to sc_debug_set (e.g. nwg=1 slots=2); recorded in config.debug")
     a = ap.parse_args()

@@ -30,6 +30,8 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("SC_MLP_ACCT", "0") not in ("", "0"):        # per-role wait accounting in the fused MLP kernel (debug builds)
+    NVCC_FLAGS.append("-DSC_MLP_ACCT")
 if os.environ.get("SC_GEMM_ACCT", "0") not in ("", "0"):       # per-role wait accounting in the GEMM kernel (debug builds)
     NVCC_FLAGS.append("-DSC_GEMM_ACCT")
 

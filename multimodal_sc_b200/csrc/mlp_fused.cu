@@ -60,6 +60,16 @@ struct MlpParams {
   int dbg;                   // sc_debug_set("mlp_dbg", bits): 1 / 2 = L2 prefetch variants (negative), 4 = no weight multicast
 };
 
+// per-role wait accounting (debug builds: SC_MLP_ACCT=1 python -m multimodal_sc_b200.build --force, then
+// sc_debug_set("mlp_dbg", 8)): CTA 0 prints, per role, its total cycles and the cycles inside each barrier wait
+#ifdef SC_MLP_ACCT
+#define MLP_WAIT(bar, par, ctr) do { const long long _t = clock64(); mbar_wait(bar, par); (ctr) += clock64() - _t; } while (0)
+constexpr bool kMlpAcct = true;
+#else
+#define MLP_WAIT(bar, par, ctr) mbar_wait(bar, par)
+constexpr bool kMlpAcct = false;
+#endif
+
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -211,8 +221,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       uint32_t ready = mbar_test(smem_u32(&w_empty[0]), 1u);
+      long long a_w = 0;
+      const long long a_t0 = clock64();
+      const bool acct = kMlpAcct && (p.dbg & 8) && blockIdx.x == 0;
       auto next_stage = [&]() -> uint32_t {
-        if (!ready) mbar_wait(smem_u32(&w_empty[stage]), phase ^ 1u);
+        if (!ready) MLP_WAIT(smem_u32(&w_empty[stage]), phase ^ 1u, a_w);
         const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
         const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
         ready = mbar_test(smem_u32(&w_empty[nstage]), nphase ^ 1u);
@@ -276,15 +289,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         load_g2(NC - 1);
       }
+      if (acct && lane == 0) printf("mlp acct: weight producer total %lld clk, waiting for a free stage %lld\n", clock64() - a_t0, a_w);
     }
   } else if (warp == 3) {
     // ===================== activation producer =====================
     if (lane == 0) {
       uint32_t t_par = 0;
       uint32_t nuse[2] = {0u, 0u};
+      long long a_x = 0, a_h = 0;
+      const long long a_t0 = clock64();
+      const bool acct = kMlpAcct && (p.dbg & 8) && blockIdx.x == 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, t_par ^= 1u) {
         const int row0 = (p.reverse ? p.tiles - 1 - tile : tile) * BM;
-        mbar_wait(smem_u32(&x_empty), t_par ^ 1u);
+        MLP_WAIT(smem_u32(&x_empty), t_par ^ 1u, a_x);
         mbar_arrive_expect_tx(smem_u32(&x_full), XA_BYTES);
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) tma_load_2d(xa + kb * KB_BYTES, &tmX, smem_u32(&x_full), kb * 64, row0);
@@ -317,7 +334,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 tma_prefetch_l2_2d(&tmHin, (jn % NC) * HC + 64, prow0);
               }
             }
-            mbar_wait(smem_u32(&h_empty[b]), (nuse[b] & 1u) ^ 1u);
+            MLP_WAIT(smem_u32(&h_empty[b]), (nuse[b] & 1u) ^ 1u, a_h);
             ++nuse[b];
             mbar_arrive_expect_tx(smem_u32(&hin_full[b]), HB_BYTES);
             tma_load_2d(hb(b), &tmHin, smem_u32(&hin_full[b]), j * HC, row0);
@@ -325,6 +342,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
       }
+      if (acct) printf("mlp acct: activation producer total %lld clk, waiting x_empty %lld, h_empty (buffer free) %lld\n", clock64() - a_t0, a_x, a_h);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -349,9 +367,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       uint32_t ready = mbar_test(smem_u32(&w_full[0]), 0u);
       int nstage = 0;
       uint32_t nphase = 0;
+      long long a_w = 0, a_a1 = 0, a_hf = 0, a_a2 = 0, a_x = 0;
+      const long long a_t0 = clock64();
+      const bool acct = kMlpAcct && (p.dbg & 8) && blockIdx.x == 0;
       // wait for the current weight stage (it was tested one stage ahead); note which stage comes next
       auto acquire_stage = [&]() -> uint32_t {
-        if (!ready) mbar_wait(smem_u32(&w_full[stage]), phase);
+        if (!ready) MLP_WAIT(smem_u32(&w_full[stage]), phase, a_w);
         nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
         nphase = (stage + 1 == STAGES) ? (phase ^ 1u) : phase;
         return ring + stage * STAGE_BYTES;
@@ -359,7 +380,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto advance = [&]() { stage = nstage; phase = nphase; };
       auto gemm1 = [&](int j) {
         const int b = j & 1;
-        mbar_wait(smem_u32(&acc1_empty[b]), (n1[b] & 1u) ^ 1u);
+        MLP_WAIT(smem_u32(&acc1_empty[b]), (n1[b] & 1u) ^ 1u, a_a1);
         ++n1[b];
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(b * HC);
@@ -387,9 +408,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       };
       auto gemm2 = [&](int j) {
         const int b = j & 1;
-        mbar_wait(smem_u32(&h_full[b]), nh[b] & 1u);
+        MLP_WAIT(smem_u32(&h_full[b]), nh[b] & 1u, a_hf);
         ++nh[b];
-        if (j == 0) mbar_wait(smem_u32(&acc2_empty), t_par ^ 1u);      // previous tile's output drained
+        if (j == 0) MLP_WAIT(smem_u32(&acc2_empty), t_par ^ 1u, a_a2);      // previous tile's output drained
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ACC2_COL;
         for (int t = 0; t < 2; ++t) {
@@ -408,7 +429,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
       };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, t_par ^= 1u) {
-        mbar_wait(smem_u32(&x_full), t_par);
+        MLP_WAIT(smem_u32(&x_full), t_par, a_x);
         tc_fence_after();
         for (int j = 0; j < NC; ++j) {
           gemm1(j);
@@ -418,6 +439,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (elect_one_sync()) umma_commit(smem_u32(&acc2_full));
         __syncwarp();
       }
+      if (acct && lane == 0)
+        printf("mlp acct: mma total %lld clk, waiting weights %lld, acc1_empty %lld, h_full (chunk transformed) %lld, acc2_empty %lld, x_full %lld\n",
+               clock64() - a_t0, a_w, a_a1, a_hf, a_a2, a_x);
     }
   } else if (warp == 2) {
     // ===================== chunk storer =====================
@@ -425,21 +449,27 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // the buffer once the store has read it.  A thread of its own: the epilogue warpgroups never wait for a store.
     if (lane == 0) {
       uint32_t nuse[2] = {0u, 0u};
+      long long a_hf = 0, a_st = 0;
+      const long long a_t0 = clock64();
+      const bool acct = kMlpAcct && (p.dbg & 8) && blockIdx.x == 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
         for (int j = 0; j < NC; ++j) {
           const int b = j & 1;
-          mbar_wait(smem_u32(&h_full[b]), nuse[b] & 1u);     // all 128 rows written and fenced
+          MLP_WAIT(smem_u32(&h_full[b]), nuse[b] & 1u, a_hf);     // all 128 rows written and fenced
           ++nuse[b];
           if (p.store_h) {
+            const long long ts = kMlpAcct ? clock64() : 0;
             tma_store_2d(&tmH, hb(b), j * HC, (p.reverse ? p.tiles - 1 - tile : tile) * BM);
             tma_store_2d(&tmH, hb(b) + KB_BYTES, j * HC + 64, (p.reverse ? p.tiles - 1 - tile : tile) * BM);
             tma_store_commit();
             tma_store_wait_read<0>();
+            if (kMlpAcct) a_st += clock64() - ts;
           }
           mbar_arrive(smem_u32(&h_empty[b]));
         }
       }
       tma_store_wait_all();
+      if (acct) printf("mlp acct: chunk storer total %lld clk, waiting h_full %lld, store issue + read wait %lld\n", clock64() - a_t0, a_hf, a_st);
     }
   } else if (warp >= 4) {
     // ===================== epilogue warpgroups =====================
@@ -456,6 +486,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t bias2 = smem_base + OFF_BIAS2;
     uint32_t nuse = 0;                                       // chunks this warpgroup has processed
     uint32_t t_par = 0;
+    long long a_a1 = 0, a_hin = 0, a_a2 = 0, a_math = 0, a_out = 0;
+    const long long a_t0 = clock64();
+    const bool acct = kMlpAcct && (p.dbg & 8) && blockIdx.x == 0 && q == 0 && lane == 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, t_par ^= 1u) {
       const int64_t grow = static_cast<int64_t>(p.reverse ? p.tiles - 1 - tile : tile) * BM + r;
       const bool row_ok = grow < p.M;
@@ -463,10 +496,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t par = nuse & 1u;
         float bias_v = 0.f;
         if (!BWD && p.b1) bias_v = __ldg(p.b1 + j * HC + wg_tid);
-        mbar_wait(smem_u32(&acc1_full[wg]), par);
-        if (!BWD) mbar_wait(smem_u32(&h_empty[wg]), par ^ 1u);           // operand buffer free (GEMM2 + store of chunk j-2)
-        else mbar_wait(smem_u32(&hin_full[wg]), par);                    // hpre chunk landed in the operand buffer
+        MLP_WAIT(smem_u32(&acc1_full[wg]), par, a_a1);
+        if (!BWD) MLP_WAIT(smem_u32(&h_empty[wg]), par ^ 1u, a_hin);     // operand buffer free (GEMM2 + store of chunk j-2)
+        else MLP_WAIT(smem_u32(&hin_full[wg]), par, a_hin);              // hpre chunk landed in the operand buffer
         tc_fence_after();
+        const long long tm0 = kMlpAcct ? clock64() : 0;
         if (!BWD) {
           named_bar_sync(1 + wg, 128);                                   // previous chunk's bias reads are done
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias1 + wg_tid * 4), "f"(bias_v) : "memory");
@@ -541,13 +575,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_arrive(smem_u32(&acc1_empty[wg]));              // accumulator drained
         fence_proxy_async_smem();                            // operand buffer writes -> visible to UMMA / TMA
         mbar_arrive(smem_u32(&h_full[wg]));
+        if (kMlpAcct) a_math += clock64() - tm0;
       }
       {
         // ---- output tile: acc2 (+ b2 + residual) -> bf16, 32 bytes per row per step straight to global.  Each
         //      warpgroup takes 128 of the 256 columns (warpgroup 0 would otherwise idle from its last chunk until
         //      the next tile's first GEMM1) ----
-        mbar_wait(smem_u32(&acc2_full), t_par);
+        MLP_WAIT(smem_u32(&acc2_full), t_par, a_a2);
         tc_fence_after();
+        const long long to0 = kMlpAcct ? clock64() : 0;
         bf16* out_row = p.out + grow * DM;
         const bf16* res_row = (!BWD && p.resid && row_ok) ? p.resid + grow * DM : nullptr;
         uint32_t v[2][16];
@@ -600,8 +636,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&acc2_empty));
+        if (kMlpAcct) a_out += clock64() - to0;
       }
     }
+    if (acct)
+      printf("mlp acct: epilogue wg %d total %lld clk, waiting acc1_full %lld, %s %lld, acc2_full %lld; chunk math %lld, output tile %lld\n",
+             wg, clock64() - a_t0, a_a1, BWD ? "hin_full (hpre landed)" : "h_empty (buffer free)", a_hin, a_a2, a_math, a_out);
   }
 
   tc_fence_before();

@@ -95,13 +95,16 @@ class PPOAgent:
         With world_size > 1 the arguments are this rank's shard of the global minibatch and
         `sample_offset` is its first global sample index (noise counters are global).
         graph=True (single GPU): the step's ~130 launches are captured once per batch size in a CUDA graph and
-        replayed; the arguments are copied into the graph's static input buffers.
+        replayed; the arguments are copied into the graph's static input buffers.  graph="inplace": one graph per SET of
+        input buffers (keyed by their addresses), replayed without any copy — for callers that cycle through a few
+        persistent device buffers (HostMinibatchFeeder slots); the caller keeps those buffers alive.
         row_idx (int64 [B], device): the minibatch is rows row_idx of the given tensors (whole-rollout storage) — the
         gather is fused into the first kernels (sc_patchify_bf16, sc_ppo_loss), no gathered copy is made.
         sample_idx (int64 [B], device) + global_batch: this rank's samples sit at positions sample_idx of a global
         minibatch of `global_batch` samples (ragged data-parallel slices of update())."""
         if graph and self.world == 1 and row_idx is None and sample_idx is None:
-            return self._graphed_step(cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats)
+            return self._graphed_step(cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats,
+                                      inplace=(graph == "inplace"))
         self._step_body(cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters=False, row_idx=row_idx,
                         sample_idx=sample_idx, global_batch=global_batch, arena_cap=arena_cap)
         if not sync_stats:
@@ -166,14 +169,16 @@ class PPOAgent:
         return (tuple(cam.shape), cam.dtype, tuple(bev.shape), bev.dtype, int(sample_offset), snr, self.channel,
                 float(self.policy.engine.rician_k), self.spec, int(self.seed))
 
-    def _graphed_step(self, cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats):
+    def _graphed_step(self, cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats, inplace=False):
         key = self._graph_key(cam, bev, sample_offset)
+        if inplace:
+            key = key + tuple(t.data_ptr() for t in (cam, bev, actions, logp_old, adv, ret))
         entry = self._graphs.get(key)
         if entry is None:
             # the first step of this shape runs eagerly (allocates the activation arena, sets kernel attributes);
             # then the same schedule is recorded, not executed, against static copies of the inputs
             self._step_body(cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters=False)
-            static = [t.clone() for t in (cam, bev, actions, logp_old, adv, ret)]
+            static = [t if inplace else t.clone() for t in (cam, bev, actions, logp_old, adv, ret)]
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

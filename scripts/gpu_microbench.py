@@ -26,6 +26,30 @@ def rec(name, secs, nbytes, units=None, unit_name=None):
     out[name] = d
     print(name, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items()})
 
+# pure-write and pure-read streams (what a write-heavy / read-heavy kernel can expect, next to the 50/50 copy peak)
+big = torch.empty(1 << 29, device="cuda")                       # 2 GiB fp32
+st8 = torch.zeros(8, device="cuda")
+s = t(lambda: ops.step_begin(big, st8, None))
+rec("pure_write_2GiB_sc_step_begin", s, big.numel() * 4)
+s = t(lambda: big.zero_())
+rec("pure_write_2GiB_torch_memset", s, big.numel() * 4)
+b16 = big.view(torch.bfloat16).view(-1, 256)
+cs = torch.zeros(256, device="cuda")
+s = t(lambda: ops.colsum(b16, cs))
+rec("pure_read_2GiB_sc_colsum", s, big.numel() * 4)
+dst = torch.empty(1 << 28, device="cuda")
+s = t(lambda: dst.copy_(big[:1 << 28]))
+rec("copy_1GiB_torch", s, dst.numel() * 8)
+del big, b16, dst
+# patchify (both observation shapes, bf16 and fp32 sources)
+for name, shape, P in (("cam", (4096, 3, 128, 128), 16), ("bev", (4096, 1, 64, 64), 8)):
+    for dt in (torch.bfloat16, torch.float32):
+        img = torch.rand(*shape, device="cuda").to(dt)
+        outp = torch.empty(shape[0] * (shape[2] // P) ** 2, shape[1] * P * P, device="cuda", dtype=torch.bfloat16)
+        s = t(lambda: ops.patchify(img, P, out=outp))
+        rec(f"patchify_{name}_{str(dt).split('.')[-1]}_B4096", s, img.numel() * img.element_size() + outp.numel() * 2)
+        del img, outp
+
 k = sp.k_sym
 for B in (4096, 32768):
     z = torch.randn(2, B, k, device="cuda")
