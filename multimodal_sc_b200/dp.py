@@ -114,8 +114,12 @@ class OverlappedGradAllReduce:
 
 
 def global_adv_moments(sums: torch.Tensor, local_count: int, pg=None):
-    """sums = float64 [sum A, sum A^2] over the local shard -> (global sums, global count)."""
+    """sums = float64 [sum A, sum A^2] over the local shard -> (global sums, global count).  The count is reduced with the
+    sums (ranks may own different numbers of environments); one small all-reduce and one host read per rollout."""
     world, _ = world_info(pg)
-    if world > 1:
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=pg)
-    return sums, local_count * world
+    if world == 1:
+        return sums, local_count
+    buf = torch.cat([sums.reshape(2), torch.tensor([float(local_count)], dtype=sums.dtype, device=sums.device)])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=pg)
+    sums.copy_(buf[:2])
+    return sums, int(round(float(buf[2])))

@@ -71,6 +71,10 @@ class PPOAgent:
         self.pg = process_group
         self.world, self.rank = dp.world_info(process_group)
         dev = policy.device
+        # a new agent is a new optimizer (the oracle builds a fresh torch.optim.Adam): the flat Adam moments live next to
+        # the parameters in the policy's FlatParams, so they are reset here; checkpoint.load() restores them afterwards
+        policy.flat.m.zero_()
+        policy.flat.v.zero_()
         self.stats = torch.zeros(8, device=dev, dtype=F32)      # pi, v, ent, kl, clipfrac, l_sem, -, -
         self.sums = torch.zeros(2, device=dev, dtype=torch.float64)
         # device-side mirror of step_count: the channel seed and Adam's bias correction read it inside the kernels,
@@ -94,15 +98,16 @@ class PPOAgent:
         """cam/bev fp32 or bf16, actions int64, logp_old/adv/ret fp32 — all on the policy's device.
         With world_size > 1 the arguments are this rank's shard of the global minibatch and
         `sample_offset` is its first global sample index (noise counters are global).
-        graph=True (single GPU): the step's ~130 launches are captured once per batch size in a CUDA graph and
-        replayed; the arguments are copied into the graph's static input buffers.  graph="inplace": one graph per SET of
+        graph=True: the step's ~130 launches are captured once per batch size in a CUDA graph and replayed (+2.5 % on one
+        B200: no launch gaps); the arguments are copied into the graph's static input buffers.  With world_size > 1 the
+        NCCL all-reduce of the flat gradient bucket is captured with the step (the single-all-reduce schedule only).  graph="inplace": one graph per SET of
         input buffers (keyed by their addresses), replayed without any copy — for callers that cycle through a few
         persistent device buffers (HostMinibatchFeeder slots); the caller keeps those buffers alive.
         row_idx (int64 [B], device): the minibatch is rows row_idx of the given tensors (whole-rollout storage) — the
         gather is fused into the first kernels (sc_patchify_bf16, sc_ppo_loss), no gathered copy is made.
         sample_idx (int64 [B], device) + global_batch: this rank's samples sit at positions sample_idx of a global
         minibatch of `global_batch` samples (ragged data-parallel slices of update())."""
-        if graph and self.world == 1 and row_idx is None and sample_idx is None:
+        if graph and row_idx is None and sample_idx is None and (self.world == 1 or not self.overlap_allreduce):
             return self._graphed_step(cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats,
                                       inplace=(graph == "inplace"))
         self._step_body(cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters=False, row_idx=row_idx,
@@ -144,14 +149,15 @@ class PPOAgent:
         elif ov is not None:                                     # a rank without samples still joins every collective
             for name in ("dec", "cam_enc", "bev_enc"):
                 ov.ready(name)
-        if self.world > 1:
+        timed = self.world > 1 and not torch.cuda.is_current_stream_capturing()    # timing events cannot be captured
+        if timed:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         if ov is not None:
             ov.finish()
         else:
             dp.allreduce_flat_grads(flat.g32, self.pg)
-        if self.world > 1:
+        if timed:
             ev1.record()
             self.allreduce_events = (ev0, ev1)
         if device_counters:

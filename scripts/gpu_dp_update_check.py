@@ -46,20 +46,26 @@ for channel in ("awgn", "rayleigh"):
     st_1 = ag_1.update(ro)
     perms_equal = all(torch.equal(a, b) for a, b in zip(ag_dp.last_perms, ag_1.last_perms))
     local_counts = None
-    worst = {}
+    worst, first = {}, {}
     for i, (a, b) in enumerate(zip(ag_1.last_step_stats, ag_dp.last_step_stats)):
         for k in ("pi", "v", "ent", "kl", "l_sem", "total"):
-            worst[k] = max(worst.get(k, 0.0), abs(a[k] - b[k]) / max(abs(a[k]), 0.05))
+            d = abs(a[k] - b[k]) / max(abs(a[k]), 0.05)
+            worst[k] = max(worst.get(k, 0.0), d)
+            if i == 0:
+                first[k] = d
     dpar = (pol_dp.flat.p32 - pol_1.flat.p32).abs()
     # every rank must hold the same parameters after the update
     chk = pol_dp.flat.p32.double().sum().reshape(1)
     both = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(both, chk)
     res = {"perms_equal": bool(perms_equal), "steps": len(ag_dp.last_step_stats),
-           "worst_rel_stat_diff": worst, "update_mean_stats_dp": st_dp, "update_mean_stats_1rank": st_1,
+           "first_step_rel_stat_diff": first, "worst_rel_stat_diff": worst, "update_mean_stats_dp": st_dp, "update_mean_stats_1rank": st_1,
            "param_max_abs_diff": float(dpar.max()), "param_frac_diff_gt_0.02lr": float((dpar > 0.02 * sp.lr).float().mean()),
            "lr": sp.lr, "ranks_hold_identical_params": bool(all(float(b) == float(both[0]) for b in both))}
-    res["ok"] = bool(perms_equal and max(worst.values()) < 2e-2 and res["param_frac_diff_gt_0.02lr"] < 2e-2
+    # step 0 runs on identical weights: only fp32 summation order differs.  Later steps: an element whose gradient is
+    # within summation-order noise of zero moves by +-lr either way (Adam's first steps are sign-like), which perturbs
+    # the following steps' statistics at the 1e-3 level
+    res["ok"] = bool(perms_equal and max(first.values()) < 1e-4 and max(worst.values()) < 2e-2
                      and res["ranks_hold_identical_params"])
     out[channel] = res
 if rank == 0:

@@ -7,7 +7,7 @@ import torch
 
 from multimodal_sc_b200 import ops
 
-B, k = 4096, 1024
+B, k = (int(sys.argv[2]) if len(sys.argv) > 2 else 4096), 1024
 kind = sys.argv[1] if len(sys.argv) > 1 else "awgn"
 z = torch.randn(2, B, k, device="cuda")
 y16 = torch.empty(B, 2, k, device="cuda", dtype=torch.bfloat16)

@@ -184,8 +184,9 @@ def _update_worker(rank, world, port, q):
         adv, ret = oppo.gae(loc["rewards"], loc["values"], loc["dones"], loc["last_value"], SPEC.gamma, SPEC.lam)
         sums = torch.tensor([adv.double().sum(), adv.double().pow(2).sum()])
         sums, count = dp.global_adv_moments(sums, adv.numel())
-        mean = sums[0] / (T * N)
-        std = (sums[1] / (T * N) - mean * mean).clamp_min(0).sqrt()
+        assert count == T * N                                  # unequal shards: the count is reduced, not local * world
+        mean = sums[0] / count
+        std = (sums[1] / count - mean * mean).clamp_min(0).sqrt()
         adv = ((adv.double() - mean) / (std + SPEC.adv_eps)).float()
         flat = lambda x: x.reshape(T * n_loc, *x.shape[2:])
         cam, bev, act, lp = flat(loc["cam"]), flat(loc["bev"]), flat(loc["actions"]), flat(loc["logp"])
