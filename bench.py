@@ -232,8 +232,27 @@ def run_native(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    t_start = time.perf_counter()
+
+    def phase(msg):                                   # progress marks on stderr (stdout carries the JSON line only)
+        if rank == 0:
+            print(f"[bench +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    def finish():
+        """tear-down: captured graphs hold the NCCL communicator, so they go first; with N > 1 the process then leaves
+        without the collective destroy (a rank that is already gone cannot answer it)"""
+        ag._graphs.clear()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            os._exit(0)
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # torchrun pins OMP_NUM_THREADS=1: the synthetic host inputs (2 x 436 MB + a 872 MB rollout per rank) are generated
+    # outside every timed region, with this rank's share of the host cores
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there when
     # NCCL_DEBUG is set) are pointed at stderr until the line is printed
     sys.stdout.flush()
@@ -305,14 +324,16 @@ def run_native(a):
             per_step[tag] = {"median": d[len(d) // 2], "min": d[0], "max": d[-1]}
         return float(ms)
 
+    phase("inputs ready, warm-up")
     for i in range(max(a.warmup, 3)):
         step_dev(i)
+    phase("timed region (device-resident)")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
+    l0 = _lib.launch_count() + ag.replayed_launches
     ms_total = timed(step_dev, a.steps, tag="value")
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() + ag.replayed_launches - l0   # eager launches + kernels inside the replayed graphs
     ar_ms = None
     if world > 1:                                             # device time of the gradient all-reduce: one eager step (the
         saved, GRAPH = GRAPH, False                           # graph replays carry no timing events), after the timed region
@@ -324,6 +345,7 @@ def run_native(a):
     value = world * B * a.steps / (ms_total * 1e-3)
 
     # end-to-end: host buffers, H2D + D2H inside the timed region
+    phase("timed region (end to end from pinned host buffers)")
     for i in range(2):
         step_host(i, i == 1)
     ms_e2e = timed(step_host, a.steps, with_last=True, tag="e2e")
@@ -331,6 +353,7 @@ def run_native(a):
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
     # roofline pass: one extra step with every launch bracketed by CUDA events on the launching stream
+    phase("roofline pass")
     barrier()
     GRAPH = False                                   # per-launch events need the eager schedule
     with ops.profile() as prof:
@@ -341,6 +364,7 @@ def run_native(a):
     # owns N_ENVS whole environments and update() slices the global permutation by rank (ragged local minibatches)
     upd = None
     if not a.no_update:
+        phase("update_e2e")
         T_ro, n_env = sp.rollout_t, max(2 * B // sp.rollout_t, 1)
         ro = synthetic.rollout(sp, T_ro, n_env, seed=300 + rank)
         ro["cam"], ro["bev"] = ro["cam"].bfloat16(), ro["bev"].bfloat16()
@@ -361,9 +385,9 @@ def run_native(a):
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish()
         return
+    phase("cpu baseline / secondary configs")
     peaks = _peaks()
     gemm = {k: v for k, v in summ.items() if k.startswith("gemm_")}
     g_ms = sum(v["ms"] for v in gemm.values())
@@ -449,8 +473,8 @@ def run_native(a):
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    phase("done")
+    finish()
 
 
 def main():

@@ -18,7 +18,7 @@ import os
 
 import torch
 
-from . import dp, ops
+from . import _lib, dp, ops
 from .model import SemComPolicy
 from .spec import SpecV0
 
@@ -90,6 +90,8 @@ class PPOAgent:
         self.last_perms = []                                     # permutations / per-minibatch statistics of the last
         self.last_step_stats = []                                #   update() (parity tests)
         self.allreduce_events = None                             # (start, end) CUDA events around the last gradient all-reduce
+        self.replayed_launches = 0                               # library kernels executed through CUDA-graph replays (the
+                                                                 # library's own counter only sees launches at capture time)
 
     # ---- one optimizer step on one (local) minibatch ---------------------------------------------
     def minibatch_step(self, cam, bev, actions, logp_old, adv, values_unused, ret, sample_offset: int = 0,
@@ -187,11 +189,13 @@ class PPOAgent:
             static = [t if inplace else t.clone() for t in (cam, bev, actions, logp_old, adv, ret)]
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._step_body(*static, sample_offset, device_counters=True)
-            self._graphs[key] = (g, static)
+            self._graphs[key] = (g, static, _lib.launch_count() - l0)
         else:
-            g, static = entry
+            g, static, n_launches = entry
+            self.replayed_launches += n_launches
             for dst, src in zip(static, (cam, bev, actions, logp_old, adv, ret)):
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
