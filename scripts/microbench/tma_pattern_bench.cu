@@ -78,6 +78,33 @@ stream_kernel(const __grid_constant__ CUtensorMap tm2, const __grid_constant__ C
   if (acc == 0x12345678abcdefULL) *sink = acc;
 }
 
+// ---- store side: W warps per CTA, each owns two staging slots and streams (rows x 64-column) SWIZZLE_128B boxes of a row-major
+// [M, ncols] bf16 matrix with TMA stores (the GEMM's staged epilogue writes 32-row x 64-column = 4 KB boxes, one per warp
+// and chunk).  rows_per_box = 32 (4 KB) or 128 (16 KB).  No math, no loads: the write path alone.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__global__ void __launch_bounds__(256, 1)
+store_kernel(const __grid_constant__ CUtensorMap tmS, int row_tiles, int col_chunks, int rows_per_box, int warps, int delay) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= warps || lane != 0) return;
+  const uint32_t slot0 = smem_u32(smem) + warp * 2 * rows_per_box * 128;
+  const int boxes_per_tile = 128 / rows_per_box;              // row boxes per 128-row tile
+  int n = 0;
+  for (int tile = blockIdx.x; tile < row_tiles; tile += gridDim.x) {
+    // this warp's share of the tile: row boxes warp, warp + warps, ... ; every 64-column chunk
+    for (int rb = warp; rb < boxes_per_tile; rb += warps)
+      for (int c = 0; c < col_chunks; ++c, ++n) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the slot used two stores ago has been read
+        tma_store_2d(&tmS, slot0 + (n & 1) * rows_per_box * 128, c * 64, tile * 128 + rb * rows_per_box);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (delay > 0) { const long long t0 = clock64(); while (clock64() - t0 < delay) {} }
+      }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -135,5 +162,37 @@ int main() {
         }
         printf("%-40s stages %2d delay %4d clk: %7.1f us  %7.1f GB/s\n", names[mode], stages, delay, best * 1e3, M * 512.0 / (best * 1e-3) / 1e9);
       }
+  // ---- store side ----
+  printf("# TMA stores into a row-major [M, ncols] bf16 matrix (1 GiB), GB/s of HBM writes\n");
+  CK(cudaFuncSetAttribute(store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  for (int ncols : {256, 1024})
+    for (int rows_per_box : {32, 128}) {
+      CUtensorMap tmS;
+      const long long Ms = (1ll << 30) / (ncols * 2);
+      cuuint64_t dims[2] = {(cuuint64_t)ncols, (cuuint64_t)Ms}; cuuint64_t str[1] = {(cuuint64_t)ncols * 2};
+      cuuint32_t box[2] = {64, (cuuint32_t)rows_per_box}; cuuint32_t es[2] = {1, 1};
+      CUresult r = enc(&tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { printf("encode store map failed %d\n", (int)r); return 1; }
+      for (int warps : {1, 4, 8}) {
+        if (rows_per_box == 128 && warps > 1) continue;
+        for (int delay : {0, 400}) {
+          float best = 1e9f;
+          for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaMemsetAsync(flush, rep, 512ll << 20));
+            CK(cudaEventRecord(e0));
+            store_kernel<<<sms, 256, 65536>>>(tmS, (int)(Ms / 128), ncols / 64, rows_per_box, warps, delay);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+          }
+          printf("stores: ncols %4d, box %3d rows x 64 cols (%2d KB), %d issuing warps, delay %3d clk: %7.1f us  %7.1f GB/s\n", ncols,
+                 rows_per_box, rows_per_box * 128 / 1024, warps, delay, best * 1e3, (double)(1ll << 30) / (best * 1e-3) / 1e9);
+        }
+      }
+    }
   return 0;
 }
