@@ -139,6 +139,9 @@ struct GemmParams {
   int reverse;                  // 1 = items (and the k-blocks of a split-K item) are walked in descending order
   int ln_split;                 // column split: both epilogue warpgroups drain the SAME tile, columns 0-127 / 128-255
                                 // (NWG = 2, SLOTS = 2; fused LayerNorm and the output-only staged epilogues)
+  int ln_prefetch;              // split LayerNorm epilogue: the NEXT tile's residual chunks are requested into L2 at the start
+                                // of this tile (its TMA loads can only be issued once this tile's stores have drained the two
+                                // slots, so their latency is exposed at every tile; from L2 it is a third of the HBM latency)
 };
 
 struct Item {
@@ -1244,6 +1247,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (G::LN_TILES != 0) {
               const uint32_t ln_base = smem_base + G::SMEM + G::RING + NWG * BIAS_TILE_BYTES;
               if constexpr (G::LN_XCHG != 0) {
+                if (ln_split && p.ln_prefetch && lane == 0 && next.valid && p.in_row_period == 0 && !(p.dbg & 3)) {
+                  tma_prefetch_l2_2d(&tmIn, next.n0 + (wg * 2) * 64, next.in_row0);
+                  tma_prefetch_l2_2d(&tmIn, next.n0 + (wg * 2 + 1) * 64, next.in_row0);
+                }
                 if (ln_split)
                   staged_tile_ln_split(p, &tmOut, &tmAux, &tmIn, t_addr, ring, ib0, bias_tile, ln_base, ln_base + BIAS_TILE_BYTES,
                                        ln_base + 2 * BIAS_TILE_BYTES, lane, wg, q, row0, static_cast<int64_t>(row0) + lane,
@@ -1288,7 +1295,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 struct DebugOverrides {
   int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0,
-          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 0, ln_split = 1, mcb = 0, col_split = 0;
+          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 512, ln_split = 1, mcb = 0, col_split = 0, ln_prefetch = 0;
 };
 DebugOverrides g_dbg;
 
@@ -1372,6 +1379,7 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "ln_split")) g_dbg.ln_split = value;
   else if (!strcmp(key, "mcb")) g_dbg.mcb = value;
   else if (!strcmp(key, "col_split")) g_dbg.col_split = value;
+  else if (!strcmp(key, "ln_prefetch")) g_dbg.ln_prefetch = value;
   else if (!strcmp(key, "nwg")) g_dbg.nwg = value;
   else if (!strcmp(key, "gemm_dbg")) g_dbg.gemm_dbg = value;
   else if (!strcmp(key, "slots")) g_dbg.slots = value;
@@ -1409,6 +1417,10 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   // cta2_wgrad: CTA pairs (cta_group::2, 256 x 256 tile per pair, each CTA loads half of B) for the split-K weight
   // gradients only: one long item per pair, so the accumulator hand-off that hurt the K = 256 shapes happens once, and
   // the operand traffic from L2 per FLOP drops by a third
+  // cta2_mink (default 512): activation x weight GEMMs with a long reduction (the qkv dgrad, K = 768; any K = 1024 shape
+  // without a fused LayerNorm) also run as CTA pairs: with K >= 512 a tile holds 8+ k-blocks, the accumulator hand-off is
+  // amortised, and the per-SM operand ingest drops from 48 to 32 KB per k-block — these shapes were waiting for operands
+  // 39-54 % of the MMA warp's time (profiles/r2_gemm_wait_accounting.txt): dgrad_qkv 108-117 -> 99-100 us per launch
   const bool cta2 = g_dbg.cta2 != 0 ||
                     (g_dbg.cta2_wgrad != 0 && a_mn && b_mn && ksplit > 1 && M % (2 * BM) == 0 && N % BN == 0) ||
                     (g_dbg.cta2_mink > 0 && !a_mn && K >= g_dbg.cta2_mink && ksplit <= 1 && !epi->ln_out &&
@@ -1555,6 +1567,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   // one-warpgroup / 4-slot form
   // (measured: K <= 256 shapes gain 4-7 %, the K = 1024 fc2 shape loses 2-4 % -> short K only; ln_split = 2 forces it)
   p.ln_split = (fused_ln && (g_dbg.ln_split == 2 || (g_dbg.ln_split == 1 && K <= 256))) ? 1 : 0;
+  p.ln_prefetch = g_dbg.ln_prefetch != 0;
   const int nwg = fused_ln ? (p.ln_split ? 2 : 1) : (g_dbg.nwg ? (g_dbg.nwg == 2 ? 2 : 1) : ((short_k && !light_in) ? 2 : 1));
   const int slots = fused_ln ? (p.ln_split ? 2 : 4) : (g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2));
   // output-only staged epilogues with two warpgroups: column split as an option (sc_debug_set("col_split", 1 | 2)); off:
