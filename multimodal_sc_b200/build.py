@@ -30,6 +30,8 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("SC_MBAR_LIMIT", "") != "":                    # bring-up builds: mbarrier waits trap after 2^N tries
+    NVCC_FLAGS.append(f"-DSC_MBAR_SPIN_LIMIT=(1u<<{int(os.environ['SC_MBAR_LIMIT'])})")
 if os.environ.get("SC_MLP_ACCT", "0") not in ("", "0"):        # per-role wait accounting in the fused MLP kernel (debug builds)
     NVCC_FLAGS.append("-DSC_MLP_ACCT")
 if os.environ.get("SC_GEMM_ACCT", "0") not in ("", "0"):       # per-role wait accounting in the GEMM kernel (debug builds)

@@ -139,10 +139,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return done;
 }
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host), never hang the GPU box.
+// SC_MBAR_SPIN_LIMIT (build.py: SC_MBAR_LIMIT=<log2>) shortens the bound for bring-up runs of new barrier protocols
+// (every try may sleep up to 20 us, so 2^24 tries can be minutes).
+#ifndef SC_MBAR_SPIN_LIMIT
+#define SC_MBAR_SPIN_LIMIT (1u << 24)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #pragma unroll 1
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
-    if (it > (1u << 24)) {                                   // >= seconds even if every try returns at once
+    if (it > SC_MBAR_SPIN_LIMIT) {                           // >= seconds even if every try returns at once
       printf("semcom: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
       __trap();

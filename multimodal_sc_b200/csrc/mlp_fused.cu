@@ -24,6 +24,9 @@
 // sectors), h / dhpre leave the operand buffer by TMA, the residual tile is prefetched to L2 by the producer.
 #include "common.cuh"
 
+int sc_mlp_bwd_pair_launch(const void* dy, const void* w1, const void* w2, const void* hpre, void* dhpre, void* dx, int64_t M,
+                           int R, int dbg, cudaStream_t st);      // mlp_bwd_pair.cu
+
 namespace {
 
 constexpr int BM = 128;                 // rows per tile
@@ -743,6 +746,13 @@ extern "C" int sc_mlp_bwd_dgrad(const void* dy, const void* w1, const void* w2, 
   SC_REQUIRE(sc_aligned16(dy) && sc_aligned16(w1) && sc_aligned16(w2) && sc_aligned16(hpre) && sc_aligned16(dhpre) &&
                  sc_aligned16(dx),
              SC_E_ALIGN, "sc_mlp_bwd_dgrad: all pointers must be 16-byte aligned");
+  // mlp_dbg bit 32 (opt-in): the CTA-pair kernel (cta_group::2, mlp_bwd_pair.cu) — the leader issues every MMA once for both
+  // 128-row tiles, each CTA stages half of every weight tile, three hidden buffers.  Bit-identical results, but 6 % SLOWER
+  // (388 vs 367 us per 262144 tokens, profiles/r2_mlp_wait_accounting.txt): with the MMA warp no longer pacing the kernel the
+  // epilogue warps' chunk math takes twice as long (they share the SM's shared-memory bandwidth with MMAs that now run
+  // back to back: a 128 x 128 x 16 MMA alone reads 8 KB per 64 clk = the full 128 B/clk).
+  if ((g_mlp_dbg & 32) && M > BM)
+    return sc_mlp_bwd_pair_launch(dy, w1, w2, hpre, dhpre, dx, M, R, g_mlp_dbg, static_cast<cudaStream_t>(stream));
   MlpParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.R = R; p.tiles = static_cast<int>((M + BM - 1) / BM);

@@ -96,6 +96,29 @@ def test_mlp_bwd_dgrad_matches_autograd(cuda_lib, M, R):
     assert _rel(dx, dx_ref) < 1e-2, ("dx", _rel(dx, dx_ref))
 
 
+@pytest.mark.parametrize("M,R", [(777, 1024), (148 * 128 * 2 + 129, 1024), (260, 384)])
+def test_mlp_bwd_pair_kernel_is_bit_identical(cuda_lib, M, R):
+    """the opt-in CTA-pair form of sc_mlp_bwd_dgrad (cta_group::2, mlp_dbg bit 32; kept as a measured alternative, slower than
+    the default) computes exactly what the default kernel does: ragged tails, several super-tiles per pair, odd chunk count"""
+    from multimodal_sc_b200 import ops
+    x, w1, b1, w2, b2, _ = _mk(M, R, seed=300 + M)
+    g = torch.Generator(device="cuda").manual_seed(M)
+    dy = torch.randn(M, 256, generator=g, device="cuda").to(BF16)
+    hpre = (torch.randn(M, R, generator=g, device="cuda") * 1.5).to(BF16)
+    outs = []
+    for dbg in (0, 32):
+        ops.debug_set("mlp_dbg", dbg)
+        try:
+            dhpre = torch.full((M, R), float("nan"), device="cuda", dtype=BF16)
+            dx = torch.full((M, 256), float("nan"), device="cuda", dtype=BF16)
+            ops.mlp_bwd_dgrad(dy, w1, w2, hpre, dhpre=dhpre, dx=dx)
+            outs.append((dhpre, dx))
+        finally:
+            ops.debug_set("mlp_dbg", 0)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert not torch.isnan(outs[1][1].float()).any()
+
+
 def test_mlp_rejects_bad_shapes(cuda_lib):
     from multimodal_sc_b200 import _lib, ops
     x = torch.zeros(128, 128, device="cuda", dtype=BF16)
