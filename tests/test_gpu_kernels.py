@@ -360,3 +360,26 @@ def test_snr_embed_fwd_bwd(cuda_lib):
         _close(dW, Wr.grad, 1e-4, 1e-5, "dW")
         _close(du, ur.grad, 1e-4, 1e-5, "du")
         _close(dv, vr.grad, 1e-4, 1e-5, "dv")
+
+
+def test_quantised_channel_matches_golden_v2(cuda_lib):
+    """native quantised-symbol channel (forward + straight-through backward) against the committed oracle vectors
+    tests/golden/oracle_v2.pt (scripts/make_golden_v2.py)"""
+    import os
+    from multimodal_sc_b200 import ops
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_v2.pt"))
+    gen = torch.Generator().manual_seed(23)
+    z = torch.randn(3, 2, SPEC.k_sym, generator=gen) * 0.4
+    z[0, 0, :4] *= 30.0
+    snr = torch.tensor([0.0, 8.0, 16.0])
+    dy = torch.randn(3, 2, SPEC.k_sym, generator=gen)
+    for bits in (2, 5):
+        y, _, scale = ops.pnorm_channel_fwd(z.cuda(), "awgn", snr.cuda(), seed=7, quant_bits=bits, quant_clip=2.0)
+        dz, _ = ops.pnorm_channel_bwd(dy.cuda(), z.cuda(), scale, "awgn", snr.cuda(), seed=7, quant_bits=bits, quant_clip=2.0)
+        yr, dzr = g[f"quant{bits}_clip2_awgn_seed7_y"], g[f"quant{bits}_clip2_awgn_seed7_dz"]
+        step = 4.0 / 2 ** bits
+        flipped = (y.cpu() - yr).abs() > 0.25 * step              # a symbol within an ulp of a decision boundary
+        assert float(flipped.float().mean()) < 1e-3
+        _close(y.cpu()[~flipped], yr[~flipped], 1e-5, 2e-5, f"y quant{bits}")
+        ok = (~flipped).all(dim=-1)
+        _close(dz.cpu()[ok], dzr[ok], 1e-4, 2e-5, f"dz quant{bits}")

@@ -341,3 +341,34 @@ def test_round2_options_match_oracle(cuda_lib, spec_kw):
     if spec.snr_cond:
         for enc in ("cam_enc", "bev_enc"):
             assert float(dict(n.named_parameters())[f"{enc}.snr.w"].grad.abs().max()) > 0
+
+
+def test_round2_options_match_golden_v2(cuda_lib):
+    """native forward with the round-2 spec options against the committed oracle outputs (tests/golden/oracle_v2.pt,
+    scripts/make_golden_v2.py): same seeded initialisation, same inputs, bf16 tolerance (quantised symbols: a symbol within
+    bf16 rounding of a decision boundary may land in the neighbouring cell, so only the downstream outputs are compared)"""
+    import dataclasses
+    import importlib.util
+    import os
+    from multimodal_sc_b200 import synthetic
+    from multimodal_sc_b200.model import SemComPolicy
+    here = os.path.dirname(__file__)
+    spec_ = importlib.util.spec_from_file_location("make_golden_v2", os.path.join(here, "..", "scripts", "make_golden_v2.py"))
+    mg = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mg)
+    g = torch.load(os.path.join(here, "golden", "oracle_v2.pt"))
+    mb = synthetic.minibatch(SPEC, 2, seed=0)
+    snr2 = torch.tensor([2.0, 14.0]).cuda()
+    for name, kw in mg.OPTIONS.items():
+        spec = dataclasses.replace(SPEC, **kw)
+        o = mg.policy_for(spec)
+        n = SemComPolicy(spec)
+        n.load_state_dict(o.state_dict())
+        with torch.no_grad():
+            l, v, aux = n(mb["cam"].cuda(), mb["bev"].cuda(), snr2, channel="rayleigh", seed=1234)
+        tol = 6e-2 if spec.quant_bits else 2e-2
+        assert _rel(l, g[f"fwd_{name}_logits"]) < tol, (name, _rel(l, g[f"fwd_{name}_logits"]))
+        assert _rel(v, g[f"fwd_{name}_value"]) < tol, (name, _rel(v, g[f"fwd_{name}_value"]))
+        assert abs(float(aux["l_sem"]) - float(g[f"fwd_{name}_l_sem"])) < 2e-2 * float(g[f"fwd_{name}_l_sem"]), name
+        if not spec.quant_bits:
+            assert _rel(aux["y"][:, :, :8], g[f"fwd_{name}_y_head"]) < 2e-2, name

@@ -190,3 +190,45 @@ def test_golden_vectors_v1_rician():
     assert torch.allclose(y, g["rician_k2.5_seed99_off5_y"], rtol=1e-6, atol=1e-7)
     assert torch.allclose(och.rician_fading(och.make_fading(99, 3, 5), 2.5), g["rician_fading_seed99_b3_off5_k2.5"],
                           rtol=1e-6, atol=1e-7)
+
+
+def test_golden_vectors_v2_options():
+    """oracle against tests/golden/oracle_v2.pt (scripts/make_golden_v2.py): pins the round-2 spec options — b-bit quantised
+    symbols with the clipped straight-through gradient, SNR-conditioned encoders, exact-erf GELU."""
+    import dataclasses
+    import importlib.util
+    spec_ = importlib.util.spec_from_file_location("make_golden_v2", os.path.join(os.path.dirname(__file__), "..", "scripts", "make_golden_v2.py"))
+    mg = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mg)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_v2.pt"))
+    sp = SpecV0()
+    gen = torch.Generator().manual_seed(23)
+    z = torch.randn(3, 2, sp.k_sym, generator=gen) * 0.4
+    z[0, 0, :4] *= 30.0
+    snr = torch.tensor([0.0, 8.0, 16.0])
+    dy = torch.randn(3, 2, sp.k_sym, generator=gen)
+    for bits in (2, 5):
+        zr = z.clone().requires_grad_(True)
+        y, zn = och.channel_forward(zr, snr, "awgn", seed=7, quant_bits=bits, quant_clip=2.0)
+        (y * dy).sum().backward()
+        assert torch.allclose(y, g[f"quant{bits}_clip2_awgn_seed7_y"], rtol=1e-6, atol=1e-6)
+        assert torch.allclose(zr.grad, g[f"quant{bits}_clip2_awgn_seed7_dz"], rtol=1e-5, atol=1e-6)
+        # properties: the noiseless transmit symbols lie on the 2^bits-level grid; the clipped symbols get no gradient
+        tx = och.quantize_ste(zn.detach(), bits, 2.0)
+        step = 4.0 / 2 ** bits
+        lv = tx / step - 0.5
+        assert float((lv - lv.round()).abs().max()) < 1e-5 and int(torch.unique(lv.round()).numel()) <= 2 ** bits
+        assert float(tx.abs().max()) <= 2.0
+    mb = synthetic.minibatch(sp, 2, seed=0)
+    snr2 = torch.tensor([2.0, 14.0])
+    base = None
+    for name, kw in mg.OPTIONS.items():
+        pol = mg.policy_for(dataclasses.replace(sp, **kw))
+        with torch.no_grad():
+            l, v, aux = pol(mb["cam"], mb["bev"], snr2, channel="rayleigh", seed=1234)
+        assert torch.allclose(l, g[f"fwd_{name}_logits"], rtol=1e-4, atol=1e-5), name
+        assert torch.allclose(v, g[f"fwd_{name}_value"], rtol=1e-4, atol=1e-5), name
+        assert torch.allclose(aux["l_sem"], g[f"fwd_{name}_l_sem"], rtol=1e-4), name
+        assert torch.allclose(aux["y"][:, :, :8], g[f"fwd_{name}_y_head"], rtol=1e-4, atol=1e-5), name
+    # the options change the outputs (the vectors are not accidentally those of the default spec)
+    assert not torch.allclose(g["fwd_snr_cond_logits"], g["fwd_erf_logits"], rtol=1e-3, atol=1e-4)
