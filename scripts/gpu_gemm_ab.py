@@ -16,7 +16,7 @@ for name in names or ["proj_ln", "fc2_ln", "proj", "qkv", "fc1"]:
     A, kw = spec["A"](), spec["kw"]()
     out = torch.empty(spec["M"], spec["N"], device="cuda", dtype=torch.bfloat16)
     run = lambda: ops.gemm(A, spec["B"], b_mn=spec.get("b_mn", False), out=out, **kw)
-    res = {}
+    res, ref, same = {}, None, True
     for mode in ("off", "on", "off", "on"):
         for k, v in sw.items():
             ops.debug_set(k, int(v) if mode == "on" else 0)
@@ -29,6 +29,10 @@ for name in names or ["proj_ln", "fc2_ln", "proj", "qkv", "fc1"]:
             e0.record(); run(); e1.record(); torch.cuda.synchronize()
             tot += e0.elapsed_time(e1)
         res.setdefault(mode, []).append(round(tot / 10 * 1e3, 1))
+        snap = [out.clone()] + [v.clone() for k_, v in kw.items() if k_ == "aux_out"] + ([kw["ln"]["y"].clone()] if "ln" in kw else [])
+        same = same and all(torch.equal(a_, b_) for a_, b_ in zip(ref, snap)) if mode == "on" else same
+        if mode == "off":
+            ref = snap
     for k in sw:
         ops.debug_set(k, 0)
-    print(f"{name:10s} M {spec['M']} N {spec['N']} K {A.shape[1]}: off {res['off']} us, on {res['on']} us  ({sw})", flush=True)
+    print(f"{name:10s} M {spec['M']} N {spec['N']} K {A.shape[1]}: off {res['off']} us, on {res['on']} us  ({sw}); outputs identical: {same}", flush=True)

@@ -126,9 +126,8 @@ def test_ppo_minibatch_step_parity(cuda_lib):
     for k in ("pi", "v", "ent", "kl", "l_sem", "total"):
         assert abs(sn[k] - so[k]) <= 2e-2 * max(abs(so[k]), 0.05), (k, sn[k], so[k])
     assert sn["clipfrac"] == pytest.approx(so["clipfrac"], abs=1.0 / B + 1e-6)
-    # first Adam step = lr * g / (|g| + eps): where the gradient is resolved (|g_oracle| > 10 x the tensor's max gradient error is
-    # not available here without the gradients, so: > 1 % of the tensor's largest update-free scale) the update must have
-    # the oracle's sign; the strict form (update within 2e-2 lr wherever the gradient is resolved) runs at B = 4096 in
+    # first Adam step = lr * g / (|g| + eps), i.e. ~lr * sign(g): wherever the oracle moved a weight by ~lr the native update must
+    # have the same sign.  The strict form (update within 2e-2 lr wherever the gradient is resolved) runs at B = 4096 in
     # tests/test_gpu_parity_full.py::test_cfg3_minibatch_step_b4096
     agree, total = 0, 0
     for k, v in n.state_dict().items():
