@@ -372,3 +372,28 @@ def test_round2_options_match_golden_v2(cuda_lib):
         assert abs(float(aux["l_sem"]) - float(g[f"fwd_{name}_l_sem"])) < 2e-2 * float(g[f"fwd_{name}_l_sem"]), name
         if not spec.quant_bits:
             assert _rel(aux["y"][:, :, :8], g[f"fwd_{name}_y_head"]) < 2e-2, name
+
+
+def test_rank_without_samples_still_steps(cuda_lib):
+    """a data-parallel rank that owns no sample of a global minibatch (possible with few environments per rank) must still
+    run the step's collectives and optimizer: with an empty row index the step skips forward / backward, leaves the gradient
+    bucket at zero and Adam does not move the weights; and update() drops the tail like the oracle (n not a multiple of
+    the minibatch)"""
+    from multimodal_sc_b200 import synthetic
+    from multimodal_sc_b200.model import SemComPolicy
+    from multimodal_sc_b200.ppo import PPOAgent
+    pol = SemComPolicy(SPEC, seed=3)
+    ag = PPOAgent(pol, SPEC, minibatch=8, seed=1)
+    ro = synthetic.rollout(SPEC, 4, 2, seed=1)
+    dev = lambda x, dt=None: (x.reshape(8, *x.shape[2:]).cuda() if dt is None else x.reshape(8, *x.shape[2:]).cuda().to(dt))
+    p0 = pol.flat.p32.clone()
+    empty = torch.empty(0, dtype=torch.int64, device="cuda")
+    st = ag.minibatch_step(dev(ro["cam"]), dev(ro["bev"]), dev(ro["actions"]), dev(ro["logp"]), dev(ro["rewards"]), None,
+                           dev(ro["values"]), row_idx=empty, sample_idx=empty, global_batch=8)
+    assert ag.step_count == 1 and int(ag.dev_step) == 1
+    assert torch.equal(pol.flat.p32, p0) and float(pol.flat.g32.abs().max()) == 0.0
+    assert all(v == 0.0 for v in st.values()), st
+    # tail: 8 samples, minibatch 3 -> 2 steps per epoch (the oracle's range(0, n - mb + 1, mb))
+    ag2 = PPOAgent(pol, SPEC, minibatch=3, epochs=2, seed=1)
+    ag2.update(ro)
+    assert ag2.step_count == 4 and len(ag2.last_step_stats) == 4
