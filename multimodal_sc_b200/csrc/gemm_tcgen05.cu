@@ -438,7 +438,9 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
   // a compile-time value (the low 7 bits of swz_row are sw << 4)
   const uint32_t swz_row = static_cast<uint32_t>(lane) * 128u | (sw << 4);
 
-  auto out_slot = [&](int c) { return SLOTS == 4 ? (two_out ? 2 * (c & 1) + 1 : c) : (two_out ? 1 : (c & 1)); };
+  // SLOTS = 1 (output-only epilogues, two warpgroups): one slot per warp, every chunk waits for the store of the chunk before
+  // it — the 32 KB that saves buy a FOURTH pipeline stage, i.e. a whole K = 256 tile of operands in flight
+  auto out_slot = [&](int c) { return SLOTS == 4 ? (two_out ? 2 * (c & 1) + 1 : c) : (SLOTS == 1 ? 0 : (two_out ? 1 : (c & 1))); };
   auto aux_slot = [&](int c) { return SLOTS == 4 ? 2 * (c & 1) : 0; };
 
   uint32_t v[2][16];
@@ -460,7 +462,7 @@ __device__ __forceinline__ void staged_tile(const GemmParams& p, const CUtensorM
     } else if (lane == 0) {
       // the TMA store that last read the slot(s) must have drained them
       if (SLOTS == 4) { if (two_out) tma_store_wait_read<1>(); else tma_store_wait_read<3>(); }
-      else { if (two_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
+      else { if (two_out || SLOTS == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
     }
     __syncwarp();
   };
@@ -1180,7 +1182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool stage_bias = (p.bias != nullptr) && !(p.dbg & 1);
       const uint32_t ib0 = smem_u32(&epi_in_bar[ew][0]);
       auto in_row = [&](int row0) { return p.in_row_period > 0 ? row0 % p.in_row_period : row0; };
-      constexpr int PRE = SLOTS == 4 ? 4 : 2;                                  // input chunks requested ahead of a tile
+      constexpr int PRE = SLOTS == 4 ? 4 : (SLOTS == 1 ? 0 : 2);               // input chunks requested ahead of a tile
       if (has_in && lane == 0 && first < num_items) {
         const Item it = get_item(first);
 #pragma unroll
@@ -1295,7 +1297,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 struct DebugOverrides {
   int64_t a_lbo = 0, a_sbo = 0, a_kstep = 0, b_lbo = 0, b_sbo = 0, b_kstep = 0, max_ctas = 0, generic_epi = 0, cta2 = 0, nwg = 0,
-          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 512, ln_split = 1, mcb = 0, col_split = 0, ln_prefetch = 0;
+          gemm_dbg = 0, slots = 0, cta2_wgrad = 1, cta2_mink = 512, ln_split = 1, mcb = 0, col_split = 0, ln_prefetch = 0, one_slot = 1;
 };
 DebugOverrides g_dbg;
 
@@ -1380,6 +1382,7 @@ extern "C" int sc_debug_set(const char* key, int64_t value) {
   else if (!strcmp(key, "mcb")) g_dbg.mcb = value;
   else if (!strcmp(key, "col_split")) g_dbg.col_split = value;
   else if (!strcmp(key, "ln_prefetch")) g_dbg.ln_prefetch = value;
+  else if (!strcmp(key, "one_slot")) g_dbg.one_slot = value;
   else if (!strcmp(key, "nwg")) g_dbg.nwg = value;
   else if (!strcmp(key, "gemm_dbg")) g_dbg.gemm_dbg = value;
   else if (!strcmp(key, "slots")) g_dbg.slots = value;
@@ -1569,7 +1572,12 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
   p.ln_split = (fused_ln && (g_dbg.ln_split == 2 || (g_dbg.ln_split == 1 && K <= 256))) ? 1 : 0;
   p.ln_prefetch = g_dbg.ln_prefetch != 0;
   const int nwg = fused_ln ? (p.ln_split ? 2 : 1) : (g_dbg.nwg ? (g_dbg.nwg == 2 ? 2 : 1) : ((short_k && !light_in) ? 2 : 1));
-  const int slots = fused_ln ? (p.ln_split ? 2 : 4) : (g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2));
+  int slots = fused_ln ? (p.ln_split ? 2 : 4) : (g_dbg.slots ? (g_dbg.slots == 4 ? 4 : 2) : (light_in ? 4 : 2));
+  // one_slot: output-only staged epilogues of the short-K shapes (qkv, the proj dgrad, ...) with two warpgroups give one of
+  // their two staging slots per warp to the pipeline: 4 x 48 KB stages hold a whole K = 256 tile (wait accounting: the MMA
+  // warp of the qkv GEMM waited for operands 38 % of its time with both epilogue warpgroups idle half of theirs):
+  // qkv 126.0 -> 123.6 us, the K = 256 plain dgrads 56.4 -> 53.1 us per 262144 rows; sc_debug_set("one_slot", 0) = off
+  if (!fused_ln && nwg == 2 && slots == 2 && p.epi_mode == EPI_OUT1 && !p.ln_split && g_dbg.one_slot != 0) slots = 1;
   // output-only staged epilogues with two warpgroups: column split as an option (sc_debug_set("col_split", 1 | 2)); off:
   // on the whole step it is neutral (gemm_fwd 6.708 vs 6.705 ms, dgrad 1.96 vs 2.00 ms)
   // (measured: the one-output shapes gain 2-5 %; the two-output fc1 epilogue waits for its own stores at every chunk and
@@ -1579,7 +1587,7 @@ extern "C" int sc_gemm_bf16(const void* A, const void* B, int64_t M, int64_t N, 
     p.ln_split = 1;
 #define SC_LAUNCH1(AM, BMJ, C2, W, S) launch<AM, BMJ, C2, W, S>(tmA, tmB, tmOut, tmAux, tmIn, p, grid, st)
 #define SC_LAUNCH(AM, BMJ)                                                                          \
-  (nwg == 2 ? (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 2, 4) : SC_LAUNCH1(AM, BMJ, 0, 2, 2))           \
+  (nwg == 2 ? (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 2, 4) : (slots == 1 ? SC_LAUNCH1(AM, BMJ, 0, 2, 1) : SC_LAUNCH1(AM, BMJ, 0, 2, 2))) \
             : (slots == 4 ? SC_LAUNCH1(AM, BMJ, 0, 1, 4) : SC_LAUNCH1(AM, BMJ, 0, 1, 2)))
 #define SC_LAUNCH_PAIR(AM, BMJ) (nwg == 2 ? SC_LAUNCH1(AM, BMJ, 1, 2, 2) : SC_LAUNCH1(AM, BMJ, 1, 1, 2))
 #define SC_LAUNCH_MCB(AM, BMJ)                                                                      \

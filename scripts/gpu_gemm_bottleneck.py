@@ -45,6 +45,8 @@ def make(shape_name):
                     kw=lambda: dict(aux_in=g(M, 1024)))
     if shape_name == "dgrad_fc1":  # dx = dhpre W1
         return dict(M=M, N=256, K=1024, A=lambda: g(M, 1024), B=g(1024, 256), b_mn=True, kw=lambda: dict())
+    if shape_name == "dgrad_proj":  # dao = dx1 W_proj: K = 256, plain bf16 output
+        return dict(M=M, N=256, K=256, A=lambda: g(M, 256), B=g(256, 256), b_mn=True, kw=lambda: dict())
     if shape_name == "dgrad_qkv":  # dxn1 = dqkv W_qkv: K = 768
         return dict(M=M, N=256, K=768, A=lambda: g(M, 768), B=g(768, 256), b_mn=True, kw=lambda: dict())
     if shape_name == "sym":        # symbol projection: [M,256] x [16,256]^T + bias -> fp32 [M,16]

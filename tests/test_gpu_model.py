@@ -250,6 +250,7 @@ def test_forward_matches_committed_golden_vectors(cuda_lib):
 @pytest.mark.parametrize("name,switches", [
     ("single-CTA wgrads", {"cta2_wgrad": 0}),
     ("single-CTA long-K dgrads", {"cta2_mink": 0}),
+    ("two staging slots / three stages for the output-only short-K epilogues", {"one_slot": 0}),
     ("one-warpgroup fused LayerNorm", {"ln_split": 0}),
     ("split fused LayerNorm on every K", {"ln_split": 2}),
     ("fused-MLP backward without weight multicast", {"mlp_dbg": 4}),
@@ -271,7 +272,7 @@ def test_schedule_switches_preserve_results(cuda_lib, name, switches):
     B = 256
     mb = synthetic.minibatch(SPEC, B, seed=21, device="cuda")
     defaults = {"cta2_wgrad": 1, "ln_split": 1, "mlp_dbg": 0, "pdl": 0, "alternate": 0, "gemm_dbg": 0, "mcb": 0, "col_split": 0,
-                "cta2_mink": 512}
+                "cta2_mink": 512, "one_slot": 1}
 
     def run(sw):
         for k, v in {**defaults, **{k: v for k, v in sw.items() if k in defaults}}.items():
