@@ -354,11 +354,12 @@ class Engine:
 
     # ---- forward --------------------------------------------------------------------------
     def forward(self, cam, bev, snr_db, channel, seed, noise, fading, sample_offset, train, want_aux=False,
-                seed_dev=None, row_idx=None, sample_idx=None, arena=None):
+                seed_dev=None, row_idx=None, sample_idx=None, arena=None, need_recon=True):
         """row_idx (int64 [B], optional): the step's samples are rows row_idx of cam / bev (the minibatch gather is fused
         into the patchify pass).  sample_idx (int64 [B], optional): global sample index of every local sample for the
         channel's noise counters (default sample_offset + b).  arena: the activation arena to use (default: the shared
-        arena of this batch size)."""
+        arena of this batch size).  need_recon=False skips the reconstruction head (act(): only the actor-critic outputs
+        are needed, L_sem is not)."""
         sp, f = self.spec, self.flat
         B = cam.shape[0] if row_idx is None else row_idx.numel()
         A = arena if arena is not None else self.arena(B)
@@ -416,8 +417,9 @@ class Engine:
             self._block_fwd(A, f"dec.blocks.{l}", xd[l], xd[l + 1], B, Sd, train, xn1_ready=fuse_ln, next_ln=nxt)
         tn = final_ln["y"]
         feat = ops.meanpool_fwd(tn.view(B, Sd, D), out_bf16=A.buf("dec.f", (B, D)))
-        recon = A.buf("dec.recon", (Md, D))
-        ops.gemm(tn, f.w16("dec.recon.weight"), bias=f.w32("dec.recon.bias"), out=recon)
+        if need_recon:
+            recon = A.buf("dec.recon", (Md, D))
+            ops.gemm(tn, f.w16("dec.recon.weight"), bias=f.w32("dec.recon.bias"), out=recon)
         # ---- heads ----
         trunk = A.buf("ac.trunk", (B, D))
         ops.gemm(feat, f.w16("ac.trunk.weight"), bias=f.w32("ac.trunk.bias"), act="tanh", out=trunk)

@@ -134,7 +134,7 @@ class GraphedAct:
     def _body(self):
         pol, sp = self.policy, self.policy.spec
         ho, _ = pol.engine.forward(self.cam, self.bev, self.snr_db, self.channel, self.seed, None, None, 0,
-                                   train=False, seed_dev=self.counter)
+                                   train=False, seed_dev=self.counter, need_recon=False)
         self._ops.sample_action(ho, self.u, sp.n_actions, action=self.action, logp=self.logp)
         self.value.copy_(ho[:, sp.n_actions])
         self.counter.add_(1)
