@@ -749,8 +749,7 @@ extern "C" int sc_mlp_bwd_dgrad(const void* dy, const void* w1, const void* w2, 
   // mlp_dbg bit 32 (opt-in): the CTA-pair kernel (cta_group::2, mlp_bwd_pair.cu) — the leader issues every MMA once for both
   // 128-row tiles, each CTA stages half of every weight tile, three hidden buffers.  Bit-identical results, but 6 % SLOWER
   // (388 vs 367 us per 262144 tokens, profiles/r2_mlp_wait_accounting.txt): with the MMA warp no longer pacing the kernel the
-  // epilogue warps' chunk math takes twice as long (they share the SM's shared-memory bandwidth with MMAs that now run
-  // back to back: a 128 x 128 x 16 MMA alone reads 8 KB per 64 clk = the full 128 B/clk).
+  // epilogue warps' chunk math takes twice as long (they contend with MMAs that now run back to back).
   if ((g_mlp_dbg & 32) && M > BM)
     return sc_mlp_bwd_pair_launch(dy, w1, w2, hpre, dhpre, dx, M, R, g_mlp_dbg, static_cast<cudaStream_t>(stream));
   MlpParams p;
