@@ -476,8 +476,13 @@ def run_native(a):
     if ar_ms is not None:
         line["allreduce_ms"] = ar_ms
         line["allreduce"] = {"ms": ar_ms, "bytes": pol.flat.numel * 4, "share_of_step": ar_ms / (ms_total / a.steps),
-                             "what": "CUDA events around the NCCL all-reduce of the flat fp32 gradient bucket in one eager step right after the timed "
-                                     "region, rank 0 (includes waiting for the slowest rank to finish its backward)"}
+                             "impl": "peer" if ag._fused is not None else "nccl",
+                             "what": ("CUDA events around sc_dp_barrier + sc_dp_reduce_adam + sc_dp_barrier (gradient reduce-scatter, "
+                                      "sharded Adam and parameter all-gather over NVLink peer memory: the optimizer is INSIDE this time)"
+                                      if ag._fused is not None else
+                                      "CUDA events around the NCCL all-reduce of the flat fp32 gradient bucket") +
+                                     " in one eager step right after the timed region, rank 0 (includes waiting for the slowest rank "
+                                     "to finish its backward)"}
     if upd:
         line["update_e2e"] = upd
     if secondary:

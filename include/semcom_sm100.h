@@ -31,7 +31,7 @@ extern "C" {
 #define SC_E_LAUNCH (-4)
 #define SC_E_DRIVER (-5)
 
-#define SC_ABI_VERSION 3
+#define SC_ABI_VERSION 4
 
 /* channel kinds (SPEC v0 a4) */
 #define SC_CH_NONE 0
@@ -265,6 +265,46 @@ int sc_snr_embed_fwd(const float* snr_db, float snr_db_scalar, const float* u, c
                      float* emb, float* h, int64_t B, int D, int E, void* stream);
 int sc_snr_embed_bwd(const float* demb, const float* h, const float* snr_db, float snr_db_scalar, const float* W,
                      float* dW, float* du, float* dv, float demb_scale, int64_t B, int D, int E, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * SURVEY.md 8e / 8f rank 2 (ABI version 4): the data-parallel gradient exchange FUSED with the optimizer, over
+ * NVLink peer memory instead of an NCCL all-reduce followed by sc_adam_flat.
+ *
+ * Every rank (one process per GPU) keeps its flat fp32 gradient bucket, fp32 master parameters and bf16 shadow in
+ * PEER memory: allocated by sc_peer_alloc (plain cudaMalloc, not a pool, so it can be exported), exported as a
+ * 64-byte handle (cudaIpcMemHandle_t), exchanged by the host (torch.distributed.all_gather_object) and mapped by
+ * every other rank with sc_peer_import.  One optimizer step is then
+ *
+ *     sc_dp_barrier      every rank's backward is complete (its gradients are final, nobody reads parameters)
+ *     sc_dp_reduce_adam  rank r owns slice r of the flat bucket (contiguous, 4-float granularity): it READS that slice
+ *                        of every rank's gradients through NVLink, sums them in rank order 0..world-1 (every rank holds
+ *                        bit-identical parameters afterwards), applies Adam with ITS moments (m / v are only
+ *                        maintained for the own slice: optimizer state is sharded) and WRITES the updated fp32
+ *                        parameters and the bf16 shadow of the slice into every rank's buffers
+ *     sc_dp_barrier      every rank's writes have landed (parameters complete, gradient buckets may be zeroed)
+ *
+ * = reduce-scatter + sharded Adam + all-gather in one pass over the bucket; per rank (world - 1) / world of the
+ * bucket crosses NVLink as loads and 1.5 x that as stores.  All three launches are CUDA-graph capturable.
+ * These five sc_peer_* helpers are the only entry points that allocate or map memory.
+ *
+ * flags: peer memory, SC_DP_MAX_WORLD uint64 per rank, zero-initialised; flags[p] (host array of `world` DEVICE
+ * pointers, entry `rank` being the local buffer) is rank p's flag array as mapped into this process.  epoch: local
+ * device int64, zero-initialised, advanced by every barrier (all ranks call the same sequence of barriers).
+ * A barrier that is not completed within ~20 s traps (the launch fails instead of hanging the GPU). */
+#define SC_DP_MAX_WORLD 16
+#define SC_PEER_HANDLE_BYTES 64
+int sc_peer_alloc(void** ptr, int64_t bytes);                 /* zero-filled; device-synchronous */
+int sc_peer_free(void* ptr);
+int sc_peer_export(const void* ptr, void* handle);            /* handle: SC_PEER_HANDLE_BYTES host bytes */
+int sc_peer_import(const void* handle, void** ptr);           /* maps another PROCESS's allocation */
+int sc_peer_close(void* ptr);
+int sc_dp_barrier(void* const* flags, int64_t* epoch, int world, int rank, void* stream);
+/* g32 / p32 / p16: host arrays of `world` device pointers (entry `rank` = the local buffers); m, v local, n floats
+ * each (n % 4 == 0).  step / step_dev as in sc_adam_flat.  max_ctas > 0 caps the grid (tests that run two ranks on
+ * one device). */
+int sc_dp_reduce_adam(const void* const* g32, void* const* p32, void* const* p16, float* m, float* v, int world,
+                      int rank, int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                      const int64_t* step_dev, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

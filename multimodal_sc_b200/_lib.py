@@ -12,8 +12,11 @@ import torch
 
 LIB_PATH = Path(__file__).resolve().parent / "libsemcom_sm100.so"
 
-ABI_VERSION = 3          # SC_ABI_VERSION in include/semcom_sm100.h (3: index arguments for the fused minibatch gather /
-                         # ragged data-parallel slices, quantised symbols, SNR embedding, erf GELU, sc_step_begin)
+ABI_VERSION = 4          # SC_ABI_VERSION in include/semcom_sm100.h (3: index arguments for the fused minibatch gather /
+                         # ragged data-parallel slices, quantised symbols, SNR embedding, erf GELU, sc_step_begin;
+                         # 4: peer-memory helpers, sc_dp_barrier, sc_dp_reduce_adam)
+SC_DP_MAX_WORLD = 16
+SC_PEER_HANDLE_BYTES = 64
 SC_CH = {"none": 0, "awgn": 1, "rayleigh": 2, "rician": 3}
 SC_ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2, "gelu_erf": 3}
 
@@ -88,6 +91,14 @@ _PROTOS = {
     "sc_step_begin": [_P, _I64, _P, _I, _P, _P],
     "sc_snr_embed_fwd": [_P, _F, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_snr_embed_bwd": [_P, _P, _P, _F, _P, _P, _P, _P, _F, _I64, _I, _I, _P],
+    "sc_peer_alloc": [C.POINTER(C.c_void_p), _I64],
+    "sc_peer_free": [_P],
+    "sc_peer_export": [_P, _P],
+    "sc_peer_import": [_P, C.POINTER(C.c_void_p)],
+    "sc_peer_close": [_P],
+    "sc_dp_barrier": [C.POINTER(C.c_void_p), _P, _I, _I, _P],
+    "sc_dp_reduce_adam": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _I, _I, _I64,
+                          _F, _F, _F, _F, _I64, _P, _I, _P],
 }
 _RESTYPES = {"sc_last_error": C.c_char_p, "sc_launch_count": C.c_int64}
 

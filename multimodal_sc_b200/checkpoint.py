@@ -26,6 +26,8 @@ def to_state(agent) -> dict:
     model = {k: v.detach().to("cpu", torch.float32).clone() for k, v in pol.state_dict().items()}
     if _is_native(agent):
         flat = pol.flat
+        if getattr(agent, "_fused", None) is not None:           # sharded optimizer state: complete it first (collective)
+            agent._fused.gather_moments()
         m = {n: flat._view(flat.m, n).detach().to("cpu").clone() for n in flat.shapes}
         v = {n: flat._view(flat.v, n).detach().to("cpu").clone() for n in flat.shapes}
         opt_step = int(agent.step_count)

@@ -526,6 +526,22 @@ __device__ __forceinline__ float gelu_bwd(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
 
+// one element of torch.optim.Adam (arithmetic order of the foreach implementation, lerp form for the first moment);
+// shared by sc_adam_flat and the peer-memory reduce + Adam kernel so both paths round identically
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float step_size, float b1, float b2,
+                                            float eps, float inv_sqrt_bc2) {
+  m = m + (1.f - b1) * (g - m);
+  v = b2 * v + (1.f - b2) * g * g;
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+  p = p - step_size * (m / denom);
+}
+// bias corrections of step t, recomputed in double like the host does (device-side step counters: CUDA-graph replays)
+__device__ __forceinline__ void adam_bias_corrections(double t, float lr, float b1, float b2, float& step_size,
+                                                      float& inv_sqrt_bc2) {
+  step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), t)));
+  inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), t)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -469,9 +469,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     // bias corrections
     __shared__ float bc[2];
     if (threadIdx.x == 0) {
-      const double t = static_cast<double>(step + *step_dev);
-      bc[0] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), t)));
-      bc[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), t)));
+      adam_bias_corrections(static_cast<double>(step + *step_dev), lr, b1, b2, bc[0], bc[1]);
     }
     __syncthreads();
     step_size = bc[0];
@@ -487,11 +485,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     float* P = &pp.x; float* G = &gg.x; float* Mo = &mm.x; float* V = &vv.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float gs = G[j] * grad_scale;
-      Mo[j] = Mo[j] + (1.f - b1) * (gs - Mo[j]);            // lerp form used by torch
-      V[j] = b2 * V[j] + (1.f - b2) * gs * gs;
-      const float denom = sqrtf(V[j]) * inv_sqrt_bc2 + eps;
-      P[j] = P[j] - step_size * (Mo[j] / denom);
+      adam_update(P[j], G[j] * grad_scale, Mo[j], V[j], step_size, b1, b2, eps, inv_sqrt_bc2);
     }
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
@@ -500,10 +494,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = n4 * 4 + threadIdx.x;
-    const float gs = g[i] * grad_scale;
-    const float mo = m[i] + (1.f - b1) * (gs - m[i]);
-    const float vo = b2 * v[i] + (1.f - b2) * gs * gs;
-    const float po = p[i] - step_size * (mo / (sqrtf(vo) * inv_sqrt_bc2 + eps));
+    float mo = m[i], vo = v[i], po = p[i];
+    adam_update(po, g[i] * grad_scale, mo, vo, step_size, b1, b2, eps, inv_sqrt_bc2);
     m[i] = mo; v[i] = vo; p[i] = po;
     if (pb) pb[i] = __float2bfloat16(po);
   }

@@ -70,7 +70,10 @@ class FlatParams:
     """flat fp32 master / bf16 shadow / fp32 grad / Adam moments; 256-byte aligned slots."""
     ALIGN = 64   # elements
 
-    def __init__(self, spec: SpecV0, device):
+    def __init__(self, spec: SpecV0, device, peer: bool = False):
+        """peer=True: gradients, master parameters and the bf16 shadow live in exportable device memory
+        (peer.peer_empty) so that the other ranks of a data-parallel job can map them (peer.PeerReduceAdam)."""
+        self.peer = bool(peer)
         self.shapes = param_shapes(spec)
         self.offsets = OrderedDict()
         off = 0
@@ -82,9 +85,15 @@ class FlatParams:
             off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = off
         self._views = {}
-        self.p32 = torch.zeros(off, device=device, dtype=F32)
-        self.p16 = torch.zeros(off, device=device, dtype=BF16)
-        self.g32 = torch.zeros(off, device=device, dtype=F32)
+        if self.peer:
+            from .peer import peer_empty
+            self.p32 = peer_empty(off, F32, device)
+            self.p16 = peer_empty(off, BF16, device)
+            self.g32 = peer_empty(off, F32, device)
+        else:
+            self.p32 = torch.zeros(off, device=device, dtype=F32)
+            self.p16 = torch.zeros(off, device=device, dtype=BF16)
+            self.g32 = torch.zeros(off, device=device, dtype=F32)
         self.m = torch.zeros(off, device=device, dtype=F32)
         self.v = torch.zeros(off, device=device, dtype=F32)
 
@@ -568,12 +577,20 @@ class _PolicyFn(torch.autograd.Function):
 
 
 class SemComPolicy(nn.Module):
-    def __init__(self, spec: SpecV0 = SpecV0(), device=None, init_std: float | None = None, seed: int = 0):
+    def __init__(self, spec: SpecV0 = SpecV0(), device=None, init_std: float | None = None, seed: int = 0,
+                 peer: bool | None = None):
+        """peer: keep the flat parameter / gradient buckets in NVLink peer memory (the fused data-parallel optimizer
+        step, peer.PeerReduceAdam, maps them into the other ranks).  Default: on when torch.distributed runs with more
+        than one rank on the NCCL backend (one process per GPU) and SC_DP_FUSED is not 0."""
         super().__init__()
         _lib.require_device()
         self.spec = spec
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.flat = FlatParams(spec, self.device)
+        if peer is None:
+            import torch.distributed as dist
+            peer = (os.environ.get("SC_DP_FUSED", "1") != "0" and dist.is_available() and dist.is_initialized()
+                    and dist.get_world_size() > 1 and dist.get_backend() == "nccl")
+        self.flat = FlatParams(spec, self.device, peer=peer)
         _init_flat(self.flat, spec, spec.init_std if init_std is None else init_std, seed)
         self.engine = Engine(spec, self.flat, self.device)
         for name in self.flat.shapes:                       # nested parameter tree -> oracle state_dict keys

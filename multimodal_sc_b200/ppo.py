@@ -5,8 +5,12 @@ Drop-in for `oracle/ppo.py: PPOAgent` (same constructor arguments, `update(rollo
 trainer).  One optimizer step is a fixed kernel schedule on the current stream:
 
     sc_step_begin (zero flat grad + stats, step counter) -> Engine.forward -> sc_mse_fwd_bwd -> sc_ppo_loss -> Engine.backward
-      -> [NCCL all-reduce of the flat fp32 bucket, data-parallel only; SC_DP_OVERLAP=1 launches it in three regions,
-          each as soon as backward has finished writing it] -> sc_adam_flat
+      -> one rank:       sc_adam_flat
+         data parallel:  sc_dp_barrier -> sc_dp_reduce_adam -> sc_dp_barrier   (peer.PeerReduceAdam: reduce-scatter +
+                         sharded Adam + all-gather in one pass over NVLink peer memory; default when the policy's buckets
+                         are in peer memory)
+         or              NCCL all-reduce of the flat fp32 bucket -> sc_adam_flat   (fused_dp=False / SC_DP_FUSED=0;
+                         SC_DP_OVERLAP=1 launches the all-reduce in three regions as backward finishes writing them)
 
 Data parallelism: every rank holds whole trajectories; the only data-path
 collectives are the flat-gradient all-reduce (one per optimizer step) and a 2-double all-reduce
@@ -62,7 +66,8 @@ class HostMinibatchFeeder:
 
 class PPOAgent:
     def __init__(self, policy: SemComPolicy, spec: SpecV0 = SpecV0(), *, epochs: int = 1, minibatch: int = 4096,
-                 snr_db: float = 10.0, channel: str = "awgn", seed: int = 1234, process_group=None):
+                 snr_db: float = 10.0, channel: str = "awgn", seed: int = 1234, process_group=None,
+                 fused_dp: bool | None = None):
         self.policy, self.spec = policy, spec
         self.epochs, self.minibatch = epochs, minibatch
         self.snr_db, self.channel, self.seed = snr_db, channel, seed
@@ -86,6 +91,17 @@ class PPOAgent:
         # opt-in: measured 2 % SLOWER at 2 GPUs (21.6 -> 22.0-22.3 ms): the NCCL kernels take SMs away from the
         # persistent one-CTA-per-SM GEMMs, whose displaced CTAs then run as a second wave (profiles/README.md)
         self.overlap_allreduce = os.environ.get("SC_DP_OVERLAP", "0") != "0"
+        # data parallel: gradient exchange fused with the optimizer over peer memory (default whenever the policy's flat
+        # buckets are in peer memory, i.e. it was built under an initialised NCCL process group); construction is a collective
+        if fused_dp is None:
+            fused_dp = self.world > 1 and policy.flat.peer and not self.overlap_allreduce
+        self._fused = None
+        if fused_dp and self.world > 1:
+            from .peer import PeerReduceAdam
+            cache = policy.flat.__dict__.setdefault("_peer_reducers", {})    # one mapping per (buckets, group): a second
+            if id(process_group) not in cache:                               # agent on the same policy reuses it
+                cache[id(process_group)] = PeerReduceAdam(policy.flat, process_group)
+            self._fused = cache[id(process_group)]
         self._lsem_weight = 1.0 / self.world                     # this rank's share of the global-minibatch mean L_sem
         self.last_perms = []                                     # permutations / per-minibatch statistics of the last
         self.last_step_stats = []                                #   update() (parity tests)
@@ -155,6 +171,17 @@ class PPOAgent:
         if timed:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
+        if self._fused is not None:
+            # barrier -> reduce-scatter + sharded Adam + all-gather over peer memory -> barrier (three launches)
+            if device_counters:
+                self._fused.step(sp.lr, sp.beta1, sp.beta2, sp.adam_eps, 0, step_dev=self.dev_step)
+            else:
+                self._fused.step(sp.lr, sp.beta1, sp.beta2, sp.adam_eps, self.step_count + 1)
+                self.step_count += 1
+            if timed:
+                ev1.record()
+                self.allreduce_events = (ev0, ev1)
+            return
         if ov is not None:
             ov.finish()
         else:

@@ -39,7 +39,7 @@ def test_header_symbols_exported(built):
 
 def test_version_and_no_fallback(built):
     lib = _lib.load()
-    assert lib.sc_version() == _lib.ABI_VERSION == 3
+    assert lib.sc_version() == _lib.ABI_VERSION == 4
     if not torch.cuda.is_available():
         assert lib.sc_device_ok() == -3                       # SC_E_ARCH: no device -> refuse
         assert "no CUDA device" in _lib.last_error() or "sm_100" in _lib.last_error()
