@@ -208,6 +208,24 @@ class Engine:
         # deterministic=True: weight gradients without split-K (one red.add per element, in stream order) — a debug /
         # test mode; the default split-K wgrads add their K-slices in arbitrary order (fp32 rounding-level run-to-run noise)
         self.deterministic = os.environ.get("SC_DETERMINISTIC", "0") != "0"
+        # Small batches (cfg2, cfg4, act()): every kernel is a single wave that is bound by its own ramp-up and tail,
+        # not by data (profiles/README.md).  The two encoders are independent until the channel, so the LiDAR-BEV encoder
+        # runs on a second stream (a parallel branch of the CUDA graph when the forward is captured): one encoder's CTAs
+        # fill the SMs the other's tail leaves idle and no kernel waits for a launch gap; backward does the same with
+        # per-encoder scratch buffers.  Measured (profiles/r2_enc_overlap_ab.json): forward B = 256 0.73 -> 0.65 ms as a
+        # graph, B = 1024 +5 %; nothing to gain at B = 4096, where it stays off.  SC_ENC_OVERLAP=0 turns it off.
+        self.enc_overlap = os.environ.get("SC_ENC_OVERLAP", "1") != "0"
+        self.enc_overlap_max_batch = int(os.environ.get("SC_ENC_OVERLAP_MAX_BATCH", "1024"))
+        self._enc_stream = None
+
+    def _enc_side_stream(self, B: int):
+        """the second encoder stream, or None when this forward keeps both encoders on the current stream"""
+        if (not self.enc_overlap or B > self.enc_overlap_max_batch or ops._PROF is not None
+                or self.wgrad_stream is not None):
+            return None
+        if self._enc_stream is None:
+            self._enc_stream = torch.cuda.Stream(self.device)
+        return self._enc_stream
 
     def arena(self, B: int, cap: int = 0) -> _Arena:
         """the shared arena of batch size B, or (cap >= B) the capacity arena for up to `cap` samples"""
@@ -314,13 +332,14 @@ class Engine:
         if next_ln is not None and not fuse_ln:
             self._run_ln(x_out, next_ln)
 
-    def _block_bwd(self, A, pfx, x_in, dx_out, dx_in, prev_bias_grad, B, S):
+    def _block_bwd(self, A, pfx, x_in, dx_out, dx_in, prev_bias_grad, B, S, tag=""):
         """dx_out: grad wrt block output [M,D] (its column sums were already added to fc2.bias grad by the
         producer).  Writes dx_in; adds colsum(dx_in) to `prev_bias_grad` (bias of whatever produced x_in)."""
         sp, f = self.spec, self.flat
         M, D, H = x_in.shape[0], sp.d_model, sp.n_heads
         k = lambda n: A[f"{pfx}.{n}"]
-        s = lambda n, shape, dt=BF16: A.buf(f"scratch.{n}.S{shape[0] // B}", shape, dt)   # shared across blocks of one width
+        # scratch is shared across the blocks of one width (`tag` separates encoders that run on two streams)
+        s = lambda n, shape, dt=BF16: A.buf(f"scratch{tag}.{n}.S{shape[0] // B}", shape, dt)
         side = self._side_on()
         # With the wgrads on the side stream, the buffers they read (dhpre, dx1, dqkv) alternate between two scratch
         # sets by block parity, and the side stream never lags by more than one block: LN1-backward of block j (the
@@ -361,6 +380,38 @@ class Engine:
                           f.g(f"{pfx}.ln1.weight"), f.g(f"{pfx}.ln1.bias"), dres=dx1, dx=dx_in,
                           colsum=prev_bias_grad)
 
+    def _encoder_fwd(self, A, mi, enc, img, patch, B, S, z_mm, snr_db, train, row_idx):
+        """one modality encoder: patchify -> patch embedding (+ LN) -> blocks -> final norm -> symbol projection into z_mm[mi]"""
+        sp, f = self.spec, self.flat
+        D, C = sp.d_model, sp.c_sym
+        M = B * S
+        tok = ops.patchify(img, patch, out=A.buf(f"{enc}.tok", (M, img.shape[1] * patch * patch)), row_idx=row_idx)
+        xs = [A.buf(f"{enc}.x{l}", (M, D)) for l in range(sp.enc_layers + 1)]
+        fuse_ln = self.fused_ln and D == 256
+        # every LayerNorm rides on the epilogue of the GEMM that produces its input: the patch embedding feeds
+        # block 0's LN1, each block's fc2 feeds the next block's LN1 / the final norm
+        if sp.snr_cond:
+            # SNR-conditioned encoder: the per-sample embedding rides on the row-group add of the epilogue (the same
+            # path the mean-pool backward uses); that epilogue kind has no fused LayerNorm, so block 0's LN1 runs
+            # as its own kernel
+            emb, _ = ops.snr_embed_fwd(snr_db, f.w32(f"{enc}.snr.u"), f.w32(f"{enc}.snr.v"), f.w32(f"{enc}.snr.w"), B,
+                                       emb=A.buf(f"{enc}.snr_emb", (B, D), F32),
+                                       h=A.buf(f"{enc}.snr_h", (B, sp.snr_embed_dim), F32))
+            ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
+                     rowadd=f.w16(f"{enc}.pos"), rowgrp=emb, rowgrp_size=S, rowgrp_scale=1.0, out=xs[0])
+            if fuse_ln:
+                self._run_ln(xs[0], self._block_ln1(A, f"{enc}.blocks.0", M))
+        else:
+            ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
+                     rowadd=f.w16(f"{enc}.pos"), out=xs[0],
+                     ln=self._block_ln1(A, f"{enc}.blocks.0", M) if fuse_ln else None)
+        final_ln = self._ln_spec(A, f"{enc}.norm", M, f"{enc}.t", f"{enc}.mean", f"{enc}.rstd")
+        for l in range(sp.enc_layers):
+            nxt = self._block_ln1(A, f"{enc}.blocks.{l + 1}", M) if l + 1 < sp.enc_layers else final_ln
+            self._block_fwd(A, f"{enc}.blocks.{l}", xs[l], xs[l + 1], B, S, train, xn1_ready=fuse_ln, next_ln=nxt)
+        t = final_ln["y"]
+        ops.gemm(t, f.w16(f"{enc}.sym.weight"), bias=f.w32(f"{enc}.sym.bias"), out_f32=z_mm[mi].view(M, C))
+
     # ---- forward --------------------------------------------------------------------------
     def forward(self, cam, bev, snr_db, channel, seed, noise, fading, sample_offset, train, want_aux=False,
                 seed_dev=None, row_idx=None, sample_idx=None, arena=None, need_recon=True):
@@ -377,34 +428,20 @@ class Engine:
         D, S, C = sp.d_model, sp.cam_tokens, sp.c_sym
         k_sym = sp.k_sym
         z_mm = A.buf("z_mm", (2, B, k_sym), F32)                       # modality-major symbols
-        for mi, (enc, img, patch) in enumerate((("cam_enc", cam, sp.cam_patch), ("bev_enc", bev, sp.bev_patch))):
-            M = B * S
-            tok = ops.patchify(img, patch, out=A.buf(f"{enc}.tok", (M, img.shape[1] * patch * patch)), row_idx=row_idx)
-            xs = [A.buf(f"{enc}.x{l}", (M, D)) for l in range(sp.enc_layers + 1)]
-            fuse_ln = self.fused_ln and D == 256
-            # every LayerNorm rides on the epilogue of the GEMM that produces its input: the patch embedding feeds
-            # block 0's LN1, each block's fc2 feeds the next block's LN1 / the final norm
-            if sp.snr_cond:
-                # SNR-conditioned encoder: the per-sample embedding rides on the row-group add of the epilogue (the same
-                # path the mean-pool backward uses); that epilogue kind has no fused LayerNorm, so block 0's LN1 runs
-                # as its own kernel
-                emb, _ = ops.snr_embed_fwd(snr_db, f.w32(f"{enc}.snr.u"), f.w32(f"{enc}.snr.v"), f.w32(f"{enc}.snr.w"), B,
-                                           emb=A.buf(f"{enc}.snr_emb", (B, D), F32),
-                                           h=A.buf(f"{enc}.snr_h", (B, sp.snr_embed_dim), F32))
-                ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
-                         rowadd=f.w16(f"{enc}.pos"), rowgrp=emb, rowgrp_size=S, rowgrp_scale=1.0, out=xs[0])
-                if fuse_ln:
-                    self._run_ln(xs[0], self._block_ln1(A, f"{enc}.blocks.0", M))
-            else:
-                ops.gemm(tok, f.w16(f"{enc}.patch_embed.weight"), bias=f.w32(f"{enc}.patch_embed.bias"),
-                         rowadd=f.w16(f"{enc}.pos"), out=xs[0],
-                         ln=self._block_ln1(A, f"{enc}.blocks.0", M) if fuse_ln else None)
-            final_ln = self._ln_spec(A, f"{enc}.norm", M, f"{enc}.t", f"{enc}.mean", f"{enc}.rstd")
-            for l in range(sp.enc_layers):
-                nxt = self._block_ln1(A, f"{enc}.blocks.{l + 1}", M) if l + 1 < sp.enc_layers else final_ln
-                self._block_fwd(A, f"{enc}.blocks.{l}", xs[l], xs[l + 1], B, S, train, xn1_ready=fuse_ln, next_ln=nxt)
-            t = final_ln["y"]
-            ops.gemm(t, f.w16(f"{enc}.sym.weight"), bias=f.w32(f"{enc}.sym.bias"), out_f32=z_mm[mi].view(M, C))
+        side = self._enc_side_stream(B)
+        main = torch.cuda.current_stream(self.device)
+        if side is not None:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)                                      # inputs / earlier work of this stream are visible
+        # (the BEV encoder goes first so that, eagerly, its launches are already queued when the camera's start)
+        for mi, (enc, img, patch) in ((1, ("bev_enc", bev, sp.bev_patch)), (0, ("cam_enc", cam, sp.cam_patch))):
+            with torch.cuda.stream(side if (side is not None and mi == 1) else main):
+                self._encoder_fwd(A, mi, enc, img, patch, B, S, z_mm, snr_db, train, row_idx)
+        if side is not None:
+            join = torch.cuda.Event()
+            join.record(side)
+            main.wait_event(join)
         # ---- channel ----
         y16 = A.buf("y16", (B, 2, k_sym))
         y32 = A.buf("y32", (B, 2, k_sym), F32) if want_aux else None
@@ -489,33 +526,50 @@ class Engine:
                               sample_offset=sample_offset, fading=fading, dz_bf16=dz_mm,
                               z_strides=(sp.k_sym, B * sp.k_sym, B, sp.k_sym), seed_dev=seed_dev, sample_idx=sample_idx,
                               quant_bits=sp.quant_bits, quant_clip=sp.quant_clip)
-        # encoders
-        M = B * S
-        for mi, enc in enumerate(("cam_enc", "bev_enc")):
-            dz = dz_mm[mi].view(M, C)
-            dt = A.buf("scratch.dxn.S%d" % S, (M, D))
-            self._linear_bwd(dz, A[f"{enc}.t"], f"{enc}.sym", dx=dt)
-            Le = sp.enc_layers
-            dxa = A.buf("scratch.dxa.S%d" % S, (M, D))
-            dxb = A.buf("scratch.dxb.S%d" % S, (M, D))
-            ops.layernorm_bwd(dt, A[f"{enc}.x{Le}"], A[f"{enc}.mean"], A[f"{enc}.rstd"], f.w32(f"{enc}.norm.weight"),
-                              f.g(f"{enc}.norm.weight"), f.g(f"{enc}.norm.bias"), dx=dxa,
-                              colsum=f.g(f"{enc}.blocks.{Le - 1}.fc2.bias"))
-            cur, nxt = dxa, dxb
-            for l in range(Le - 1, -1, -1):
-                prev_bias = f.g(f"{enc}.blocks.{l - 1}.fc2.bias") if l > 0 else f.g(f"{enc}.patch_embed.bias")
-                self._block_bwd(A, f"{enc}.blocks.{l}", A[f"{enc}.x{l}"], cur, nxt, prev_bias, B, S)
-                cur, nxt = nxt, cur
-            ops.colsum(cur.view(B, S * D), f.g(f"{enc}.pos").view(-1))
-            if sp.snr_cond:               # d emb[b] = sum over the sample's tokens of d x0 (mean-pool x S), then the tiny MLP
-                demb = ops.meanpool_fwd(cur.view(B, S, D), out_f32=A.buf(f"{enc}.snr_demb", (B, D), F32))
-                ops.snr_embed_bwd(demb, A[f"{enc}.snr_h"], snr_db, f.w32(f"{enc}.snr.w"), f.g(f"{enc}.snr.w"),
-                                  f.g(f"{enc}.snr.u"), f.g(f"{enc}.snr.v"), demb_scale=float(S))
-            self._linear_bwd(cur, A[f"{enc}.tok"], f"{enc}.patch_embed", bias_colsum=False)
+        # encoders (independent of each other: on two streams for small batches, see Engine.__init__)
+        side = self._enc_side_stream(B) if grad_ready is None else None
+        main = torch.cuda.current_stream(self.device)
+        if side is not None:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+        for mi, enc in ((1, "bev_enc"), (0, "cam_enc")) if side is not None else ((0, "cam_enc"), (1, "bev_enc")):
+            with torch.cuda.stream(side if (side is not None and mi == 1) else main):
+                self._encoder_bwd(A, mi, enc, B, dz_mm, snr_db, tag=".bev" if (side is not None and mi == 1) else "")
             if grad_ready is not None:
                 self._join_side()
                 grad_ready(enc)
+        if side is not None:
+            join = torch.cuda.Event()
+            join.record(side)
+            main.wait_event(join)
         self._join_side()                         # the flat gradient bucket is complete on the current stream
+
+    def _encoder_bwd(self, A, mi, enc, B, dz_mm, snr_db, tag=""):
+        """backward of one modality encoder from d z_mm[mi]; `tag` names its own scratch set (two-stream backward)"""
+        sp, f = self.spec, self.flat
+        D, S, C = sp.d_model, sp.cam_tokens, sp.c_sym
+        M = B * S
+        dz = dz_mm[mi].view(M, C)
+        dt = A.buf("scratch%s.dxn.S%d" % (tag, S), (M, D))
+        self._linear_bwd(dz, A[f"{enc}.t"], f"{enc}.sym", dx=dt)
+        Le = sp.enc_layers
+        dxa = A.buf("scratch%s.dxa.S%d" % (tag, S), (M, D))
+        dxb = A.buf("scratch%s.dxb.S%d" % (tag, S), (M, D))
+        ops.layernorm_bwd(dt, A[f"{enc}.x{Le}"], A[f"{enc}.mean"], A[f"{enc}.rstd"], f.w32(f"{enc}.norm.weight"),
+                          f.g(f"{enc}.norm.weight"), f.g(f"{enc}.norm.bias"), dx=dxa,
+                          colsum=f.g(f"{enc}.blocks.{Le - 1}.fc2.bias"))
+        cur, nxt = dxa, dxb
+        for l in range(Le - 1, -1, -1):
+            prev_bias = f.g(f"{enc}.blocks.{l - 1}.fc2.bias") if l > 0 else f.g(f"{enc}.patch_embed.bias")
+            self._block_bwd(A, f"{enc}.blocks.{l}", A[f"{enc}.x{l}"], cur, nxt, prev_bias, B, S, tag=tag)
+            cur, nxt = nxt, cur
+        ops.colsum(cur.view(B, S * D), f.g(f"{enc}.pos").view(-1))
+        if sp.snr_cond:               # d emb[b] = sum over the sample's tokens of d x0 (mean-pool x S), then the tiny MLP
+            demb = ops.meanpool_fwd(cur.view(B, S, D), out_f32=A.buf(f"{enc}.snr_demb", (B, D), F32))
+            ops.snr_embed_bwd(demb, A[f"{enc}.snr_h"], snr_db, f.w32(f"{enc}.snr.w"), f.g(f"{enc}.snr.w"),
+                              f.g(f"{enc}.snr.u"), f.g(f"{enc}.snr.v"), demb_scale=float(S))
+        self._linear_bwd(cur, A[f"{enc}.tok"], f"{enc}.patch_embed", bias_colsum=False)
 
     def _join_side(self):
         if self._side_done:
