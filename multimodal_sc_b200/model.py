@@ -223,6 +223,8 @@ class Engine:
         if (not self.enc_overlap or B > self.enc_overlap_max_batch or ops._PROF is not None
                 or self.wgrad_stream is not None):
             return None
+        if B < 128 and not torch.cuda.is_current_stream_capturing():
+            return None            # eagerly these sizes are bound by the host's launch rate: two more events per pass cost 10 %
         if self._enc_stream is None:
             self._enc_stream = torch.cuda.Stream(self.device)
         return self._enc_stream

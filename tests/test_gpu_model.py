@@ -261,6 +261,7 @@ def test_forward_matches_committed_golden_vectors(cuda_lib):
     ("weight tiles shared by CTA clusters (multicast)", {"mcb": 1}),
     ("column-split epilogue for one-output GEMMs", {"col_split": 1}),
     ("column-split epilogue also for two outputs", {"col_split": 2}),
+    ("both encoders on one stream (the default at this size is two)", {"single_encoder_stream": 1}),
 ])
 def test_schedule_switches_preserve_results(cuda_lib, name, switches):
     """Every schedule / kernel-variant switch of the library (profiles/README.md, negative-results table) computes the
@@ -280,6 +281,10 @@ def test_schedule_switches_preserve_results(cuda_lib, name, switches):
         pol = SemComPolicy(SPEC, seed=0)
         if sw.get("side_stream"):
             pol.engine.wgrad_stream = torch.cuda.Stream()
+        if sw.get("single_encoder_stream"):
+            pol.engine.enc_overlap = False
+        else:
+            assert pol.engine._enc_side_stream(B) is not None or sw.get("side_stream")
         ag = PPOAgent(pol, SPEC, minibatch=B, seed=5)
         grads = {}
         orig = ops.adam_flat
