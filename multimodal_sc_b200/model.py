@@ -213,9 +213,10 @@ class Engine:
         # runs on a second stream (a parallel branch of the CUDA graph when the forward is captured): one encoder's CTAs
         # fill the SMs the other's tail leaves idle and no kernel waits for a launch gap; backward does the same with
         # per-encoder scratch buffers.  Measured (profiles/r2_enc_overlap_ab.json): forward B = 256 0.73 -> 0.65 ms as a
-        # graph, B = 1024 +5 %; nothing to gain at B = 4096, where it stays off.  SC_ENC_OVERLAP=0 turns it off.
+        # graph, B = 1024 +5 %, the 4096-sample PPO step +0.4 % (same-box A/B, twice); above 4096 samples it stays off (the
+        # second scratch set costs 1.6 GB per 4096 samples).  SC_ENC_OVERLAP=0 turns it off.
         self.enc_overlap = os.environ.get("SC_ENC_OVERLAP", "1") != "0"
-        self.enc_overlap_max_batch = int(os.environ.get("SC_ENC_OVERLAP_MAX_BATCH", "1024"))
+        self.enc_overlap_max_batch = int(os.environ.get("SC_ENC_OVERLAP_MAX_BATCH", "4096"))
         self._enc_stream = None
 
     def _enc_side_stream(self, B: int):

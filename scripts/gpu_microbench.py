@@ -95,5 +95,17 @@ n = 5165866 // 4 * 4
 p_, g_, m_, v_ = (torch.randn(n, device="cuda") for _ in range(4)); pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
 s = t(lambda: ops.adam_flat(p_, g_, m_.abs_(), v_.abs_(), pb, 3e-4, 0.9, 0.999, 1e-8, 3))
 rec("adam_flat_5.17M", s, n * 30)
+# the peer-memory reduce + Adam kernel with every "rank" on this device (local HBM side of the kernel only: the NVLink side is
+# measured on two / eight GPUs by scripts/gpu_dp_fused_check.py): world = 1 moves the same 30 B per element as adam_flat
+import ctypes as C
+from multimodal_sc_b200 import _lib
+from multimodal_sc_b200.peer import preload_kernels
+preload_kernels("cuda")
+arr = lambda *ts: (C.c_void_p * len(ts))(*[x.data_ptr() for x in ts])
+lib = _lib.load()
+st = torch.cuda.current_stream().cuda_stream
+s = t(lambda: _lib.check(lib.sc_dp_reduce_adam(arr(g_), arr(p_), arr(pb), m_.abs_().data_ptr(), v_.abs_().data_ptr(), 1, 0, n,
+                                               3e-4, 0.9, 0.999, 1e-8, 3, None, 0, st)))
+rec("dp_reduce_adam_world1_5.17M", s, n * 30)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/microbench.json", "w"), indent=1)
