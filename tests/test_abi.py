@@ -72,3 +72,17 @@ def test_flat_bucket_layout():
         assert fp.w32(name).data_ptr() == fp.p32.data_ptr() + 4 * off
         assert fp.w16(name).data_ptr() % 16 == 0                    # TMA base alignment of the bf16 shadow
     assert fp.numel >= prev_end
+
+
+def test_peer_memory_has_no_host_fallback(built):
+    """peer.py: exportable device memory and the fused data-parallel optimizer step exist on the GPU only"""
+    from multimodal_sc_b200 import peer
+    with pytest.raises(_lib.SemcomError):
+        peer.peer_empty(16, torch.float32, "cpu")
+    assert not peer.is_peer(torch.zeros(4))
+    # the slice rule of sc_dp_reduce_adam (4-float granularity) is dp.shard_bounds on n / 4
+    from multimodal_sc_b200 import dp
+    n4, world = 1291504, 8
+    cover = [dp.shard_bounds(n4, world, r) for r in range(world)]
+    assert cover[0][0] == 0 and cover[-1][1] == n4 and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+
