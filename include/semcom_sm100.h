@@ -250,6 +250,14 @@ int sc_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int
 
 int sc_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* a10 (PPOAgent.update): dst[i, :] = src[idx[i], :], rows of row_bytes (multiple of 16; idx NULL = plain copy).  src may
+ * be PINNED HOST memory (unified addressing): the kernel is then the host -> device transfer of one minibatch — only its
+ * rows cross PCIe, in permutation order, on a side stream while the previous optimizer step computes.  Grid: up to one
+ * CTA of 512 threads per SM, max_ctas > 0 caps it (16 saturate PCIe and displace the fewest CTAs of a step running
+ * beside it).  Indices outside [0, src_rows) leave their destination row untouched. */
+int sc_gather_rows(const void* src, int64_t src_rows, int64_t row_bytes, const int64_t* idx, void* dst, int64_t n_rows,
+                   int max_ctas, void* stream);
+
 /* a10: first kernel of an optimizer step: zero the flat gradient bucket (n floats, n % 4 == 0) and the statistics
  * vector (n_stats floats), and advance the device-side step counter (*step_dev += 1, optional) that the channel seed
  * and Adam's bias correction read inside a captured CUDA graph — one launch instead of two memsets and an add. */

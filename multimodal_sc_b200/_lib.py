@@ -89,6 +89,7 @@ _PROTOS = {
     "sc_adam_flat": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P, _P],
     "sc_cast_f32_bf16": [_P, _P, _I64, _P],
     "sc_step_begin": [_P, _I64, _P, _I, _P, _P],
+    "sc_gather_rows": [_P, _I64, _I64, _P, _P, _I64, _I, _P],
     "sc_snr_embed_fwd": [_P, _F, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_snr_embed_bwd": [_P, _P, _P, _F, _P, _P, _P, _P, _F, _I64, _I, _I, _P],
     "sc_peer_alloc": [C.POINTER(C.c_void_p), _I64],

@@ -456,6 +456,46 @@ cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// row gather (a10, PPOAgent.update): dst[i, :] = src[idx[i], :] for rows of row_bytes (multiple of 16).  src may be
+// PINNED HOST memory (unified addressing): the kernel then IS the host -> device transfer of the minibatch — only the rows
+// of this minibatch cross PCIe, in permutation order, while the previous optimizer step still computes.  Measured
+// (scripts/gpu_gather_bw.py, gpu_gather_overlap.py): 51 GB/s alone (cudaMemcpyAsync of the same bytes: 55 GB/s) with as
+// few as 8 CTAs of 512 threads, four 16-byte loads per thread in flight.  Beside the PPO step it costs that step ~1 ms
+// whatever the grid: the 384-thread GEMM variants use the whole register file (168 x 384), so an SM that hosts a gather
+// CTA runs its GEMM CTA as a second wave — hence FEW fat CTAs for a SHORT time (callers pass max_ctas = 16) rather than
+// one thin CTA per SM (148 x 128 threads: +4.4 ms on the step).
+// ------------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 512;
+__global__ void __launch_bounds__(kGatherThreads)
+gather_rows_kernel(const uint4* __restrict__ src, const int64_t* __restrict__ idx, uint4* __restrict__ dst,
+                   int64_t n_rows, int64_t units_per_row, int64_t src_rows) {
+  pdl_sync();
+  const int64_t total = n_rows * units_per_row;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t u0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; u0 < total; u0 += 4 * stride) {
+    uint4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t u = u0 + j * stride;
+      ok[j] = u < total;
+      if (ok[j]) {
+        const int64_t r = u / units_per_row, c = u - r * units_per_row;
+        const int64_t sr = idx ? idx[r] : r;
+        ok[j] = sr >= 0 && sr < src_rows;                          // an out-of-range index leaves the row untouched
+        if (ok[j]) asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
+                                : "l"(src + sr * units_per_row + c));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ok[j]) dst[u0 + j * stride] = v[j];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -614,6 +654,25 @@ int sc_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
   sc_launch_kernel(cast_kernel, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, src, (bf16*)dst, n);
   sc_count_launch(1);
   SC_CHECK_LAUNCH("sc_cast_f32_bf16");
+  return SC_OK;
+}
+
+int sc_gather_rows(const void* src, int64_t src_rows, int64_t row_bytes, const int64_t* idx, void* dst, int64_t n_rows,
+                   int max_ctas, void* stream) {
+  int rc = sc_check_device();
+  if (rc != SC_OK) return rc;
+  SC_REQUIRE(src && dst && n_rows > 0 && src_rows > 0 && row_bytes > 0 && row_bytes % 16 == 0, SC_E_SHAPE,
+             "sc_gather_rows: n_rows=%lld src_rows=%lld row_bytes=%lld", (long long)n_rows, (long long)src_rows,
+             (long long)row_bytes);
+  SC_REQUIRE(sc_aligned16(src) && sc_aligned16(dst), SC_E_ALIGN, "sc_gather_rows: unaligned pointer");
+  const int64_t units = row_bytes / 16;
+  int64_t blocks = (n_rows * units + 4 * kGatherThreads - 1) / (4 * kGatherThreads);
+  const int64_t cap = max_ctas > 0 ? max_ctas : sc_num_sms();
+  if (blocks > cap) blocks = cap;
+  sc_launch_kernel(gather_rows_kernel, dim3((unsigned)blocks), dim3(kGatherThreads), 0, (cudaStream_t)stream,
+                   static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst), n_rows, units, src_rows);
+  sc_count_launch(1);
+  SC_CHECK_LAUNCH("sc_gather_rows");
   return SC_OK;
 }
 

@@ -120,6 +120,7 @@ _ALGO_BYTES = {
     "ppo_loss": lambda a, k, r: _nbytes(a[0]) * 2 + a[0].shape[0] * 20,
     "adam_flat": lambda a, k, r: a[0].numel() * 30,
     "step_begin": lambda a, k, r: _nbytes(a[0]),
+    "gather_rows": lambda a, k, r: 2 * _nbytes(a[2]),
 }
 
 
@@ -521,6 +522,23 @@ def step_begin(grad, stats, step_dev=None):
         assert step_dev.dtype == torch.int64 and step_dev.is_cuda
     check(_lib.load().sc_step_begin(ptr(grad), grad.numel(), ptr(stats), stats.numel(), ptr(step_dev), stream_ptr(grad)),
           "sc_step_begin")
+
+
+@_profiled("gather_rows")
+def gather_rows(src, idx, out, max_ctas: int = 0):
+    """out[i] = src[idx[i]] over the leading dimension (idx int64 on the device, or None = copy).  `src` may live in PINNED
+    host memory: the kernel then pulls exactly the minibatch's rows over PCIe (PPOAgent.update's host -> device path)."""
+    _cuda(out)
+    if not (src.is_cuda or src.is_pinned()):
+        raise _lib.SemcomError("gather_rows: the source must be device or pinned host memory")
+    assert src.is_contiguous() and out.is_contiguous() and src.dtype == out.dtype and src.shape[1:] == out.shape[1:]
+    n = out.shape[0]
+    if idx is not None:
+        assert idx.is_cuda and idx.dtype == torch.int64 and idx.numel() == n
+    row_bytes = src[0].numel() * src.element_size()
+    check(_lib.load().sc_gather_rows(src.data_ptr(), src.shape[0], row_bytes, ptr(idx), out.data_ptr(), n, max_ctas,
+                                     stream_ptr(out)), "sc_gather_rows")
+    return out
 
 
 @_profiled("snr_embed_fwd")

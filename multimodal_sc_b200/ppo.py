@@ -112,7 +112,7 @@ class PPOAgent:
     # ---- one optimizer step on one (local) minibatch ---------------------------------------------
     def minibatch_step(self, cam, bev, actions, logp_old, adv, values_unused, ret, sample_offset: int = 0,
                        sync_stats: bool = True, graph: bool = False, *, row_idx=None, sample_idx=None,
-                       global_batch: int | None = None, arena_cap: int = 0):
+                       global_batch: int | None = None, arena_cap: int = 0, obs_gathered: bool = False):
         """cam/bev fp32 or bf16, actions int64, logp_old/adv/ret fp32 — all on the policy's device.
         With world_size > 1 the arguments are this rank's shard of the global minibatch and
         `sample_offset` is its first global sample index (noise counters are global).
@@ -123,19 +123,21 @@ class PPOAgent:
         persistent device buffers (HostMinibatchFeeder slots); the caller keeps those buffers alive.
         row_idx (int64 [B], device): the minibatch is rows row_idx of the given tensors (whole-rollout storage) — the
         gather is fused into the first kernels (sc_patchify_bf16, sc_ppo_loss), no gathered copy is made.
+        obs_gathered=True: cam / bev already hold exactly the B rows of this minibatch (update() streams them from pinned
+        host memory with sc_gather_rows); row_idx then only indexes actions / logp_old / adv / ret.
         sample_idx (int64 [B], device) + global_batch: this rank's samples sit at positions sample_idx of a global
         minibatch of `global_batch` samples (ragged data-parallel slices of update())."""
         if graph and row_idx is None and sample_idx is None and (self.world == 1 or not self.overlap_allreduce):
             return self._graphed_step(cam, bev, actions, logp_old, adv, ret, sample_offset, sync_stats,
                                       inplace=(graph == "inplace"))
         self._step_body(cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters=False, row_idx=row_idx,
-                        sample_idx=sample_idx, global_batch=global_batch, arena_cap=arena_cap)
+                        sample_idx=sample_idx, global_batch=global_batch, arena_cap=arena_cap, obs_gathered=obs_gathered)
         if not sync_stats:
             return None
         return self.read_stats()
 
     def _step_body(self, cam, bev, actions, logp_old, adv, ret, sample_offset, device_counters: bool, row_idx=None,
-                   sample_idx=None, global_batch=None, arena_cap: int = 0):
+                   sample_idx=None, global_batch=None, arena_cap: int = 0, obs_gathered: bool = False):
         """the kernel schedule of one optimizer step.  device_counters=True: seed and Adam step come from
         self.dev_step inside the kernels (graph capture / replay), otherwise from the host's step_count."""
         sp, pol = self.spec, self.policy
@@ -154,8 +156,10 @@ class PPOAgent:
         ov = self._overlap if (self.world > 1 and self.overlap_allreduce) else None
         if Bl > 0:
             arena = eng.arena(Bl, cap=arena_cap) if arena_cap else None
+            if obs_gathered:
+                assert cam.shape[0] == Bl and bev.shape[0] == Bl, (cam.shape, bev.shape, Bl)
             ho, A = eng.forward(cam, bev, self.snr_db, self.channel, seed, None, None, sample_offset, train=True,
-                                seed_dev=sdev, row_idx=row_idx, sample_idx=sample_idx, arena=arena)
+                                seed_dev=sdev, row_idx=None if obs_gathered else row_idx, sample_idx=sample_idx, arena=arena)
             eng.l_sem(A, Bl, self.stats[5:6], grad_coef=sem_coef)
             dho = A.buf("ac.dho", tuple(ho.shape), F32)
             ops.ppo_loss(ho, actions, logp_old, adv, ret, sp.n_actions, sp.clip_eps, sp.c_v, sp.c_ent, inv_m,
@@ -232,16 +236,25 @@ class PPOAgent:
             return None
         return self.read_stats()
 
-    def read_stats(self) -> dict:
+    def _stats_snapshot(self) -> torch.Tensor:
+        """device copy of this step's statistics, this rank's L_sem already weighted by its share of the global minibatch
+        (so that a SUM over ranks gives the global-minibatch means); no host synchronisation"""
         st = self.stats.clone()
         if self.world > 1:
             st[5] *= self._lsem_weight
-            torch.distributed.all_reduce(st, group=self.pg)
-        s = st.cpu().tolist()                                     # the step's device->host read
+        return st
+
+    def _stats_dict(self, s) -> dict:
         out = {"pi": s[0], "v": s[1], "ent": s[2], "kl": s[3], "clipfrac": s[4], "l_sem": s[5]}
         sp = self.spec
         out["total"] = out["pi"] + sp.c_v * out["v"] - sp.c_ent * out["ent"] + sp.c_sem * out["l_sem"]
         return out
+
+    def read_stats(self) -> dict:
+        st = self._stats_snapshot()
+        if self.world > 1:
+            torch.distributed.all_reduce(st, group=self.pg)
+        return self._stats_dict(st.cpu().tolist())                # the step's device->host read
 
     def allreduce_ms(self):
         """device time of the last gradient all-reduce (None on one rank); synchronises"""
@@ -260,6 +273,53 @@ class PPOAgent:
         ops.adv_normalize(adv, self.sums, count, sp.adv_eps)
         return adv, ret
 
+    def _update_streamed(self, steps, cam_host, bev_host, act, lp, adv, ret, mb, cap, snaps):
+        """update()'s optimizer steps with the observations streamed from pinned host memory: the rows of step j + 1 are
+        gathered over PCIe (sc_gather_rows, side stream, 16 CTAs) into the other staging slot while step j
+        runs; events order slot reuse in both directions."""
+        dev = self.policy.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_obs_stream", None) is None:
+            self._obs_stream, self._obs_stage = torch.cuda.Stream(dev), {}
+        cs = self._obs_stream
+        rows_max = max(nr for _, _, nr in steps)
+        key = (rows_max, cam_host.dtype, tuple(cam_host.shape[1:]), bev_host.dtype, tuple(bev_host.shape[1:]))
+        if self._obs_stage.get("key") != key:
+            self._obs_stage = {"key": key, "slots": [
+                (torch.empty((rows_max, *cam_host.shape[1:]), dtype=cam_host.dtype, device=dev),
+                 torch.empty((rows_max, *bev_host.shape[1:]), dtype=bev_host.dtype, device=dev)) for _ in range(2)]}
+        slots = self._obs_stage["slots"]
+        idx_ready = torch.cuda.Event()
+        idx_ready.record(main)                                    # the index uploads were enqueued on this stream
+        cs.wait_event(idx_ready)
+        ready, free = [None, None], [None, None]
+
+        def prefetch(j):
+            rows_d, _, nr = steps[j]
+            k = j & 1
+            with torch.cuda.stream(cs):
+                if free[k] is not None:
+                    cs.wait_event(free[k])                        # the step that read this slot has finished with it
+                if nr > 0:
+                    # 16 CTAs saturate PCIe; more would only displace more GEMM CTAs of the step running beside it
+                    ops.gather_rows(cam_host, rows_d, slots[k][0][:nr], max_ctas=16)
+                    ops.gather_rows(bev_host, rows_d, slots[k][1][:nr], max_ctas=16)
+                ready[k] = torch.cuda.Event()
+                ready[k].record(cs)
+
+        prefetch(0)
+        for j, (rows_d, pos_d, nr) in enumerate(steps):
+            k = j & 1
+            if j + 1 < len(steps):
+                prefetch(j + 1)                                   # queued before this step's launches: runs beside them
+            main.wait_event(ready[k])
+            self.minibatch_step(slots[k][0][:nr], slots[k][1][:nr], act, lp, adv, None, ret, sample_offset=0,
+                                row_idx=rows_d, sample_idx=pos_d, global_batch=mb, arena_cap=cap, sync_stats=False,
+                                obs_gathered=True)
+            free[k] = torch.cuda.Event()
+            free[k].record(main)
+            snaps.append(self._stats_snapshot())
+
     # ---- full update over a rollout ----------------------------------------------------------------
     def update(self, rollout: dict) -> dict:
         """rollout: this rank's trajectories (whole environments; dict of [T, N_local, ...] tensors, host or device).
@@ -269,8 +329,10 @@ class PPOAgent:
         draws the SAME global permutation and processes, of each global minibatch, the samples whose environment it
         owns, at their global positions for the noise counters — so the N-rank update equals the 1-rank update on the
         concatenated rollout (tests/test_dp_gloo.py, scripts/gpu_dp_check.py).
-        The observations go to the device once; minibatches are never materialised: the gather by `perm` is fused into
-        sc_patchify_bf16 / sc_ppo_loss (row-index argument)."""
+        Device-resident or pageable observations go to the device once and minibatches are never materialised: the gather
+        by `perm` is fused into sc_patchify_bf16 / sc_ppo_loss (row-index argument).  Observations in pinned host memory are
+        streamed instead: each minibatch's rows cross PCIe (sc_gather_rows) while the previous step computes.
+        Statistics are read back once, after the last step."""
         dev = self.policy.device
         to = lambda x, dt=F32: x.to(dev, dt, non_blocking=True).contiguous()
         rewards, values, dones = to(rollout["rewards"]), to(rollout["values"]), to(rollout["dones"])
@@ -278,28 +340,55 @@ class PPOAgent:
         adv, ret = self.compute_advantages(rewards, values, dones, to(rollout["last_value"]))
         n = T * N
         obs_dt = lambda x: x.dtype if x.dtype == torch.bfloat16 else F32
-        cam_h = to(rollout["cam"], obs_dt(rollout["cam"])).reshape(n, *rollout["cam"].shape[2:])
-        bev_h = to(rollout["bev"], obs_dt(rollout["bev"])).reshape(n, *rollout["bev"].shape[2:])
+        # Observations in PINNED host memory are not copied wholesale: every minibatch's rows are pulled over PCIe by
+        # sc_gather_rows on a side stream while the previous optimizer step computes (double-buffered staging), so the
+        # transfer of the rollout (872 MB for 8192 samples, ~16 ms of PCIe) leaves the critical path except for the
+        # first minibatch.  SC_UPDATE_STREAM=0, pageable or device-resident rollouts: one copy up front, the gather fused
+        # into sc_patchify_bf16.
+        stream_obs = (os.environ.get("SC_UPDATE_STREAM", "1") != "0" and
+                      all((not rollout[k].is_cuda) and rollout[k].is_pinned() and rollout[k].is_contiguous() and
+                          rollout[k].dtype in (torch.bfloat16, F32) for k in ("cam", "bev")))
+        if stream_obs:
+            cam_h = rollout["cam"].view(n, *rollout["cam"].shape[2:])
+            bev_h = rollout["bev"].view(n, *rollout["bev"].shape[2:])
+        else:
+            cam_h = to(rollout["cam"], obs_dt(rollout["cam"])).reshape(n, *rollout["cam"].shape[2:])
+            bev_h = to(rollout["bev"], obs_dt(rollout["bev"])).reshape(n, *rollout["bev"].shape[2:])
         act = to(rollout["actions"], torch.int64).reshape(n)
         lp = to(rollout["logp"]).reshape(n)
         adv, ret = adv.reshape(n), ret.reshape(n)
         env_lo, n_envs_global = dp.env_shard(N, self.pg)
         n_global = T * n_envs_global
         mb = min(self.minibatch, n_global)                         # `minibatch` is the GLOBAL minibatch on any world size
-        tot, cnt = {}, 0
+        tot, cnt, snaps = {}, 0, []
         self.last_perms, self.last_step_stats = [], []
+        steps, cap = [], 0
         for _ in range(self.epochs):
             perm = torch.randperm(n_global, generator=self.gen)    # host, seeded: bit-exact with the oracle
             self.last_perms.append(perm)
             slices = [dp.local_minibatch_indices(perm[i:i + mb], n_envs_global, env_lo, N)
                       for i in range(0, n_global - mb + 1, mb)]
-            # one capacity arena for the ragged local slices of this epoch (exact-size arena on one rank)
-            cap = 0 if self.world == 1 else (max(int(r.numel()) for r, _ in slices) + 255) // 256 * 256
-            for rows, pos in slices:
-                rows_d = rows.to(dev, non_blocking=True)
-                pos_d = None if self.world == 1 else pos.to(dev, non_blocking=True)
-                s = self.minibatch_step(cam_h, bev_h, act, lp, adv, None, ret, sample_offset=0, row_idx=rows_d,
-                                        sample_idx=pos_d, global_batch=mb, arena_cap=cap)
+            # one capacity arena for the ragged local slices of the update (exact-size arena on one rank)
+            if self.world > 1:
+                cap = max(cap, (max(int(r.numel()) for r, _ in slices) + 255) // 256 * 256)
+            # the index vectors go to the device up front and the per-minibatch statistics stay there until the update is
+            # over: no host round trip between optimizer steps (a per-step read leaves the GPU idle while the host
+            # enqueues the next step's ~130 launches)
+            steps += [(rows.to(dev, non_blocking=True), None if self.world == 1 else pos.to(dev, non_blocking=True),
+                       int(rows.numel())) for rows, pos in slices]
+        if stream_obs and steps:
+            self._update_streamed(steps, cam_h, bev_h, act, lp, adv, ret, mb, cap, snaps)
+        else:
+            for rows_d, pos_d, _ in steps:
+                self.minibatch_step(cam_h, bev_h, act, lp, adv, None, ret, sample_offset=0, row_idx=rows_d,
+                                    sample_idx=pos_d, global_batch=mb, arena_cap=cap, sync_stats=False)
+                snaps.append(self._stats_snapshot())
+        if snaps:
+            S = torch.stack(snaps)
+            if self.world > 1:
+                torch.distributed.all_reduce(S, group=self.pg)    # one small all-reduce per update, not one per step
+            for row in S.cpu().tolist():                          # the update's only device->host read
+                s = self._stats_dict(row)
                 self.last_step_stats.append(s)
                 for k, v in s.items():
                     tot[k] = tot.get(k, 0.0) + v

@@ -397,3 +397,58 @@ def test_rank_without_samples_still_steps(cuda_lib):
     ag2 = PPOAgent(pol, SPEC, minibatch=3, epochs=2, seed=1)
     ag2.update(ro)
     assert ag2.step_count == 4 and len(ag2.last_step_stats) == 4
+
+
+def test_gather_rows_from_device_and_pinned_host(cuda_lib):
+    """sc_gather_rows: dst[i] = src[idx[i]] for device and pinned-host sources (the PCIe path of update()), bit-exact;
+    out-of-range indices leave their rows untouched"""
+    from multimodal_sc_b200 import _lib, ops
+    g = torch.Generator().manual_seed(3)
+    for shape, dt in [((37, 3, 16, 24), torch.bfloat16), ((129, 8), torch.float32), ((5, 1, 64, 64), torch.bfloat16)]:
+        src = torch.randn(shape, generator=g).to(dt)
+        idx = torch.randint(0, shape[0], (53,), generator=g)
+        ref = src[idx]
+        for s_ in (src.cuda(), src.pin_memory()):
+            out = torch.zeros((53, *shape[1:]), dtype=dt, device="cuda")
+            ops.gather_rows(s_, idx.cuda(), out)
+            torch.cuda.synchronize()
+            assert torch.equal(out.cpu(), ref)
+            out2 = torch.zeros((shape[0], *shape[1:]), dtype=dt, device="cuda")
+            ops.gather_rows(s_, None, out2)                       # idx = None: plain copy
+            assert torch.equal(out2.cpu(), src)
+    bad = torch.tensor([0, 99, -1, 2]).cuda()
+    out = torch.full((4, 8), 7.0, device="cuda")
+    ops.gather_rows(src := torch.arange(40, dtype=torch.float32).view(5, 8).cuda(), bad, out)
+    assert torch.equal(out[0], src[0]) and torch.equal(out[3], src[2]) and bool((out[1:3] == 7.0).all())
+    with pytest.raises(_lib.SemcomError):
+        ops.gather_rows(torch.zeros(4, 8), None, torch.zeros(4, 8, device="cuda"))      # pageable host memory
+
+
+def test_update_streamed_from_pinned_host_equals_update_from_device(cuda_lib):
+    """update() with the rollout in PINNED host memory (observation rows pulled over PCIe per minibatch, double-buffered,
+    one step ahead) == update() with the rollout on the device (gather fused into patchify): same permutations, the
+    first step's statistics equal up to summation order, all steps within the bf16 tolerance; 2 epochs x 4 minibatches"""
+    from multimodal_sc_b200 import synthetic
+    from multimodal_sc_b200.model import SemComPolicy
+    from multimodal_sc_b200.ppo import PPOAgent
+    T, N = 8, 8
+    ro = synthetic.rollout(SPEC, T, N, seed=13)
+    runs = []
+    for mode in ("device", "pinned"):
+        pol = SemComPolicy(SPEC, seed=0)
+        ag = PPOAgent(pol, SPEC, minibatch=16, epochs=2, seed=5, channel="rayleigh", snr_db=3.0)
+        r = {k: (v.cuda() if mode == "device" else v.pin_memory()) for k, v in ro.items()}
+        st = ag.update(r)
+        torch.cuda.synchronize()
+        assert (getattr(ag, "_obs_stream", None) is not None) == (mode == "pinned")
+        runs.append((ag.last_perms, ag.last_step_stats, st, pol.flat.p32.clone(), ag.step_count))
+    (p0, s0, u0, w0, c0), (p1, s1, u1, w1, c1) = runs
+    assert c0 == c1 == 8 and len(s0) == len(s1) == 8
+    assert all(torch.equal(a, b) for a, b in zip(p0, p1))
+    for k in ("pi", "v", "ent", "kl", "l_sem", "total"):
+        assert abs(s0[0][k] - s1[0][k]) <= 1e-5 * max(abs(s0[0][k]), 0.05), (k, s0[0][k], s1[0][k])
+        for a, b in zip(s0, s1):
+            assert abs(a[k] - b[k]) <= 2e-2 * max(abs(a[k]), 0.05), (k, a[k], b[k])
+    d = (w0 - w1).abs()
+    assert float((d > 0.02 * SPEC.lr).float().mean()) < 0.02, float((d > 0.02 * SPEC.lr).float().mean())
+
