@@ -465,15 +465,27 @@ class Engine:
             nxt = self._block_ln1(A, f"dec.blocks.{l + 1}", Md) if l + 1 < sp.dec_layers else final_ln
             self._block_fwd(A, f"dec.blocks.{l}", xd[l], xd[l + 1], B, Sd, train, xn1_ready=fuse_ln, next_ln=nxt)
         tn = final_ln["y"]
-        feat = ops.meanpool_fwd(tn.view(B, Sd, D), out_bf16=A.buf("dec.f", (B, D)))
+        # the reconstruction head and the mean-pool -> trunk -> heads chain both start from tn and are independent: with the
+        # second stream available the three small launches of the chain run beside / in the tail of the recon GEMM
         if need_recon:
             recon = A.buf("dec.recon", (Md, D))
-            ops.gemm(tn, f.w16("dec.recon.weight"), bias=f.w32("dec.recon.bias"), out=recon)
+            if side is not None:
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
+            with torch.cuda.stream(side if side is not None else main):
+                ops.gemm(tn, f.w16("dec.recon.weight"), bias=f.w32("dec.recon.bias"), out=recon)
+                if side is not None:
+                    join = torch.cuda.Event()
+                    join.record(side)
+        feat = ops.meanpool_fwd(tn.view(B, Sd, D), out_bf16=A.buf("dec.f", (B, D)))
         # ---- heads ----
         trunk = A.buf("ac.trunk", (B, D))
         ops.gemm(feat, f.w16("ac.trunk.weight"), bias=f.w32("ac.trunk.bias"), act="tanh", out=trunk)
         ho = ops.heads_fwd(trunk, f.w32("ac.head.weight"), f.w32("ac.head.bias"),
                            out=A.buf("ac.ho", (B, sp.n_actions + 1), F32))
+        if need_recon and side is not None:
+            main.wait_event(join)
         return ho, A
 
     def l_sem(self, A, B, loss_accum, grad_coef=None):
