@@ -127,6 +127,13 @@ int sc_mlp_fwd(const void* x, const void* w1, const float* b1, const void* w2, c
                const void* resid, void* hpre, void* h, void* out, int64_t M, int D, int R, void* stream);
 int sc_mlp_bwd_dgrad(const void* dy, const void* w1, const void* w2, const void* hpre, void* dhpre, void* dx,
                      int64_t M, int D, int R, void* stream);
+/* inference form of sc_mlp_fwd (no hpre / h saves) with the LayerNorm that consumes the block's output fused into the
+ * output epilogue: out = resid + W2 gelu(W1 x + b1) + b2 and ln_out = LayerNorm(out) * gamma + beta (statistics of the
+ * bf16-rounded out, like sc_layernorm_fwd on the stored tensor; ln_mean / ln_rstd fp32 [M], optional) — one launch less per
+ * transformer block where launches, not bytes, set the pace (cfg2, act()). */
+int sc_mlp_fwd_ln(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const void* resid,
+                  void* out, const float* ln_gamma, const float* ln_beta, float ln_eps, void* ln_out, float* ln_mean,
+                  float* ln_rstd, int64_t M, int D, int R, void* stream);
 
 /* test hook: override UMMA descriptor fields (0 = library default). Not for product use. */
 int sc_debug_set(const char* key, int64_t value);

@@ -66,6 +66,7 @@ _PROTOS = {
     "sc_gemm_bf16": [_P, _P, _I64, _I64, _I64, _I, _I, _I64, _I64, C.POINTER(GemmEpilogue), _I, _P],
     "sc_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
+    "sc_mlp_fwd_ln": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I64, _I, _I, _P],
     "sc_attn_fwd": [_P, _P, _P, _I64, _I, _I, _P],
     "sc_attn_bwd": [_P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "sc_patchify_bf16": [_P, _I, _P, _I64, _I, _I, _I, _I, _P, _P],

@@ -58,6 +58,14 @@ struct MlpParams {
   const bf16* resid;         // fwd, optional
   bf16* hpre;                // fwd, optional: pre-activation copy [M, R]
   bf16* out;                 // fwd: out [M, 256];  bwd: dx [M, 256]
+  // fwd, optional (inference form, no h / hpre saves): LayerNorm of the output row as a second output — the LayerNorm that
+  // consumes the block's output (next block's LN1 / the stack's final norm) rides on this kernel instead of its own launch
+  const float* ln_gamma;
+  const float* ln_beta;
+  bf16* ln_out;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
   int store_h;               // fwd: h is saved (TMA store from the operand buffer);  bwd: always 1 (dhpre)
   int reverse;               // 1 = row tiles are walked in descending order
   int dbg;                   // sc_debug_set("mlp_dbg", bits): 1 / 2 = L2 prefetch variants (negative), 4 = no weight multicast
@@ -606,6 +614,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
           }
         };
+        // fused LayerNorm (forward, p.ln_out): pass 1 below also accumulates sum x / sum x^2 of the bf16-rounded values of
+        // this warpgroup's 128 columns; the partial sums of a row are exchanged with the partner warpgroup through the
+        // first 2 KB of the hidden-chunk operand buffers (free between the tile's last GEMM2 — acc2_full — and the next
+        // tile's first chunk epilogue, which every warpgroup only starts after its own pass 2); pass 2 re-reads the
+        // accumulator from TMEM (it is only released afterwards), redoes + b2 + residual and writes LN(x).
+        const bool do_ln = !BWD && p.ln_out != nullptr;
+        uint64_t s1 = 0ull, s2 = 0ull;                        // packed (0.f, 0.f)
+        if (do_ln) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(hbuf + wg_tid * 4), "f"(__ldg(p.ln_gamma + wg * 128 + wg_tid)) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(hbuf + 512 + wg_tid * 4), "f"(__ldg(p.ln_beta + wg * 128 + wg_tid)) : "memory");
+        }
         auto process = [&](int s, const uint32_t (&vv)[16], const float4 (&bb)[4], const uint4 (&ii)[2]) {
           uint64_t x[8];
 #pragma unroll
@@ -618,10 +637,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               x[2 * qd + 1] = add2(add2(x[2 * qd + 1], pk2(bb[qd].z, bb[qd].w)), unpack2_bf16(iw[2 * qd + 1]));
             }
           }
-          if (row_ok) {
-            uint32_t o[8];
+          uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = pack2_bf16(x[i]);
+          for (int i = 0; i < 8; ++i) o[i] = pack2_bf16(x[i]);
+          if (do_ln) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint64_t xr = unpack2_bf16(o[i]);
+              s1 = add2(s1, xr);
+              s2 = fma2(xr, xr, s2);
+            }
+          }
+          if (row_ok) {
             st_global_v4(out_row + s * 16, o[0], o[1], o[2], o[3]);
             st_global_v4(out_row + s * 16 + 8, o[4], o[5], o[6], o[7]);
           }
@@ -636,6 +663,54 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld_wait();
           if (s + 2 < s_hi) issue(s + 2, v[0], bv[0], iv[0]);
           process(s + 1, v[1], bv[1], iv[1]);
+        }
+        if (do_ln) {
+          float a0, a1, q0, q1;
+          upk2(s1, a0, a1);
+          upk2(s2, q0, q1);
+          // my partial sums into the PARTNER's buffer, the partner's arrive in mine
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(hb(wg ^ 1) + 1024 + r * 8), "f"(a0 + a1), "f"(q0 + q1) : "memory");
+          named_bar_sync(3, 256);                             // both warpgroups: partial sums and gamma / beta are in place
+          float pa, pq;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pa), "=f"(pq) : "r"(hbuf + 1024 + r * 8));
+          const float mean = (a0 + a1 + pa) * (1.0f / DM);
+          const float var = fmaxf((q0 + q1 + pq) * (1.0f / DM) - mean * mean, 0.0f);
+          const float rstd = rsqrtf(var + p.ln_eps);
+          if (row_ok && wg == 0) {
+            if (p.ln_mean) p.ln_mean[grow] = mean;
+            if (p.ln_rstd) p.ln_rstd[grow] = rstd;
+          }
+          const uint64_t rs2 = pk2(rstd, rstd), nm2 = pk2(-mean * rstd, -mean * rstd);
+          bf16* ln_row = p.ln_out + grow * DM;
+          auto pass2 = [&](int s, const uint32_t (&vv)[16], const float4 (&bb)[4], const uint4 (&ii)[2]) {
+            const uint32_t iw[8] = {ii[0].x, ii[0].y, ii[0].z, ii[0].w, ii[1].x, ii[1].y, ii[1].z, ii[1].w};
+            uint32_t o[8];
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const int cl = (s - s_lo) * 16 + qd * 4;        // column inside this warpgroup's half
+              const float4 g = lds_f4(hbuf + cl * 4), bt = lds_f4(hbuf + 512 + cl * 4);
+              uint64_t x0 = add2(add2(pk2u(vv[4 * qd], vv[4 * qd + 1]), pk2(bb[qd].x, bb[qd].y)), unpack2_bf16(iw[2 * qd]));
+              uint64_t x1 = add2(add2(pk2u(vv[4 * qd + 2], vv[4 * qd + 3]), pk2(bb[qd].z, bb[qd].w)), unpack2_bf16(iw[2 * qd + 1]));
+              x0 = unpack2_bf16(pack2_bf16(x0));              // the normalised value is LN of the bf16 x that was stored
+              x1 = unpack2_bf16(pack2_bf16(x1));
+              o[2 * qd] = pack2_bf16(fma2(fma2(x0, rs2, nm2), pk2(g.x, g.y), pk2(bt.x, bt.y)));
+              o[2 * qd + 1] = pack2_bf16(fma2(fma2(x1, rs2, nm2), pk2(g.z, g.w), pk2(bt.z, bt.w)));
+            }
+            if (row_ok) {
+              st_global_v4(ln_row + s * 16, o[0], o[1], o[2], o[3]);
+              st_global_v4(ln_row + s * 16 + 8, o[4], o[5], o[6], o[7]);
+            }
+          };
+          issue(s_lo, v[0], bv[0], iv[0]);
+#pragma unroll 1
+          for (int s = s_lo; s < s_hi; s += 2) {
+            tmem_ld_wait();
+            issue(s + 1, v[1], bv[1], iv[1]);
+            pass2(s, v[0], bv[0], iv[0]);
+            tmem_ld_wait();
+            if (s + 2 < s_hi) issue(s + 2, v[0], bv[0], iv[0]);
+            pass2(s + 1, v[1], bv[1], iv[1]);
+          }
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&acc2_empty));
@@ -708,11 +783,14 @@ int check_common(const char* name, int64_t M, int D, int R) {
 
 }  // namespace
 
-extern "C" int sc_mlp_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
-                          const void* resid, void* hpre, void* h, void* out, int64_t M, int D, int R, void* stream) {
+static int mlp_fwd_impl(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                        const void* resid, void* hpre, void* h, void* out, const float* ln_gamma, const float* ln_beta,
+                        float ln_eps, void* ln_out, float* ln_mean, float* ln_rstd, int64_t M, int D, int R, void* stream) {
   int rc = sc_check_device();
   if (rc != SC_OK) return rc;
   SC_REQUIRE(x && w1 && w2 && out, SC_E_SHAPE, "sc_mlp_fwd: null operand");
+  SC_REQUIRE(!ln_out || (ln_gamma && ln_beta && !hpre && !h && sc_aligned16(ln_out)), SC_E_SHAPE,
+             "sc_mlp_fwd_ln: needs gamma and beta, a 16-byte aligned ln_out, and the inference form (no hpre / h saves)");
   if ((rc = check_common("sc_mlp_fwd", M, D, R)) != SC_OK) return rc;
   SC_REQUIRE(sc_aligned16(x) && sc_aligned16(w1) && sc_aligned16(w2) && sc_aligned16(resid) && sc_aligned16(hpre) &&
                  sc_aligned16(h) && sc_aligned16(out) && sc_aligned16(b1) && sc_aligned16(b2),
@@ -725,6 +803,8 @@ extern "C" int sc_mlp_fwd(const void* x, const void* w1, const float* b1, const 
   p.hpre = static_cast<bf16*>(hpre);
   p.out = static_cast<bf16*>(out);
   p.store_h = h != nullptr;
+  p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_eps = ln_eps;
+  p.ln_out = static_cast<bf16*>(ln_out); p.ln_mean = ln_mean; p.ln_rstd = ln_rstd;
   p.dbg = g_mlp_dbg;
   p.reverse = sc_take_direction();
   CUtensorMap tmX, tmWa, tmWb, tmH, tmHin, tmResid;
@@ -735,6 +815,20 @@ extern "C" int sc_mlp_fwd(const void* x, const void* w1, const float* b1, const 
   if (h && (rc = sc_encode_tmap_2d_bf16(&tmH, h, (uint64_t)R, (uint64_t)M, (uint64_t)R * 2, 64, BM)) != SC_OK) return rc;
   if (resid && (rc = sc_encode_tmap_2d_bf16(&tmResid, resid, DM, (uint64_t)M, DM * 2, 64, BM)) != SC_OK) return rc;
   return launch_mlp<0>(tmX, tmWa, tmWb, tmH, tmHin, tmResid, p, static_cast<cudaStream_t>(stream), "sc_mlp_fwd");
+}
+
+extern "C" int sc_mlp_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                          const void* resid, void* hpre, void* h, void* out, int64_t M, int D, int R, void* stream) {
+  return mlp_fwd_impl(x, w1, b1, w2, b2, resid, hpre, h, out, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, M, D, R,
+                      stream);
+}
+
+extern "C" int sc_mlp_fwd_ln(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                             const void* resid, void* out, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                             void* ln_out, float* ln_mean, float* ln_rstd, int64_t M, int D, int R, void* stream) {
+  SC_REQUIRE(ln_out, SC_E_SHAPE, "sc_mlp_fwd_ln: ln_out is NULL (use sc_mlp_fwd)");
+  return mlp_fwd_impl(x, w1, b1, w2, b2, resid, nullptr, nullptr, out, ln_gamma, ln_beta, ln_eps, ln_out, ln_mean, ln_rstd,
+                      M, D, R, stream);
 }
 
 extern "C" int sc_mlp_bwd_dgrad(const void* dy, const void* w1, const void* w2, const void* hpre, void* dhpre, void* dx,

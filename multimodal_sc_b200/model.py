@@ -193,6 +193,10 @@ class Engine:
         self.fused_mlp = os.environ.get("SC_FUSED_MLP", "1") != "0"
         # SC_FUSED_LN=0: every LayerNorm forward is its own kernel instead of a GEMM epilogue
         self.fused_ln = os.environ.get("SC_FUSED_LN", "1") != "0"
+        # SC_FUSED_MLP_LN=1: the inference MLP kernel also carries the LayerNorm that follows it (sc_mlp_fwd_ln).  Off:
+        # parity-green but SLOWER — the second pass over the output accumulator sits on the critical path of a single-wave
+        # kernel and costs more than the LayerNorm launch it saves (forward B = 256 0.650 -> 0.660 ms, B = 1024 +6 %)
+        self.fused_mlp_ln = os.environ.get("SC_FUSED_MLP_LN", "0") != "0"
         self.rician_k = spec.rician_k          # K-factor used when channel == "rician" (SemComPolicy.forward may override)
         # SC_WGRAD_STREAM=1: the four weight-gradient GEMMs of every block run on a second stream, so the HBM-bound
         # LayerNorm-backward kernels of the dgrad chain (no shared memory, no TMEM) co-run with them and the tail of
@@ -320,9 +324,11 @@ class Engine:
         xn2 = ln2["y"]
         if not train and self.fused_mlp and D == 256:
             # inference: fc1 -> GELU -> fc2 in one kernel, the hidden activation never leaves the SM
+            # ... and the LayerNorm that consumes the block's output rides on its output epilogue (one launch less per block)
+            ln_fused = next_ln if (next_ln is not None and fuse_ln and self.fused_mlp_ln) else None
             ops.mlp_fwd(xn2, f.w16(f"{pfx}.fc1.weight"), f.w32(f"{pfx}.fc1.bias"), f.w16(f"{pfx}.fc2.weight"),
-                        f.w32(f"{pfx}.fc2.bias"), resid=x1, out=x_out)
-            if next_ln is not None:
+                        f.w32(f"{pfx}.fc2.bias"), resid=x1, out=x_out, ln=ln_fused)
+            if next_ln is not None and ln_fused is None:
                 self._run_ln(x_out, next_ln)
             return
         # training saves both hpre and h: two wide outputs make the fused kernel store-bound, so the forward

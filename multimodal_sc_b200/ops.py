@@ -183,9 +183,10 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, rowadd=None, rowgrp=None, r
 
 
 @_profiled("mlp_fwd")
-def mlp_fwd(x, w1, b1, w2, b2, *, resid=None, hpre=None, h=None, out=None):
+def mlp_fwd(x, w1, b1, w2, b2, *, resid=None, hpre=None, h=None, out=None, ln=None):
     """out = resid + gelu(x w1^T + b1) w2^T + b2 in one kernel (sc_mlp_fwd).  x [M,256], w1 [R,256], w2 [256,R] bf16;
-    hpre / h (bf16 [M,R]) are written when given (training)."""
+    hpre / h (bf16 [M,R]) are written when given (training).  ln (dict gamma / beta / eps / y [/ mean / rstd], inference
+    form only): y = LayerNorm(out) is written by the same kernel (sc_mlp_fwd_ln)."""
     _cuda(x, w1, w2)
     M, D = x.shape
     R = w1.shape[0]
@@ -196,6 +197,17 @@ def mlp_fwd(x, w1, b1, w2, b2, *, resid=None, hpre=None, h=None, out=None):
     for t, shp in ((resid, (M, D)), (out, (M, D)), (hpre, (M, R)), (h, (M, R))):
         if t is not None:
             assert t.dtype == BF16 and t.shape == shp and t.is_contiguous()
+    if ln is not None:
+        assert hpre is None and h is None, "the fused LayerNorm exists for the inference form only"
+        y = ln["y"]
+        assert y.dtype == BF16 and y.shape == (M, D) and y.is_contiguous() and ln["gamma"].dtype == F32 and ln["beta"].dtype == F32
+        for t in (ln.get("mean"), ln.get("rstd")):
+            assert t is None or (t.dtype == F32 and t.numel() == M and t.is_contiguous())
+        rc = _lib.load().sc_mlp_fwd_ln(ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(resid), ptr(out), ptr(ln["gamma"]),
+                                       ptr(ln["beta"]), float(ln["eps"]), ptr(y), ptr(ln.get("mean")), ptr(ln.get("rstd")),
+                                       M, D, R, stream_ptr(x))
+        check(rc, "sc_mlp_fwd_ln")
+        return out
     rc = _lib.load().sc_mlp_fwd(ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(resid), ptr(hpre), ptr(h), ptr(out),
                                 M, D, R, stream_ptr(x))
     check(rc, "sc_mlp_fwd")

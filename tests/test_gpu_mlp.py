@@ -159,3 +159,47 @@ def test_gemm_fused_layernorm_epilogue(cuda_lib, M, K, mode):
     # and against the fp32 definition
     y32 = F.layer_norm(o_ref.float(), (256,), gamma, beta, 1e-5)
     assert _rel(y, y32) < 1e-2
+
+
+@pytest.mark.parametrize("M,with_resid", [(1, True), (128, True), (200, False), (4096 + 37, True), (148 * 128 * 2 + 5, True)])
+def test_mlp_fwd_with_fused_layernorm_equals_mlp_then_layernorm(cuda_lib, M, with_resid):
+    """sc_mlp_fwd_ln (inference form): `out` is bit-identical to sc_mlp_fwd's, and ln_out / mean / rstd equal
+    sc_layernorm_fwd applied to that stored bf16 `out` (same statistics of the rounded values; summation order differs:
+    fp32 1e-5 on mean / rstd, one bf16 ulp on y) — and the torch fp32 LayerNorm of `out` within the bf16 bar"""
+    from multimodal_sc_b200 import ops
+    R = 1024
+    x, w1, b1, w2, b2, resid = _mk(M, R, seed=M + 1)
+    resid = resid if with_resid else None
+    g = torch.Generator(device="cuda").manual_seed(7)
+    gamma = 1.0 + 0.3 * torch.randn(256, generator=g, device="cuda")
+    beta = 0.2 * torch.randn(256, generator=g, device="cuda")
+    out0 = ops.mlp_fwd(x, w1, b1, w2, b2, resid=resid)
+    mean0, rstd0 = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    y0 = ops.layernorm_fwd(out0, gamma, beta, 1e-5, mean=mean0, rstd=rstd0)
+    out1 = torch.full((M, 256), float("nan"), device="cuda", dtype=BF16)
+    ln = {"gamma": gamma, "beta": beta, "eps": 1e-5, "y": torch.full((M, 256), float("nan"), device="cuda", dtype=BF16),
+          "mean": torch.full((M,), float("nan"), device="cuda"), "rstd": torch.full((M,), float("nan"), device="cuda")}
+    for _ in range(2):                                        # twice: the scratch the kernel borrows must be clean again
+        ops.mlp_fwd(x, w1, b1, w2, b2, resid=resid, out=out1, ln=ln)
+    torch.cuda.synchronize()
+    assert torch.equal(out0.view(torch.int16), out1.view(torch.int16))
+    assert torch.allclose(ln["mean"], mean0, rtol=1e-5, atol=1e-6) and torch.allclose(ln["rstd"], rstd0, rtol=1e-5, atol=1e-6)
+    d = (ln["y"].float() - y0.float()).abs()
+    assert float(d.max()) <= 2.0 ** -7 * float(y0.float().abs().max()), float(d.max())
+    assert float((d > 0).float().mean()) < 0.02                # the two agree to the last bit almost everywhere
+    ref = F.layer_norm(out0.float(), (256,), gamma, beta, 1e-5)
+    assert _rel(ln["y"], ref) < 1e-2
+
+
+def test_mlp_fwd_ln_rejects_the_training_form(cuda_lib):
+    from multimodal_sc_b200 import _lib, ops
+    x, w1, b1, w2, b2, resid = _mk(128, 1024, seed=3)
+    ln = {"gamma": torch.ones(256, device="cuda"), "beta": torch.zeros(256, device="cuda"), "eps": 1e-5,
+          "y": torch.empty(128, 256, device="cuda", dtype=BF16)}
+    with pytest.raises(AssertionError):
+        ops.mlp_fwd(x, w1, b1, w2, b2, resid=resid, hpre=torch.empty(128, 1024, device="cuda", dtype=BF16), ln=ln)
+    lib = _lib.load()
+    rc = lib.sc_mlp_fwd_ln(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), None, x.data_ptr(),
+                           None, None, 1e-5, ln["y"].data_ptr(), None, None, 128, 256, 1024, 0)
+    assert rc == -1 and "gamma" in _lib.last_error()
+
