@@ -10,6 +10,7 @@ path.  The NCCL all-reduce + sc_adam_flat schedule stays available (`PPOAgent(fu
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -117,22 +118,43 @@ class PeerReduceAdam:
         self.flags = peer_empty(_lib.SC_DP_MAX_WORLD, torch.int64, self.device)
         self.epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
         local = {"g32": flat.g32, "p32": flat.p32, "p16": flat.p16, "flags": self.flags}
-        mine = {k: export_handle(t) for k, t in local.items()}
+        # Every rank takes part in every collective below even when its own export / import fails: the failure is agreed on
+        # afterwards (one all-reduce) and raised on ALL ranks, so a caller may fall back to the NCCL schedule collectively.
+        err = None
+        try:
+            mine = {k: export_handle(t) for k, t in local.items()}
+        except _lib.SemcomError as e:
+            err, mine = e, {}
         mine["numel"] = int(flat.numel)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=pg)
         self._imported = []
         ptrs = {k: [] for k in local}
         for r, hs in enumerate(everyone):
-            if hs["numel"] != flat.numel:
-                raise _lib.SemcomError(f"rank {r} holds {hs['numel']} flat parameters, this rank {flat.numel}")
-            for k, t in local.items():
-                if r == self.rank:
-                    ptrs[k].append(t.data_ptr())
-                else:
-                    p = import_handle(hs[k], self.device)
-                    self._imported.append(p)
-                    ptrs[k].append(p)
+            if err is not None:
+                break
+            try:
+                if hs["numel"] != flat.numel:
+                    raise _lib.SemcomError(f"rank {r} holds {hs['numel']} flat parameters, this rank {flat.numel}")
+                for k, t in local.items():
+                    if r == self.rank:
+                        ptrs[k].append(t.data_ptr())
+                    else:
+                        if k not in hs:
+                            raise _lib.SemcomError(f"rank {r} could not export its buffers")
+                        if os.environ.get("SC_PEER_TEST_FAIL_IMPORT") == str(self.rank):   # test hook: this rank cannot map
+                            raise _lib.SemcomError("import refused (SC_PEER_TEST_FAIL_IMPORT)")
+                        p = import_handle(hs[k], self.device)
+                        self._imported.append(p)
+                        ptrs[k].append(p)
+            except _lib.SemcomError as e:
+                err = e
+        failed = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(failed, group=pg)
+        if int(failed.item()) > 0:
+            self.close()
+            raise _lib.SemcomError(f"peer-memory mapping failed on {int(failed.item())} of {self.world} ranks"
+                                   + (f" (this rank: {err})" if err is not None else ""))
         self._g, self._p32, self._p16, self._fl = (_ptr_array(ptrs[k]) for k in ("g32", "p32", "p16", "flags"))
         n4 = flat.numel // 4
         base, rem = divmod(n4, self.world)

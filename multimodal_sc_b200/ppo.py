@@ -93,14 +93,25 @@ class PPOAgent:
         self.overlap_allreduce = os.environ.get("SC_DP_OVERLAP", "0") != "0"
         # data parallel: gradient exchange fused with the optimizer over peer memory (default whenever the policy's flat
         # buckets are in peer memory, i.e. it was built under an initialised NCCL process group); construction is a collective
-        if fused_dp is None:
+        auto = fused_dp is None
+        if auto:
             fused_dp = self.world > 1 and policy.flat.peer and not self.overlap_allreduce
         self._fused = None
         if fused_dp and self.world > 1:
             from .peer import PeerReduceAdam
             cache = policy.flat.__dict__.setdefault("_peer_reducers", {})    # one mapping per (buckets, group): a second
             if id(process_group) not in cache:                               # agent on the same policy reuses it
-                cache[id(process_group)] = PeerReduceAdam(policy.flat, process_group)
+                try:
+                    cache[id(process_group)] = PeerReduceAdam(policy.flat, process_group)
+                except _lib.SemcomError as e:
+                    # raised on every rank together (the ranks agree on the failure): GPUs without peer access / IPC.
+                    # An explicit fused_dp=True propagates; the default takes the library's other schedule (NCCL all-reduce
+                    # + sc_adam_flat, both on the GPU) and says so.
+                    if not auto:
+                        raise
+                    import warnings
+                    warnings.warn(f"peer-memory optimizer step unavailable, using the NCCL all-reduce schedule: {e}")
+                    cache[id(process_group)] = None
             self._fused = cache[id(process_group)]
         self._lsem_weight = 1.0 / self.world                     # this rank's share of the global-minibatch mean L_sem
         self.last_perms = []                                     # permutations / per-minibatch statistics of the last
