@@ -465,6 +465,10 @@ def run_native(a):
                        "params": pol.flat.n_params(), "parallelism": f"dp{world}",
                        "schedule": "eager launches" if a.eager else "CUDA-graph replay of the whole step (PPOAgent.minibatch_step(graph='inplace'))",
                        "observations": "bf16 (fp32 U[0,1) cast once on the host before timing)",
+                       "gradient_exchange": (None if world == 1 else
+                                             ("sc_dp_barrier + sc_dp_reduce_adam + sc_dp_barrier over NVLink peer memory (reduce-scatter, "
+                                              "sharded Adam, parameter all-gather)" if ag._fused is not None else
+                                              "NCCL all-reduce of the flat fp32 bucket + sc_adam_flat")),
                        "l2_policy": "inputs larger than L2 (2 x 436 MB bf16 observation sets alternate; ~16 GB of "
                                     "activations stream per step)"},
             "model_tflops": flops_step / (ms_total / a.steps * 1e-3) / 1e12,
