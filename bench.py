@@ -365,10 +365,17 @@ def run_native(a):
     upd = None
     if not a.no_update:
         phase("update_e2e")
-        T_ro, n_env = sp.rollout_t, max(2 * B // sp.rollout_t, 1)
-        ro = synthetic.rollout(sp, T_ro, n_env, seed=300 + rank)
-        ro["cam"], ro["bev"] = ro["cam"].bfloat16(), ro["bev"].bfloat16()
-        ro = {k: v.pin_memory() for k, v in ro.items()}
+        # a rollout of `--update-steps` (default 4) global minibatches per GPU, built in chunks of <= 64 environments so that
+        # the fp32 staging of the synthetic observations stays below 1.7 GB per rank
+        T_ro, n_env = sp.rollout_t, max(a.update_steps * B // sp.rollout_t, 1)
+        parts = []
+        for c0 in range(0, n_env, 64):
+            part = synthetic.rollout(sp, T_ro, min(64, n_env - c0), seed=300 + 16 * rank + c0 // 64)
+            part["cam"], part["bev"] = part["cam"].bfloat16(), part["bev"].bfloat16()
+            parts.append(part)
+        ro = {k: torch.cat([p_[k] for p_ in parts], dim=0 if k == "last_value" else 1).contiguous().pin_memory()
+              for k in parts[0]}
+        del parts
         agu = PPOAgent(pol, sp, minibatch=B * world, epochs=1, snr_db=SNR_DB, channel="awgn", seed=4321,
                        process_group=None)
         agu.update(ro)                                          # warm-up (allocates the capacity arena on N > 1)
@@ -379,8 +386,9 @@ def run_native(a):
                "rollout": f"T={T_ro} x N={n_env} envs per GPU (bf16 observations, pinned host)",
                "minibatch_steps_per_update": (n_samples // (B * world)),
                "h2d_bytes_per_update": sum(v.numel() * v.element_size() for v in ro.values()),
-               "includes": "H2D of the rollout, sc_gae + sc_adv_normalize, host randperm, gather fused into sc_patchify_bf16 / "
-                           "sc_ppo_loss, all minibatch steps, D2H of the statistics"}
+               "includes": "H2D of the rollout (observation rows streamed per minibatch by sc_gather_rows, one step ahead), sc_gae + "
+                           "sc_adv_normalize, host randperm, gather of the per-sample vectors fused into sc_ppo_loss, all minibatch "
+                           "steps, one D2H of the statistics"}
         del ro
     if world > 1:
         dist.barrier()
@@ -512,6 +520,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg1 / cfg2 / cfg4 measurements")
     ap.add_argument("--no-update", action="store_true", help="skip the update_e2e measurement")
+    ap.add_argument("--update-steps", type=int, default=4,
+                    help="optimizer steps (global minibatches) per update() in the update_e2e measurement")
     ap.add_argument("--eager", action="store_true",
                     help="A/B: launch the step's kernels one by one instead of replaying the captured CUDA graph "
                          "(PPOAgent.minibatch_step(graph=\"inplace\"), the default: +2.5 %% at 1 GPU, +0.7 %% at 2)")
