@@ -190,3 +190,37 @@ def test_policy_in_peer_memory_trains_like_the_default_one(cuda_lib):
     for a, b in zip(out[0][1], out[1][1]):
         for k in a:
             assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+
+
+def test_peer_reduce_adam_class_with_a_one_rank_group(cuda_lib, tmp_path):
+    """peer.PeerReduceAdam end to end in this process: handle export, the collective construction (one-rank gloo group),
+    step() == sc_adam_flat bit for bit over the model's real flat bucket, gather_moments(), close()"""
+    import torch.distributed as dist
+    from multimodal_sc_b200 import ops
+    from multimodal_sc_b200.model import FlatParams
+    from multimodal_sc_b200.peer import PeerReduceAdam
+    from multimodal_sc_b200.spec import SpecV0
+    sp = SpecV0()
+    assert not dist.is_initialized()
+    dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        flat = FlatParams(sp, torch.device("cuda", 0), peer=True)
+        g = torch.Generator(device="cuda").manual_seed(9)
+        flat.p32.copy_(torch.randn(flat.numel, generator=g, device="cuda") * 0.05)
+        flat.sync_shadow()
+        red = PeerReduceAdam(flat)
+        assert (red.lo, red.hi) == (0, flat.numel) and red.world == 1
+        rp, rm, rv, rb = flat.p32.clone(), torch.zeros_like(flat.m), torch.zeros_like(flat.v), flat.p16.clone()
+        for step in (1, 2, 3):
+            flat.g32.copy_(torch.randn(flat.numel, generator=g, device="cuda") * 1e-3)
+            red.step(sp.lr, sp.beta1, sp.beta2, sp.adam_eps, step)
+            ops.adam_flat(rp, flat.g32, rm, rv, rb, sp.lr, sp.beta1, sp.beta2, sp.adam_eps, step)
+            torch.cuda.synchronize()
+            assert torch.equal(flat.p32, rp) and torch.equal(flat.p16.view(torch.int16), rb.view(torch.int16))
+            assert torch.equal(flat.m, rm) and torch.equal(flat.v, rv)
+        assert int(red.epoch) == 6
+        red.gather_moments()
+        red.close()
+    finally:
+        dist.destroy_process_group()
+
