@@ -39,7 +39,11 @@ out = {"world": world, "T": T, "N": N, "global_minibatch": MB, "epochs": EPOCHS,
 for channel in ("awgn", "rayleigh"):
     pol_dp = SemComPolicy(sp, device=dev, seed=0)
     ag_dp = PPOAgent(pol_dp, sp, minibatch=MB, epochs=EPOCHS, seed=7, channel=channel, snr_db=5.0)
-    st_dp = ag_dp.update(local_ro)
+    # the Rayleigh pass feeds the data-parallel update from PINNED host memory: observation rows are then streamed per minibatch
+    # (sc_gather_rows, one step ahead) instead of copied up front — same result expected
+    pinned = channel == "rayleigh"
+    st_dp = ag_dp.update({k: v.pin_memory() for k, v in local_ro.items()} if pinned else local_ro)
+    assert (getattr(ag_dp, "_obs_stream", None) is not None) == pinned
     pol_1 = SemComPolicy(sp, device=dev, seed=0)
     ag_1 = PPOAgent(pol_1, sp, minibatch=MB, epochs=EPOCHS, seed=7, channel=channel, snr_db=5.0, process_group=solo)
     assert ag_1.world == 1 and ag_dp.world == world
@@ -58,7 +62,8 @@ for channel in ("awgn", "rayleigh"):
     chk = pol_dp.flat.p32.double().sum().reshape(1)
     both = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(both, chk)
-    res = {"perms_equal": bool(perms_equal), "steps": len(ag_dp.last_step_stats),
+    res = {"perms_equal": bool(perms_equal), "steps": len(ag_dp.last_step_stats), "dp_rollout_in_pinned_host_memory": pinned,
+           "dp_optimizer_step": "peer memory" if ag_dp._fused is not None else "nccl",
            "first_step_rel_stat_diff": first, "worst_rel_stat_diff": worst, "update_mean_stats_dp": st_dp, "update_mean_stats_1rank": st_1,
            "param_max_abs_diff": float(dpar.max()), "param_frac_diff_gt_0.02lr": float((dpar > 0.02 * sp.lr).float().mean()),
            "lr": sp.lr, "ranks_hold_identical_params": bool(all(float(b) == float(both[0]) for b in both))}
