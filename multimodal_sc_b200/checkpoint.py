@@ -26,7 +26,10 @@ def to_state(agent) -> dict:
     model = {k: v.detach().to("cpu", torch.float32).clone() for k, v in pol.state_dict().items()}
     if _is_native(agent):
         flat = pol.flat
-        if getattr(agent, "_fused", None) is not None:           # sharded optimizer state: complete it first (collective)
+        # data parallel with the peer-memory optimizer step: every rank maintains the Adam moments of its own slice only, so
+        # they are completed first — a COLLECTIVE: every rank of the group must call to_state() / save() (any of them may
+        # then write the file; the result is identical on all ranks)
+        if getattr(agent, "_fused", None) is not None:
             agent._fused.gather_moments()
         m = {n: flat._view(flat.m, n).detach().to("cpu").clone() for n in flat.shapes}
         v = {n: flat._view(flat.v, n).detach().to("cpu").clone() for n in flat.shapes}
